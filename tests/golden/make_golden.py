@@ -1,0 +1,194 @@
+#!/usr/bin/env python
+"""
+Generate the golden vectors by running the UNMODIFIED reference (``/root/reference``) on every case of
+``cases.py``.  Runs only in the build container (the GPU box has no /root/reference); its outputs
+(``<case>.npz``, ``parser_kats.json``) are committed so that the tests never need the reference.
+
+    python tests/golden/make_golden.py [case ...]          # all cases when none is named
+    python tests/golden/make_golden.py --openfoam-fixture  # (re)build the 444-PFR network fixture first
+
+Harness-side work-arounds for reference defects; the reference files are untouched:
+ 1. ``pyparsing`` is not installed -> alias pip's vendored copy before importing ``reactions.py``.
+ 2. ``reactions.py:214`` sets ``np.seterr(all='raise')`` globally -> reset inside the ``solve_ivp`` wrapper.
+ 3. scipy BDF/Radau pass non-contiguous ``y`` -> ``np.ascontiguousarray`` in the wrapper.
+"""
+from __future__ import annotations
+
+import json
+import os
+import pickle
+import shutil
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+sys.path.insert(0, HERE)
+
+try:
+    import pyparsing  # noqa: F401
+except ModuleNotFoundError:
+    import pip._vendor.pyparsing as _pp
+    sys.modules['pyparsing'] = _pp
+sys.path.insert(0, '/root/reference')
+
+import numpy as np
+import scipy.integrate
+
+import cases as C  # noqa: E402
+
+from openccm import ConfigParser  # noqa: E402  (the reference)
+from openccm.mesh import GroupedBCs  # noqa: E402
+import openccm.system_solvers.cstr_system as ref_cstr  # noqa: E402
+import openccm.system_solvers.pfr_system as ref_pfr  # noqa: E402
+from openccm.system_solvers import solve_system as ref_solve_system  # noqa: E402
+from openccm.system_solvers.reactions import parse_reactions  # noqa: E402
+from openccm.postprocessing.analysis import network_to_rtd  # noqa: E402
+
+CAPTURE = {}
+
+
+def _patched_solve_ivp(fun, t_span, y0, **kw):
+    np.seterr(all='warn', under='ignore')
+    args = kw.pop('args', ())
+    f = lambda t, y: fun(t, np.ascontiguousarray(y), *args)
+    res = scipy.integrate.solve_ivp(f, t_span, y0, **kw)
+    CAPTURE.update(fun=fun, args=args, y0=np.array(y0, copy=True), res=res)
+    return res
+
+
+ref_cstr.solve_ivp = _patched_solve_ivp
+ref_pfr.solve_ivp = _patched_solve_ivp
+
+
+def run_reference(name: str, solver: str, t_eval_override=None, workdir=None):
+    case = C.CASES[name]
+    net = case['net']()
+    os.makedirs('cache', exist_ok=True)
+    if case['rxn']:
+        with open('reactions', 'w') as fh:
+            fh.write(C.RXN[case['rxn']])
+    with open('CONFIG', 'w') as fh:
+        fh.write(C.config_text(name, solver, 'reactions'))
+    cp = ConfigParser('CONFIG')
+    cp['SETUP']['tmp_folder_path'] = 'cache/'
+    cp.need_to_update_paths = False
+    if t_eval_override is not None:
+        cp['SIMULATION']['t_eval'] = t_eval_override
+    gb = GroupedBCs(cp)
+    cmesh = C.make_cmesh(name, net, gb)
+    model_network = net.to_model_network()
+    c, t, inlet_map, outlet_map = ref_solve_system(case['model'], model_network, cp, cmesh)
+    return dict(c=c, t=t, inlet_map=inlet_map, outlet_map=outlet_map, cp=cp, cmesh=cmesh, net=model_network,
+                capture=dict(CAPTURE))
+
+
+def golden_for(name: str) -> None:
+    case = C.CASES[name]
+    solvers = case.get('solvers', ('RK45', 'LSODA'))
+    out = {}
+    old = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix=f'golden_{name}_')
+    os.chdir(tmp)
+    try:
+        for solver in solvers:
+            r = run_reference(name, solver)
+            res = r['capture']['res']
+            out[f'c_{solver}'] = r['c']
+            out[f't_{solver}'] = r['t']
+            out[f'nfev_{solver}'] = np.int64(res.nfev)
+            if case['rtd']:
+                out[f'rtd_{solver}'] = network_to_rtd((r['c'], r['t'], r['inlet_map'], r['outlet_map']),
+                                                      r['cmesh'], r['cp'], r['net'])
+        # raw RHS evaluations at random states (inner boundary)
+        cap = r['capture']
+        rng = np.random.default_rng(C.hash_name(name) + 1)
+        y0 = cap['y0']
+        t0, tf = [float(v) for v in case['t_span'].split(', ')]
+        n_states = 6
+        ys = np.empty((n_states, y0.size)); ts = np.empty(n_states); dys = np.empty((n_states, y0.size))
+        for k in range(n_states):
+            ys[k] = y0 if k == 0 else np.abs(y0 + rng.normal(0.0, 0.5, y0.size))
+            ts[k] = t0 if k == 0 else rng.uniform(t0, min(tf, t0 + 2.0))
+            if k == 1:
+                ts[k] = t0 + 0.0005   # inside the smoothed-Heaviside ramp of H(10*t)
+            np.seterr(all='warn', under='ignore')
+            dys[k] = cap['fun'](ts[k], ys[k].copy(), *cap['args'])
+        out.update(c0=y0, ddt_y=ys, ddt_t=ts, ddt_out=dys)
+        # step-exactness data: RK45 with t_eval = all (the solver's own steps)
+        if 'RK45' in solvers and name in ('cstr_irreversible', 'cstr_net12_nacl', 'pfr_net8', 'cstr_net20_timebc'):
+            r = run_reference(name, 'RK45', t_eval_override='all')
+            out['c_RK45_all'] = r['c']; out['t_RK45_all'] = r['t']
+            out['nfev_RK45_all'] = np.int64(r['capture']['res'].nfev)
+    finally:
+        os.chdir(old)
+        shutil.rmtree(tmp, ignore_errors=True)
+    np.savez_compressed(os.path.join(HERE, f'{name}.npz'), **out)
+    print(f'[golden] {name}: ' + ', '.join(f'{k}{tuple(np.shape(v))}' for k, v in out.items()))
+
+
+def parser_kats() -> None:
+    """Reaction-parser known answers: the per-species rate strings of reactions.py:270-392 and their
+    sympy-simplified form (reactions.py:421,451)."""
+    import configparser
+    import sympy as sp
+    kats = {}
+    for key, text in C.RXN.items():
+        p = configparser.ConfigParser(); p.optionxform = str; p.read_string(text)
+        raw = parse_reactions(dict(p['REACTIONS']), dict(p['RATE CONSTANTS']))
+        kats[key] = {'raw': raw, 'sympy': {k: str(sp.parse_expr(v)) for k, v in raw.items()}}
+    with open(os.path.join(HERE, 'parser_kats.json'), 'w') as fh:
+        json.dump(kats, fh, indent=1, sort_keys=True)
+    print('[golden] parser_kats.json')
+
+
+def openfoam_fixture() -> None:
+    """Run the reference's own pipeline on examples/OpenFOAM/pipe_with_recirc (a writable copy) and freeze the
+    444-PFR model network + element geometry as a fixture (inputs only)."""
+    import openccm
+    tmp = tempfile.mkdtemp(prefix='golden_openfoam_')
+    dst = os.path.join(tmp, 'case')
+    shutil.copytree('/root/reference/examples/OpenFOAM/pipe_with_recirc', dst)
+    old = os.getcwd(); os.chdir(dst)
+    try:
+        cp = ConfigParser('CONFIG')
+        cp['SIMULATION']['run'] = 'False'
+        cp['POST-PROCESSING']['calculate_rtd'] = 'False'
+        openccm.run(cp)
+        with open('cache/pfr_network.pickle', 'rb') as fh:
+            network = pickle.load(fh)
+        with open('cache/cmesh.pickle', 'rb') as fh:
+            cmesh = pickle.load(fh)
+    finally:
+        os.chdir(old)
+    from openccm_b200.network import NetworkArrays
+    na = NetworkArrays.from_model_network(network)
+    d = {k: getattr(na, k) for k in ('n_models', 'volumes', 'flows', 'in_model', 'in_conn', 'in_other',
+                                     'out_model', 'out_conn', 'out_other')}
+    d['model_to_element_map'] = [[(float(a), int(b)) for a, b in m] for m in na.model_to_element_map]
+    with open(os.path.join(HERE, 'openfoam_2d_pfr_network.pickle'), 'wb') as fh:
+        pickle.dump(d, fh, protocol=4)
+    np.savez_compressed(os.path.join(HERE, 'openfoam_2d_pfr_geometry.npz'),
+                        centroids=np.asarray(cmesh.element_centroids), sizes=np.asarray(cmesh.element_sizes))
+    print(f'[golden] openfoam fixture: {na.n_models} PFRs, {na.flows.size} connections, '
+          f'{len(cmesh.element_sizes)} elements; bc ids inlet={cmesh.grouped_bcs.id("inlet")} '
+          f'outlet={cmesh.grouped_bcs.id("outlet")}')
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
+if __name__ == '__main__':
+    argv = sys.argv[1:]
+    if '--openfoam-fixture' in argv:
+        argv.remove('--openfoam-fixture')
+        openfoam_fixture()
+    if '--kats' in argv:
+        argv.remove('--kats')
+        parser_kats()
+        if not argv:
+            sys.exit(0)
+    names = argv or list(C.CASES)
+    if not argv:
+        parser_kats()
+    for n in names:
+        golden_for(n)

@@ -1,0 +1,254 @@
+// Device-side building blocks shared by the RHS, RK45 and BDF kernels (sm_100a).
+//
+// Thread mapping used everywhere: one thread per flat state element e = point * S + species of one ensemble
+// member, consecutive threads = consecutive addresses (species innermost), so every own-element load/store of
+// y, K_i, ... is a fully coalesced 8-byte-per-lane access.  A CTA works on a "chunk" = OCCM_BLOCK consecutive
+// elements of one member; the stage state of the points the chunk touches is staged in shared memory so that
+// the reaction terms (which couple the S species of a point) and the PFR upwind difference read it from there.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "occm_tables.h"
+
+#define OCCM_BLOCK 256
+#define OCCM_MAX_S 64
+
+struct OccmSysDev {
+    int model, S, n_models, P;
+    long long n_points, ndof;
+    const int* row_ptr; const int* row_src; const double* row_w; const double* a;
+    const int* pulse_ptr; const int* pulse_fn; const double* pulse_w;
+    const int* tables; int tables_bytes;
+    const double* fields; int n_fields;
+    int n_rxn;
+    int chunks_per_member;
+};
+
+struct OccmMemDev {
+    int M;
+    const double* k_scale; const double* q_scale; const double* bc_scale;
+};
+
+// Views into the shared-memory copy of the table blob.
+struct OccmTab {
+    int S, n_rxn, n_bc;
+    const int* term_ptr; const double* term_coeff; const int* term_rxn; const int* term_prog;
+    const int* fac_ptr; const int* fac_sp; const int* fac_ord;
+    const int* prog_ptr; const int* code; const double* consts; const int* bc_prog;
+};
+
+// Stage the blob into shared memory (all threads) and build the views. `smem` must be 8-byte aligned.
+__device__ __forceinline__ OccmTab occm_load_tables(const int* __restrict__ blob, int bytes, int* smem) {
+    const int words = bytes >> 2;
+    for (int i = threadIdx.x; i < words; i += blockDim.x) smem[i] = __ldg(blob + i);
+    __syncthreads();
+    OccmTab T;
+    const char* base = reinterpret_cast<const char*>(smem);
+    T.S = smem[OCCM_H_S]; T.n_rxn = smem[OCCM_H_NRXN]; T.n_bc = smem[OCCM_H_NBC];
+    T.term_ptr   = reinterpret_cast<const int*>(base + smem[OCCM_H_OFF_TERM_PTR]);
+    T.term_coeff = reinterpret_cast<const double*>(base + smem[OCCM_H_OFF_TERM_COEFF]);
+    T.term_rxn   = reinterpret_cast<const int*>(base + smem[OCCM_H_OFF_TERM_RXN]);
+    T.term_prog  = reinterpret_cast<const int*>(base + smem[OCCM_H_OFF_TERM_PROG]);
+    T.fac_ptr    = reinterpret_cast<const int*>(base + smem[OCCM_H_OFF_FAC_PTR]);
+    T.fac_sp     = reinterpret_cast<const int*>(base + smem[OCCM_H_OFF_FAC_SP]);
+    T.fac_ord    = reinterpret_cast<const int*>(base + smem[OCCM_H_OFF_FAC_ORD]);
+    T.prog_ptr   = reinterpret_cast<const int*>(base + smem[OCCM_H_OFF_PROG_PTR]);
+    T.code       = reinterpret_cast<const int*>(base + smem[OCCM_H_OFF_CODE]);
+    T.consts     = reinterpret_cast<const double*>(base + smem[OCCM_H_OFF_CONST]);
+    T.bc_prog    = reinterpret_cast<const int*>(base + smem[OCCM_H_OFF_BC_PROG]);
+    return T;
+}
+
+__device__ __forceinline__ double occm_powi(double x, int n) {
+    bool neg = n < 0;
+    unsigned un = neg ? (unsigned)(-n) : (unsigned)n;
+    double r = 1.0, b = x;
+    while (un) { if (un & 1u) r *= b; b *= b; un >>= 1; }
+    return neg ? 1.0 / r : r;
+}
+
+// Postfix evaluator. `row(sp)` returns the concentration of species sp at the current point.
+template <class Row>
+__device__ __noinline__ double occm_vm_eval(const OccmTab& T, int prog, const Row& row, double t, long long point,
+                                            const double* __restrict__ fields, long long n_points) {
+    double st[OCCM_VM_STACK];
+    int sp = 0;
+    const int beg = T.prog_ptr[prog], end = T.prog_ptr[prog + 1];
+    for (int pc = beg; pc < end; ++pc) {
+        const int ins = T.code[pc];
+        const int op = ins & 0xff, arg = ins >> 8;
+        switch (op) {
+            case OCCM_OP_CONST:   st[sp++] = T.consts[arg]; break;
+            case OCCM_OP_SPECIES: st[sp++] = row(arg); break;
+            case OCCM_OP_TIME:    st[sp++] = t; break;
+            case OCCM_OP_FIELD:   st[sp++] = fields ? fields[(long long)arg * n_points + point] : 0.0; break;
+            case OCCM_OP_ADD: --sp; st[sp - 1] = st[sp - 1] + st[sp]; break;
+            case OCCM_OP_SUB: --sp; st[sp - 1] = st[sp - 1] - st[sp]; break;
+            case OCCM_OP_MUL: --sp; st[sp - 1] = st[sp - 1] * st[sp]; break;
+            case OCCM_OP_DIV: --sp; st[sp - 1] = st[sp - 1] / st[sp]; break;
+            case OCCM_OP_POW: --sp; st[sp - 1] = pow(st[sp - 1], st[sp]); break;
+            case OCCM_OP_NEG: st[sp - 1] = -st[sp - 1]; break;
+            case OCCM_OP_POWI: st[sp - 1] = occm_powi(st[sp - 1], arg - OCCM_POWI_BIAS); break;
+            case OCCM_OP_SIN:  st[sp - 1] = sin(st[sp - 1]); break;
+            case OCCM_OP_COS:  st[sp - 1] = cos(st[sp - 1]); break;
+            case OCCM_OP_TAN:  st[sp - 1] = tan(st[sp - 1]); break;
+            case OCCM_OP_EXP:  st[sp - 1] = exp(st[sp - 1]); break;
+            case OCCM_OP_LOG:  st[sp - 1] = log(st[sp - 1]); break;
+            case OCCM_OP_SQRT: st[sp - 1] = sqrt(st[sp - 1]); break;
+            case OCCM_OP_ABS:  st[sp - 1] = fabs(st[sp - 1]); break;
+            case OCCM_OP_TANH: st[sp - 1] = tanh(st[sp - 1]); break;
+            case OCCM_OP_SINH: st[sp - 1] = sinh(st[sp - 1]); break;
+            case OCCM_OP_COSH: st[sp - 1] = cosh(st[sp - 1]); break;
+            case OCCM_OP_ASIN: st[sp - 1] = asin(st[sp - 1]); break;
+            case OCCM_OP_ACOS: st[sp - 1] = acos(st[sp - 1]); break;
+            case OCCM_OP_ATAN: st[sp - 1] = atan(st[sp - 1]); break;
+            case OCCM_OP_SIGN: st[sp - 1] = (st[sp - 1] > 0.0) - (st[sp - 1] < 0.0); break;
+            case OCCM_OP_FLOOR: st[sp - 1] = floor(st[sp - 1]); break;
+            case OCCM_OP_CEIL:  st[sp - 1] = ceil(st[sp - 1]); break;
+            case OCCM_OP_MIN: --sp; st[sp - 1] = fmin(st[sp - 1], st[sp]); break;
+            case OCCM_OP_MAX: --sp; st[sp - 1] = fmax(st[sp - 1], st[sp]); break;
+            case OCCM_OP_LT: --sp; st[sp - 1] = st[sp - 1] <  st[sp] ? 1.0 : 0.0; break;
+            case OCCM_OP_LE: --sp; st[sp - 1] = st[sp - 1] <= st[sp] ? 1.0 : 0.0; break;
+            case OCCM_OP_GT: --sp; st[sp - 1] = st[sp - 1] >  st[sp] ? 1.0 : 0.0; break;
+            case OCCM_OP_GE: --sp; st[sp - 1] = st[sp - 1] >= st[sp] ? 1.0 : 0.0; break;
+            case OCCM_OP_EQ: --sp; st[sp - 1] = st[sp - 1] == st[sp] ? 1.0 : 0.0; break;
+            case OCCM_OP_NE: --sp; st[sp - 1] = st[sp - 1] != st[sp] ? 1.0 : 0.0; break;
+            case OCCM_OP_AND: --sp; st[sp - 1] = (st[sp - 1] != 0.0 && st[sp] != 0.0) ? 1.0 : 0.0; break;
+            case OCCM_OP_OR:  --sp; st[sp - 1] = (st[sp - 1] != 0.0 || st[sp] != 0.0) ? 1.0 : 0.0; break;
+            case OCCM_OP_NOT: st[sp - 1] = st[sp - 1] == 0.0 ? 1.0 : 0.0; break;
+            default: break;
+        }
+    }
+    return sp > 0 ? st[sp - 1] : 0.0;
+}
+
+struct OccmNoRow { __device__ double operator()(int) const { return 0.0; } };
+
+// g_{b,s}(t): boundary / pulse time function of group b for species s (0 when none was specified).
+__device__ __forceinline__ double occm_bc_value(const OccmTab& T, int b, int s, double t) {
+    const int prog = T.bc_prog[b * T.S + s];
+    if (prog < 0) return 0.0;
+    // constant programs (the overwhelmingly common `a: inlet -> 1`) short-cut the interpreter
+    const int beg = T.prog_ptr[prog];
+    if (T.prog_ptr[prog + 1] - beg == 1 && (T.code[beg] & 0xff) == OCCM_OP_CONST) return T.consts[T.code[beg] >> 8];
+    return occm_vm_eval(T, prog, OccmNoRow(), t, 0, nullptr, 0);
+}
+
+// Net reaction rate of species s at a point whose concentrations are row(0..S-1)
+// (the generated `_ddt[s, :] += ...` lines of system_solvers/reactions.py:450-455).
+template <class Row>
+__device__ __forceinline__ double occm_reaction(const OccmTab& T, int s, const Row& row, const double* ksc, double t,
+                                                long long point, const OccmSysDev& sys) {
+    double acc = 0.0;
+    const int tb = T.term_ptr[s], te = T.term_ptr[s + 1];
+    for (int k = tb; k < te; ++k) {
+        double v = T.term_coeff[k];
+        if (ksc) v *= ksc[T.term_rxn[k]];
+        const int fb = T.fac_ptr[k], fe = T.fac_ptr[k + 1];
+        for (int f = fb; f < fe; ++f) {
+            const double x = row(T.fac_sp[f]);
+            const int ord = T.fac_ord[f];
+            double p = x;
+            for (int q = 1; q < ord; ++q) p *= x;
+            v *= p;
+        }
+        const int prog = T.term_prog[k];
+        if (prog >= 0) v *= occm_vm_eval(T, prog, row, t, point, sys.fields, sys.n_points);
+        acc += v;
+    }
+    return acc;
+}
+
+__device__ __forceinline__ double occm_pulses(const OccmSysDev& sys, const OccmTab& T, int model, int s, double t) {
+    double acc = 0.0;
+    if (sys.pulse_ptr) {
+        for (int k = sys.pulse_ptr[model]; k < sys.pulse_ptr[model + 1]; ++k)
+            acc += sys.pulse_w[k] * occm_bc_value(T, sys.pulse_fn[k], s, t);
+    }
+    return acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// d/dt of element (point p, species s).
+//   in(e)    : stage state at flat element e of this member, read from global memory (gathers)
+//   tile     : shared-memory copy of the stage state for elements [tile_lo, ...) covering this chunk's points
+// CSTR: cstr_system.py:194-203.   PFR: pfr_system.py:290-316.
+template <int MODEL, class In>
+__device__ __forceinline__ double occm_ddt_element(const OccmSysDev& sys, const OccmTab& T, const In& in,
+                                                   const double* tile, long long tile_lo, long long p, int s,
+                                                   double t, double qs, double bs, const double* ksc) {
+    const int S = sys.S;
+    const double* myrow = tile + (p * S - tile_lo);
+    auto row = [myrow](int sp) { return myrow[sp]; };
+    if (MODEL == 0) {   // CSTR
+        const int j = (int)p;
+        double acc = 0.0;
+        const int kb = __ldg(sys.row_ptr + j), ke = __ldg(sys.row_ptr + j + 1);
+        for (int k = kb; k < ke; ++k) {
+            const int src = __ldg(sys.row_src + k);
+            const double w = __ldg(sys.row_w + k);
+            if (src >= 0) acc += w * (src == j ? myrow[s] : in((long long)src * S + s));
+            else          acc += w * (bs * occm_bc_value(T, -1 - src, s, t));
+        }
+        return qs * acc + occm_pulses(sys, T, j, s, t) + occm_reaction(T, s, row, ksc, t, p, sys);
+    } else {
+        const int P = sys.P;
+        const int k = (int)(p / P);
+        const int i = (int)(p - (long long)k * P);
+        if (i > 0) {
+            const double conv = -(qs * __ldg(sys.a + k)) * (myrow[s] - myrow[s - S]);
+            return conv + occm_pulses(sys, T, k, s, t) + occm_reaction(T, s, row, ksc, t, p, sys);
+        }
+        double acc = 0.0;
+        const int eb = __ldg(sys.row_ptr + k), ee = __ldg(sys.row_ptr + k + 1);
+        for (int e = eb; e < ee; ++e) {
+            const int src = __ldg(sys.row_src + e);
+            const double w = __ldg(sys.row_w + e);
+            if (src >= 0) {
+                const long long o = (long long)P * (src + 1) - 1;   // outlet node of the upstream PFR
+                auto orow = [&in, o, S](int sp) { return in(o * S + sp); };
+                double d = -(qs * __ldg(sys.a + src)) * (in(o * S + s) - in((o - 1) * S + s));
+                d += occm_pulses(sys, T, src, s, t);
+                d += occm_reaction(T, s, orow, ksc, t, o, sys);
+                acc += w * d;
+            } else {
+                acc += w * (bs * occm_bc_value(T, -1 - src, s, t));
+            }
+        }
+        return acc;
+    }
+}
+
+// Chunk geometry: which points a chunk of OCCM_BLOCK elements starting at e0 touches and where its tile starts.
+struct OccmChunk {
+    long long e0, e1;        // element range [e0, e1)
+    long long tile_lo, tile_hi;  // staged element range
+};
+
+__device__ __forceinline__ OccmChunk occm_chunk(const OccmSysDev& sys, int ci) {
+    OccmChunk c;
+    c.e0 = (long long)ci * OCCM_BLOCK;
+    c.e1 = c.e0 + OCCM_BLOCK < sys.ndof ? c.e0 + OCCM_BLOCK : sys.ndof;
+    long long p_first = c.e0 / sys.S;
+    long long p_last = (c.e1 - 1) / sys.S;
+    if (sys.model == 1 && p_first > 0) p_first -= 1;       // upwind neighbour of the first point
+    c.tile_lo = p_first * sys.S;
+    c.tile_hi = (p_last + 1) * sys.S;
+    return c;
+}
+
+// deterministic block-wide sum (fixed tree), result valid in thread 0
+__device__ __forceinline__ double occm_block_sum(double v, double* scratch) {
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        for (int w = 0; w < nw; ++w) r += scratch[w];
+    }
+    __syncthreads();
+    return r;
+}

@@ -1,0 +1,58 @@
+// Host-side internals shared by the translation units of liboccm_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include "../../include/occm_b200.h"
+#include "occm_device.cuh"
+
+struct occm_system {
+    occm_system_desc desc;
+    OccmSysDev dev;
+    int sm_count;
+    size_t smem_tables;   // bytes of the staged table blob (8-byte aligned)
+};
+
+void occm_set_error(const char* fmt, ...);
+void occm_count_launch(int n = 1);
+
+#define OCCM_CUDA_CHECK(expr)                                                                      \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            occm_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return OCCM_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+#define OCCM_LAUNCH_CHECK(name)                                                                    \
+    do {                                                                                           \
+        cudaError_t _e = cudaGetLastError();                                                       \
+        if (_e != cudaSuccess) {                                                                   \
+            occm_set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));               \
+            return OCCM_ERR_CUDA;                                                                  \
+        }                                                                                          \
+        occm_count_launch();                                                                       \
+    } while (0)
+
+static inline OccmMemDev occm_mem_dev(const occm_members* mem, int fallback_M) {
+    OccmMemDev m;
+    m.M = mem ? mem->n_members : fallback_M;
+    m.k_scale = mem ? mem->k_scale : nullptr;
+    m.q_scale = mem ? mem->q_scale : nullptr;
+    m.bc_scale = mem ? mem->bc_scale : nullptr;
+    return m;
+}
+
+// dynamic shared memory of the element kernels: tables + tile + k_scale row + reduction scratch
+static inline size_t occm_elem_smem(const occm_system* sys) {
+    return sys->smem_tables + sizeof(double) * (OCCM_BLOCK + 3 * sys->dev.S + sys->dev.n_rxn + 40);
+}
+
+// persistent grid: a multiple of the SM count, capped by the amount of work
+static inline int occm_grid(const occm_system* sys, long long n_chunks, int ctas_per_sm) {
+    long long g = (long long)sys->sm_count * ctas_per_sm;
+    if (g > n_chunks) g = n_chunks;
+    if (g < 1) g = 1;
+    return (int)g;
+}

@@ -1,0 +1,614 @@
+// liboccm_b200.so — system handle, fused RHS kernel and the batched RK45 integrator (sm_100a).
+//
+// Kernels (all HBM-bound element-wise / gather kernels, fp64):
+//   occm_stage<MODEL, 0>      plain fused RHS   dy = A^T c + b(t) + r(c)            (16 B per element + CSR)
+//   occm_stage<MODEL, 2..7>   one Dormand-Prince stage: fused RHS of the stage state + production of the next
+//                             stage state (or y_new, or the error-norm partial sums) in the same pass
+//   occm_rk45_control         per-member error norm, accept/reject, step-size controller (scipy rk.py:111-167)
+//   occm_rk45_output          per-member dense output at the t_eval points inside the accepted step
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <atomic>
+#include "occm_host.h"
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void occm_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void occm_count_launch(int n) { g_launches += n; }
+
+extern "C" const char* occm_last_error(void) { return g_err; }
+extern "C" int occm_abi_version(void) { return OCCM_ABI_VERSION; }
+extern "C" int64_t occm_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------ system
+extern "C" int occm_system_create(occm_system** out, const occm_system_desc* d) {
+    if (!out || !d) { occm_set_error("occm_system_create: null argument"); return OCCM_ERR_INVALID; }
+    if (d->model != OCCM_MODEL_CSTR && d->model != OCCM_MODEL_PFR) { occm_set_error("unknown model %d", d->model); return OCCM_ERR_INVALID; }
+    if (d->n_species < 1 || d->n_species > OCCM_MAX_S) { occm_set_error("n_species=%d outside [1, %d]", d->n_species, OCCM_MAX_S); return OCCM_ERR_INVALID; }
+    if (d->n_models < 1) { occm_set_error("n_models must be >= 1"); return OCCM_ERR_INVALID; }
+    if (d->model == OCCM_MODEL_CSTR && d->points_per_model != 1) { occm_set_error("CSTR networks have one point per model"); return OCCM_ERR_INVALID; }
+    if (d->model == OCCM_MODEL_PFR && (d->points_per_model < 2 || !d->a)) { occm_set_error("PFR networks need points_per_model >= 2 and the a = Q/dV array"); return OCCM_ERR_INVALID; }
+    if (!d->row_ptr || !d->tables || d->tables_bytes < OCCM_H_WORDS * 4 || (d->tables_bytes & 7)) { occm_set_error("row_ptr/tables missing or malformed"); return OCCM_ERR_INVALID; }
+    int hdr[OCCM_H_WORDS];
+    OCCM_CUDA_CHECK(cudaMemcpy(hdr, d->tables, sizeof(hdr), cudaMemcpyDeviceToHost));
+    if (hdr[OCCM_H_MAGIC] != OCCM_TABLES_MAGIC || hdr[OCCM_H_BYTES] != d->tables_bytes || hdr[OCCM_H_S] != d->n_species) {
+        occm_set_error("table blob header mismatch (magic %x, bytes %d vs %d, S %d vs %d)", hdr[OCCM_H_MAGIC], hdr[OCCM_H_BYTES],
+                       d->tables_bytes, hdr[OCCM_H_S], d->n_species);
+        return OCCM_ERR_INVALID;
+    }
+    long long n_points = (long long)d->n_models * d->points_per_model;
+    long long ndof = n_points * d->n_species;
+    if (n_points >= (1ll << 31) - 2) { occm_set_error("too many points for int32 indices"); return OCCM_ERR_INVALID; }
+    occm_system* s = (occm_system*)calloc(1, sizeof(occm_system));
+    s->desc = *d;
+    OccmSysDev& v = s->dev;
+    v.model = d->model; v.S = d->n_species; v.n_models = d->n_models; v.P = d->points_per_model;
+    v.n_points = n_points; v.ndof = ndof;
+    v.row_ptr = d->row_ptr; v.row_src = d->row_src; v.row_w = d->row_w; v.a = d->a;
+    v.pulse_ptr = d->pulse_ptr; v.pulse_fn = d->pulse_fn; v.pulse_w = d->pulse_w;
+    v.tables = (const int*)d->tables; v.tables_bytes = d->tables_bytes;
+    v.fields = d->fields; v.n_fields = d->n_fields;
+    v.n_rxn = hdr[OCCM_H_NRXN];
+    v.chunks_per_member = (int)((ndof + OCCM_BLOCK - 1) / OCCM_BLOCK);
+    s->smem_tables = (size_t)d->tables_bytes;
+    int dev = 0;
+    OCCM_CUDA_CHECK(cudaGetDevice(&dev));
+    OCCM_CUDA_CHECK(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev));
+    int max_smem = 0;
+    OCCM_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (occm_elem_smem(s) > (size_t)max_smem) {
+        occm_set_error("mechanism tables (%d B) do not fit in shared memory (%d B)", d->tables_bytes, max_smem);
+        free(s);
+        return OCCM_ERR_UNSUPPORTED;
+    }
+    *out = s;
+    return OCCM_OK;
+}
+
+extern "C" int occm_system_destroy(occm_system* s) { free(s); return OCCM_OK; }
+extern "C" int64_t occm_system_ndof(const occm_system* s) { return s ? s->dev.ndof : -1; }
+
+// ------------------------------------------------------------------------------------------------ RK45 data
+// Dormand-Prince coefficients exactly as scipy builds them (scipy/integrate/_ivp/rk.py:280-320, Python float
+// divisions == IEEE double divisions evaluated at compile time here).
+namespace dp {
+constexpr double C2 = 1.0 / 5, C3 = 3.0 / 10, C4 = 4.0 / 5, C5 = 8.0 / 9;
+constexpr double A21 = 1.0 / 5;
+constexpr double A31 = 3.0 / 40, A32 = 9.0 / 40;
+constexpr double A41 = 44.0 / 45, A42 = -56.0 / 15, A43 = 32.0 / 9;
+constexpr double A51 = 19372.0 / 6561, A52 = -25360.0 / 2187, A53 = 64448.0 / 6561, A54 = -212.0 / 729;
+constexpr double A61 = 9017.0 / 3168, A62 = -355.0 / 33, A63 = 46732.0 / 5247, A64 = 49.0 / 176, A65 = -5103.0 / 18656;
+constexpr double B1 = 35.0 / 384, B3 = 500.0 / 1113, B4 = 125.0 / 192, B5 = -2187.0 / 6784, B6 = 11.0 / 84;
+constexpr double E1 = -71.0 / 57600, E3 = 71.0 / 16695, E4 = -71.0 / 1920, E5 = 17253.0 / 339200, E6 = -22.0 / 525, E7 = 1.0 / 40;
+// dense output polynomial, rows = stages 1..7 (row 2 is zero), columns = powers x^1..x^4 (rk.py:321-335)
+constexpr double P11 = 1.0, P12 = -8048581381.0 / 2820520608, P13 = 8663915743.0 / 2820520608, P14 = -12715105075.0 / 11282082432;
+constexpr double P32 = 131558114200.0 / 32700410799, P33 = -68118460800.0 / 10900136933, P34 = 87487479700.0 / 32700410799;
+constexpr double P42 = -1754552775.0 / 470086768, P43 = 14199869525.0 / 1410260304, P44 = -10690763975.0 / 1880347072;
+constexpr double P52 = 127303824393.0 / 49829197408, P53 = -318862633887.0 / 49829197408, P54 = 701980252875.0 / 199316789632;
+constexpr double P62 = -282668133.0 / 205662961, P63 = 2019193451.0 / 616988883, P64 = -1453857185.0 / 822651844;
+constexpr double P72 = 40617522.0 / 29380423, P73 = -110615467.0 / 29380423, P74 = 69997945.0 / 29380423;
+constexpr double SAFETY = 0.9, MIN_FACTOR = 0.2, MAX_FACTOR = 10.0, ERROR_EXPONENT = -1.0 / 5;
+}  // namespace dp
+
+struct OccmRkDev {
+    double* Y[2];     // state ping-pong; Y[parity[m]] is the current state of member m
+    double* KF[2];    // K1 / K7 ping-pong (first-same-as-last)
+    double* K2; double* K3; double* K4; double* K5; double* K6;
+    double* YS[2];    // materialised stage states
+    double* t; double* h; double* h_abs; double* t_new; double* t_old;
+    int* parity; int* status; int* rejected; int* accepted_now; int* out_lo; int* out_hi; int* n_rows;
+    long long* n_acc; long long* n_rej; long long* nfev;
+    double* err_partial;  // [M][chunks_per_member]
+    int* n_running;
+    double rtol, atol, t_bound;
+    long long max_steps;
+};
+
+struct occm_rk45 {
+    const occm_system* sys;
+    occm_members mem; bool has_mem;
+    occm_rk45_problem prob;
+    OccmRkDev d;
+    int M;
+    int* h_running;     // pinned host
+    long long launched_steps;
+};
+
+// ------------------------------------------------------------------------------------------------ stage kernel
+// STAGE 0: plain RHS (y_in -> dy_out).  STAGE s in 2..7: Dormand-Prince stage s of rk_step (rk.py:14-71).
+template <int MODEL, int STAGE>
+__global__ void __launch_bounds__(OCCM_BLOCK)
+occm_stage(const OccmSysDev sys, const OccmMemDev mem, const OccmRkDev rk, const double* __restrict__ t_dev, double t_scalar,
+           const double* __restrict__ y_in, double* __restrict__ dy_out) {
+    extern __shared__ double smem_d[];
+    const OccmTab T = occm_load_tables(sys.tables, sys.tables_bytes, reinterpret_cast<int*>(smem_d));
+    double* tile = smem_d + (sys.tables_bytes >> 3);
+    double* ksc_s = tile + OCCM_BLOCK + 3 * sys.S;
+    double* scratch = ksc_s + sys.n_rxn;
+    const int S = sys.S;
+    const int cpm = sys.chunks_per_member;
+    const long long total = (long long)mem.M * cpm;
+
+    for (long long c = blockIdx.x; c < total; c += gridDim.x) {
+        const int m = (int)(c / cpm);
+        const int ci = (int)(c - (long long)m * cpm);
+        if (STAGE != 0 && rk.status[m] != OCCM_MEMBER_RUNNING) continue;   // uniform over the CTA
+        const OccmChunk ch = occm_chunk(sys, ci);
+        const long long base = (long long)m * sys.ndof;
+        const double qs = mem.q_scale ? __ldg(mem.q_scale + m) : 1.0;
+        const double bs = mem.bc_scale ? __ldg(mem.bc_scale + m) : 1.0;
+        const double* ksc = nullptr;
+        if (mem.k_scale) {
+            for (int r = threadIdx.x; r < sys.n_rxn; r += OCCM_BLOCK) ksc_s[r] = __ldg(mem.k_scale + (long long)m * sys.n_rxn + r);
+            ksc = ksc_s;
+        }
+        double t_stage, h = 0.0;
+        int par = 0;
+        const double* y = nullptr; const double* k1 = nullptr;
+        if (STAGE == 0) {
+            t_stage = t_dev ? __ldg(t_dev + m) : t_scalar;
+        } else {
+            const double t0 = rk.t[m];
+            h = rk.h[m];
+            par = rk.parity[m];
+            y = rk.Y[par] + base;
+            k1 = rk.KF[par] + base;
+            t_stage = STAGE == 2 ? t0 + dp::C2 * h : STAGE == 3 ? t0 + dp::C3 * h : STAGE == 4 ? t0 + dp::C4 * h
+                    : STAGE == 5 ? t0 + dp::C5 * h : t0 + h;
+        }
+        // the stage state this kernel differentiates
+        const double* sin_ = STAGE == 0 ? y_in + base
+                           : STAGE == 3 || STAGE == 5 ? rk.YS[0] + base
+                           : STAGE == 4 || STAGE == 6 ? rk.YS[1] + base
+                           : STAGE == 7 ? rk.Y[par ^ 1] + base : nullptr;
+        auto in = [=](long long e) -> double {
+            if (STAGE == 2) return __ldg(y + e) + (dp::A21 * __ldg(k1 + e)) * h;     // y + h * a21 * K1, formed on the fly
+            return __ldg(sin_ + e);
+        };
+        // stage the points of this chunk
+        for (long long e = ch.tile_lo + threadIdx.x; e < ch.tile_hi; e += OCCM_BLOCK) tile[e - ch.tile_lo] = in(e);
+        __syncthreads();
+
+        const long long e = ch.e0 + threadIdx.x;
+        double err2 = 0.0;
+        if (e < ch.e1) {
+            const long long p = e / S;
+            const int s = (int)(e - p * S);
+            const double f = occm_ddt_element<MODEL>(sys, T, in, tile, ch.tile_lo, p, s, t_stage, qs, bs, ksc);
+            if (STAGE == 0) {
+                dy_out[base + e] = f;
+            } else {
+                const double ye = __ldg(y + e), k1e = __ldg(k1 + e);
+                if (STAGE == 2) {
+                    rk.K2[base + e] = f;
+                    rk.YS[0][base + e] = ye + (dp::A31 * k1e + dp::A32 * f) * h;
+                } else if (STAGE == 3) {
+                    rk.K3[base + e] = f;
+                    const double k2 = __ldg(rk.K2 + base + e);
+                    rk.YS[1][base + e] = ye + (dp::A41 * k1e + dp::A42 * k2 + dp::A43 * f) * h;
+                } else if (STAGE == 4) {
+                    rk.K4[base + e] = f;
+                    const double k2 = __ldg(rk.K2 + base + e), k3 = __ldg(rk.K3 + base + e);
+                    rk.YS[0][base + e] = ye + (dp::A51 * k1e + dp::A52 * k2 + dp::A53 * k3 + dp::A54 * f) * h;
+                } else if (STAGE == 5) {
+                    rk.K5[base + e] = f;
+                    const double k2 = __ldg(rk.K2 + base + e), k3 = __ldg(rk.K3 + base + e), k4 = __ldg(rk.K4 + base + e);
+                    rk.YS[1][base + e] = ye + (dp::A61 * k1e + dp::A62 * k2 + dp::A63 * k3 + dp::A64 * k4 + dp::A65 * f) * h;
+                } else if (STAGE == 6) {
+                    rk.K6[base + e] = f;
+                    const double k3 = __ldg(rk.K3 + base + e), k4 = __ldg(rk.K4 + base + e), k5 = __ldg(rk.K5 + base + e);
+                    // y_new = y + h * dot(K[:-1].T, B)   (rk.py:64)
+                    rk.Y[par ^ 1][base + e] = ye + h * (dp::B1 * k1e + dp::B3 * k3 + dp::B4 * k4 + dp::B5 * k5 + dp::B6 * f);
+                } else {  // STAGE 7: f_new = K7, error estimate (rk.py:66-69, 157-162)
+                    rk.KF[par ^ 1][base + e] = f;
+                    const double k3 = __ldg(rk.K3 + base + e), k4 = __ldg(rk.K4 + base + e), k5 = __ldg(rk.K5 + base + e),
+                                 k6 = __ldg(rk.K6 + base + e);
+                    const double yn = tile[e - ch.tile_lo];
+                    const double err = (dp::E1 * k1e + dp::E3 * k3 + dp::E4 * k4 + dp::E5 * k5 + dp::E6 * k6 + dp::E7 * f) * h;
+                    const double scale = rk.atol + fmax(fabs(ye), fabs(yn)) * rk.rtol;
+                    const double q = err / scale;
+                    err2 = q * q;
+                }
+            }
+        }
+        if (STAGE == 7) {
+            const double sum = occm_block_sum(err2, scratch);   // contains __syncthreads
+            if (threadIdx.x == 0) rk.err_partial[(long long)m * cpm + ci] = sum;
+        } else {
+            __syncthreads();   // tile is overwritten by the next chunk
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ controller
+// np.nextafter(t, +inf) for t >= 0 (the reference asserts t0 >= 0, helper_functions.py:82)
+__device__ __forceinline__ double occm_next_up(double t) { return __longlong_as_double(__double_as_longlong(t) + 1ll); }
+
+__device__ __forceinline__ void occm_rk45_plan_attempt(const OccmRkDev& rk, int m, double t, double h_abs) {
+    // rk.py:125-135 (direction = +1): h = h_abs; t_new = t + h; clip to t_bound
+    double h = h_abs;
+    double t_new = t + h;
+    if (t_new - rk.t_bound > 0.0) t_new = rk.t_bound;
+    h = t_new - t;
+    rk.h[m] = h;
+    rk.h_abs[m] = fabs(h);
+    rk.t_new[m] = t_new;
+}
+
+__global__ void __launch_bounds__(128)
+occm_rk45_control(const OccmRkDev rk, int cpm, long long ndof, const double* __restrict__ t_eval, int n_t_eval) {
+    __shared__ double scratch[8];
+    const int m = blockIdx.x;
+    if (rk.status[m] != OCCM_MEMBER_RUNNING) {
+        if (threadIdx.x == 0) rk.accepted_now[m] = 0;
+        return;
+    }
+    // deterministic reduction of the per-chunk partial sums
+    double v = 0.0;
+    for (int i = threadIdx.x; i < cpm; i += blockDim.x) v += rk.err_partial[(long long)m * cpm + i];
+    const double sum = occm_block_sum(v, scratch);
+    if (threadIdx.x != 0) return;
+
+    const double error_norm = sqrt(sum / (double)ndof);       // norm(x) = ||x||_2 / sqrt(n)   (common.py:64-66)
+    double t = rk.t[m];
+    double h_abs = rk.h_abs[m];
+    rk.nfev[m] += 6;
+    if (error_norm < 1.0) {                                    // rk.py:150-161 accepted
+        double factor = error_norm == 0.0 ? dp::MAX_FACTOR : fmin(dp::MAX_FACTOR, dp::SAFETY * pow(error_norm, dp::ERROR_EXPONENT));
+        if (rk.rejected[m]) factor = fmin(1.0, factor);
+        h_abs *= factor;
+        rk.t_old[m] = t;
+        t = rk.t_new[m];
+        rk.t[m] = t;
+        rk.parity[m] ^= 1;
+        rk.rejected[m] = 0;
+        rk.accepted_now[m] = 1;
+        const long long n_acc = ++rk.n_acc[m];
+        int status = OCCM_MEMBER_RUNNING;
+        if (t - rk.t_bound >= 0.0) status = OCCM_MEMBER_FINISHED;        // base.py:193-197
+        else if (rk.max_steps > 0 && n_acc + rk.n_rej[m] >= rk.max_steps) status = OCCM_MEMBER_MAX_STEPS;
+        // output bookkeeping (ivp.py:701-730)
+        if (t_eval) {
+            int lo = rk.out_hi[m], hi = lo;
+            while (hi < n_t_eval && t_eval[hi] <= t) ++hi;      // searchsorted(t_eval, t, side='right')
+            rk.out_lo[m] = lo; rk.out_hi[m] = hi;
+        } else {
+            const int row = rk.n_rows[m];
+            rk.out_lo[m] = row; rk.n_rows[m] = row + 1;
+            if (status == OCCM_MEMBER_RUNNING && row + 1 >= n_t_eval) status = OCCM_MEMBER_PAUSED;
+        }
+        rk.status[m] = status;
+        if (status == OCCM_MEMBER_RUNNING || status == OCCM_MEMBER_PAUSED) {
+            // start of the next _step_impl (rk.py:113-120): h_abs is clipped from below to 10 ulp(t)
+            const double min_step = 10.0 * fabs(occm_next_up(t) - t);
+            if (h_abs < min_step) h_abs = min_step;
+            occm_rk45_plan_attempt(rk, m, t, h_abs);
+        }
+    } else {                                                   // rk.py:163-166 rejected (NaN norms land here too)
+        double shrink = dp::SAFETY * pow(error_norm, dp::ERROR_EXPONENT);
+        shrink = shrink > dp::MIN_FACTOR ? shrink : dp::MIN_FACTOR;   // Python max(MIN_FACTOR, x): NaN -> MIN_FACTOR
+        h_abs *= shrink;
+        rk.rejected[m] = 1;
+        rk.accepted_now[m] = 0;
+        const long long n_rej = ++rk.n_rej[m];
+        const double min_step = 10.0 * fabs(occm_next_up(t) - t);
+        if (h_abs < min_step) rk.status[m] = isfinite(error_norm) ? OCCM_MEMBER_STEP_TOO_SMALL : OCCM_MEMBER_NONFINITE;
+        else if (rk.max_steps > 0 && n_rej + rk.n_acc[m] >= rk.max_steps) rk.status[m] = OCCM_MEMBER_MAX_STEPS;
+        else occm_rk45_plan_attempt(rk, m, t, h_abs);
+    }
+}
+
+__global__ void occm_rk45_init_members(const OccmRkDev rk, int M, double t0, double first_step, int all_mode,
+                                       const double* __restrict__ t_eval, int n_t_eval) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    rk.t[m] = t0; rk.t_old[m] = t0;
+    rk.parity[m] = 0; rk.status[m] = OCCM_MEMBER_RUNNING; rk.rejected[m] = 0; rk.accepted_now[m] = 0;
+    rk.n_acc[m] = 0; rk.n_rej[m] = 0; rk.nfev[m] = 1;       // f(t0, y0)
+    rk.out_lo[m] = 0; rk.out_hi[m] = 0; rk.n_rows[m] = all_mode ? 1 : 0;
+    double h_abs = first_step;
+    const double min_step = 10.0 * fabs(occm_next_up(t0) - t0);
+    if (h_abs < min_step) h_abs = min_step;
+    occm_rk45_plan_attempt(rk, m, t0, h_abs);
+    if (m == 0) *rk.n_running = M;
+}
+
+__global__ void occm_count_running(const int* __restrict__ status, int M, int* out) {
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    int local = 0;
+    for (int m = threadIdx.x; m < M; m += blockDim.x) local += status[m] == OCCM_MEMBER_RUNNING;
+    atomicAdd(&cnt, local);
+    __syncthreads();
+    if (threadIdx.x == 0) *out = cnt;
+}
+
+// ------------------------------------------------------------------------------------------------ output kernel
+// t_eval mode: RkDenseOutput (rk.py:575-601) at every t_eval in (t_old, t]; "all" mode: copy y_new.
+__global__ void __launch_bounds__(OCCM_BLOCK)
+occm_rk45_output(const OccmRkDev rk, int M, long long ndof, int n_save, const int* __restrict__ save_idx,
+                 const double* __restrict__ t_eval, int n_t_eval, double* __restrict__ out, double* __restrict__ out_t) {
+    const int cps = (n_save + OCCM_BLOCK - 1) / OCCM_BLOCK;
+    const long long total = (long long)M * cps;
+    for (long long c = blockIdx.x; c < total; c += gridDim.x) {
+        const int m = (int)(c / cps);
+        if (!rk.accepted_now[m]) continue;
+        const int lo = rk.out_lo[m];
+        const int hi = t_eval ? rk.out_hi[m] : lo + 1;
+        if (hi <= lo) continue;
+        const int i = (int)(c - (long long)m * cps) * OCCM_BLOCK + threadIdx.x;
+        if (i >= n_save) continue;
+        const long long e = save_idx ? save_idx[i] : i;
+        const long long base = (long long)m * ndof;
+        const int par = rk.parity[m];               // already flipped: Y[par] = y_new, Y[par^1] = y_old
+        const double t = rk.t[m];
+        if (!t_eval) {
+            out[((long long)m * n_t_eval + lo) * n_save + i] = rk.Y[par][base + e];
+            if (out_t && i == 0) out_t[(long long)m * n_t_eval + lo] = t;
+            continue;
+        }
+        const double t_old = rk.t_old[m];
+        const double h = t - t_old;
+        const double k1 = rk.KF[par ^ 1][base + e], k3 = rk.K3[base + e], k4 = rk.K4[base + e], k5 = rk.K5[base + e],
+                     k6 = rk.K6[base + e], k7 = rk.KF[par][base + e];
+        const double y_old = rk.Y[par ^ 1][base + e];
+        // Q = K^T P  (rk.py:170)
+        const double q0 = k1 * dp::P11;
+        const double q1 = k1 * dp::P12 + k3 * dp::P32 + k4 * dp::P42 + k5 * dp::P52 + k6 * dp::P62 + k7 * dp::P72;
+        const double q2 = k1 * dp::P13 + k3 * dp::P33 + k4 * dp::P43 + k5 * dp::P53 + k6 * dp::P63 + k7 * dp::P73;
+        const double q3 = k1 * dp::P14 + k3 * dp::P34 + k4 * dp::P44 + k5 * dp::P54 + k6 * dp::P64 + k7 * dp::P74;
+        for (int j = lo; j < hi; ++j) {
+            const double x = (t_eval[j] - t_old) / h;
+            const double x2 = x * x, x3 = x2 * x, x4 = x3 * x;      // np.cumprod([x, x, x, x])
+            const double yv = h * (q0 * x + q1 * x2 + q2 * x3 + q3 * x4) + y_old;
+            out[((long long)m * n_t_eval + j) * n_save + i] = yv;
+            if (out_t && i == 0) out_t[(long long)m * n_t_eval + j] = t_eval[j];
+        }
+    }
+}
+
+__global__ void occm_rk45_resume_kernel(const OccmRkDev rk, int M) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    rk.n_rows[m] = 0;
+    if (rk.status[m] == OCCM_MEMBER_PAUSED) rk.status[m] = OCCM_MEMBER_RUNNING;
+}
+
+__global__ void occm_rk45_gather_state(const OccmRkDev rk, int M, long long ndof, double* __restrict__ out) {
+    const long long total = (long long)M * ndof;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(i / ndof);
+        out[i] = rk.Y[rk.parity[m]][i];
+    }
+}
+
+__global__ void occm_rk45_write_initial(const double* __restrict__ y0, int M, long long ndof, int n_save,
+                                        const int* __restrict__ save_idx, int cap, double t0, double* __restrict__ out,
+                                        double* __restrict__ out_t) {
+    const long long total = (long long)M * n_save;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(k / n_save);
+        const int i = (int)(k - (long long)m * n_save);
+        const long long e = save_idx ? save_idx[i] : i;
+        out[((long long)m * cap) * n_save + i] = y0[(long long)m * ndof + e];
+        if (i == 0) out_t[(long long)m * cap] = t0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launch helpers
+template <int STAGE>
+static int occm_launch_stage(const occm_system* sys, const OccmMemDev& mem, const OccmRkDev& rk, const double* t_dev,
+                             double t_scalar, const double* y_in, double* dy_out, cudaStream_t st) {
+    const size_t smem = occm_elem_smem(sys);
+    const long long chunks = (long long)mem.M * sys->dev.chunks_per_member;
+    const int grid = occm_grid(sys, chunks, 8);
+    if (sys->dev.model == OCCM_MODEL_CSTR) {
+        static size_t smem_limit = 48 * 1024;   // the default opt-out limit; raise it only when needed
+        if (smem > smem_limit) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(occm_stage<0, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_limit = smem; }
+        occm_stage<0, STAGE><<<grid, OCCM_BLOCK, smem, st>>>(sys->dev, mem, rk, t_dev, t_scalar, y_in, dy_out);
+    } else {
+        static size_t smem_limit = 48 * 1024;   // the default opt-out limit; raise it only when needed
+        if (smem > smem_limit) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(occm_stage<1, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_limit = smem; }
+        occm_stage<1, STAGE><<<grid, OCCM_BLOCK, smem, st>>>(sys->dev, mem, rk, t_dev, t_scalar, y_in, dy_out);
+    }
+    OCCM_LAUNCH_CHECK("occm_stage");
+    return OCCM_OK;
+}
+
+extern "C" int occm_rhs(const occm_system* sys, const occm_members* mem, const double* t_dev, double t_scalar,
+                        const double* y, double* dy, void* stream) {
+    if (!sys || !y || !dy) { occm_set_error("occm_rhs: null argument"); return OCCM_ERR_INVALID; }
+    OccmRkDev none;
+    memset(&none, 0, sizeof(none));
+    return occm_launch_stage<0>(sys, occm_mem_dev(mem, 1), none, t_dev, t_scalar, y, dy, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ RK45 host side
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct RkLayout {
+    size_t vec, off_vec[11], off_t, off_h, off_habs, off_tnew, off_told, off_par, off_status, off_rej, off_acc_now,
+        off_lo, off_hi, off_rows, off_nacc, off_nrej, off_nfev, off_err, off_running, total;
+};
+
+static RkLayout rk_layout(const occm_system* sys, int M) {
+    RkLayout L;
+    size_t o = 0;
+    L.vec = align256((size_t)M * sys->dev.ndof * sizeof(double));
+    for (int i = 0; i < 11; ++i) { L.off_vec[i] = o; o += L.vec; }
+    auto take = [&](size_t bytes) { size_t r = o; o += align256(bytes); return r; };
+    L.off_t = take(M * 8); L.off_h = take(M * 8); L.off_habs = take(M * 8); L.off_tnew = take(M * 8); L.off_told = take(M * 8);
+    L.off_par = take(M * 4); L.off_status = take(M * 4); L.off_rej = take(M * 4); L.off_acc_now = take(M * 4);
+    L.off_lo = take(M * 4); L.off_hi = take(M * 4); L.off_rows = take(M * 4);
+    L.off_nacc = take(M * 8); L.off_nrej = take(M * 8); L.off_nfev = take(M * 8);
+    L.off_err = take((size_t)M * sys->dev.chunks_per_member * 8);
+    L.off_running = take(256);
+    L.total = o;
+    return L;
+}
+
+extern "C" size_t occm_rk45_workspace_bytes(const occm_system* sys, int32_t M) {
+    if (!sys || M < 1) return 0;
+    return rk_layout(sys, M).total;
+}
+
+extern "C" int occm_rk45_init(occm_rk45** out, const occm_system* sys, const occm_members* mem, const occm_rk45_problem* p,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+    if (!out || !sys || !p || !workspace || !p->y0 || !p->out) { occm_set_error("occm_rk45_init: null argument"); return OCCM_ERR_INVALID; }
+    const int M = mem ? mem->n_members : 1;
+    if (M < 1) { occm_set_error("n_members must be >= 1"); return OCCM_ERR_INVALID; }
+    if (!(p->t_bound > p->t0)) { occm_set_error("t_bound must be greater than t0 (forward integration only, helper_functions.py:82)"); return OCCM_ERR_INVALID; }
+    if (!(p->first_step > 0.0)) { occm_set_error("`first_step` must be positive."); return OCCM_ERR_INVALID; }
+    if (p->first_step > fabs(p->t_bound - p->t0)) { occm_set_error("`first_step` exceeds bounds."); return OCCM_ERR_INVALID; }
+    if (!(p->rtol > 0.0) || !(p->atol >= 0.0)) { occm_set_error("rtol must be > 0 and atol >= 0"); return OCCM_ERR_INVALID; }
+    if (p->n_t_eval < 1) { occm_set_error("n_t_eval (or the row capacity in all-steps mode) must be >= 1"); return OCCM_ERR_INVALID; }
+    if (!p->t_eval && p->n_t_eval < 2) { occm_set_error("all-steps mode needs a row capacity >= 2"); return OCCM_ERR_INVALID; }
+    if (!p->t_eval && !p->out_t) { occm_set_error("all-steps mode needs out_t"); return OCCM_ERR_INVALID; }
+    const RkLayout L = rk_layout(sys, M);
+    if (workspace_bytes < L.total) { occm_set_error("workspace too small: %zu < %zu", workspace_bytes, L.total); return OCCM_ERR_WORKSPACE; }
+    if ((uintptr_t)workspace & 255) { occm_set_error("workspace must be 256-byte aligned"); return OCCM_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+
+    occm_rk45* rk = (occm_rk45*)calloc(1, sizeof(occm_rk45));
+    rk->sys = sys; rk->M = M; rk->prob = *p;
+    rk->has_mem = mem != nullptr;
+    if (mem) rk->mem = *mem; else { memset(&rk->mem, 0, sizeof(rk->mem)); rk->mem.n_members = 1; }
+    char* w = (char*)workspace;
+    OccmRkDev& d = rk->d;
+    double* vecs[11];
+    for (int i = 0; i < 11; ++i) vecs[i] = (double*)(w + L.off_vec[i]);
+    d.Y[0] = vecs[0]; d.Y[1] = vecs[1]; d.KF[0] = vecs[2]; d.KF[1] = vecs[3];
+    d.K2 = vecs[4]; d.K3 = vecs[5]; d.K4 = vecs[6]; d.K5 = vecs[7]; d.K6 = vecs[8]; d.YS[0] = vecs[9]; d.YS[1] = vecs[10];
+    d.t = (double*)(w + L.off_t); d.h = (double*)(w + L.off_h); d.h_abs = (double*)(w + L.off_habs);
+    d.t_new = (double*)(w + L.off_tnew); d.t_old = (double*)(w + L.off_told);
+    d.parity = (int*)(w + L.off_par); d.status = (int*)(w + L.off_status); d.rejected = (int*)(w + L.off_rej);
+    d.accepted_now = (int*)(w + L.off_acc_now); d.out_lo = (int*)(w + L.off_lo); d.out_hi = (int*)(w + L.off_hi);
+    d.n_rows = (int*)(w + L.off_rows);
+    d.n_acc = (long long*)(w + L.off_nacc); d.n_rej = (long long*)(w + L.off_nrej); d.nfev = (long long*)(w + L.off_nfev);
+    d.err_partial = (double*)(w + L.off_err);
+    d.n_running = (int*)(w + L.off_running);
+    d.rtol = p->rtol; d.atol = p->atol; d.t_bound = p->t_bound; d.max_steps = p->max_steps;
+
+    if (cudaHostAlloc((void**)&rk->h_running, sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+        occm_set_error("cudaHostAlloc failed"); free(rk); return OCCM_ERR_CUDA;
+    }
+    const size_t state_bytes = (size_t)M * sys->dev.ndof * sizeof(double);
+    OCCM_CUDA_CHECK(cudaMemcpyAsync(d.Y[0], p->y0, state_bytes, cudaMemcpyDeviceToDevice, st));
+    occm_rk45_init_members<<<(M + 127) / 128, 128, 0, st>>>(d, M, p->t0, p->first_step, p->t_eval ? 0 : 1, p->t_eval, p->n_t_eval);
+    OCCM_LAUNCH_CHECK("occm_rk45_init_members");
+    // K1 = f(t0, y0)   (rk.py:94)
+    const OccmMemDev md = occm_mem_dev(rk->has_mem ? &rk->mem : nullptr, 1);
+    int rc = occm_launch_stage<0>(sys, md, d, nullptr, p->t0, d.Y[0], d.KF[0], st);
+    if (rc) { free(rk); return rc; }
+    if (!p->t_eval) {
+        // ivp.py:653-655: ts = [t0], ys = [y0]
+        const int n_save = p->save_idx ? p->n_save : (int)sys->dev.ndof;
+        const long long total = (long long)M * n_save;
+        const int grid = (int)((total + OCCM_BLOCK - 1) / OCCM_BLOCK < 65535 ? (total + OCCM_BLOCK - 1) / OCCM_BLOCK : 65535);
+        occm_rk45_write_initial<<<grid, OCCM_BLOCK, 0, st>>>(d.Y[0], M, sys->dev.ndof, n_save, p->save_idx, p->n_t_eval, p->t0,
+                                                             p->out, p->out_t);
+        OCCM_LAUNCH_CHECK("occm_rk45_write_initial");
+    }
+    rk->launched_steps = 0;
+    *out = rk;
+    return OCCM_OK;
+}
+
+static int occm_rk45_launch_step(occm_rk45* rk, cudaStream_t st) {
+    const occm_system* sys = rk->sys;
+    const OccmMemDev md = occm_mem_dev(rk->has_mem ? &rk->mem : nullptr, 1);
+    const OccmRkDev& d = rk->d;
+    int rc;
+    if ((rc = occm_launch_stage<2>(sys, md, d, nullptr, 0.0, nullptr, nullptr, st))) return rc;
+    if ((rc = occm_launch_stage<3>(sys, md, d, nullptr, 0.0, nullptr, nullptr, st))) return rc;
+    if ((rc = occm_launch_stage<4>(sys, md, d, nullptr, 0.0, nullptr, nullptr, st))) return rc;
+    if ((rc = occm_launch_stage<5>(sys, md, d, nullptr, 0.0, nullptr, nullptr, st))) return rc;
+    if ((rc = occm_launch_stage<6>(sys, md, d, nullptr, 0.0, nullptr, nullptr, st))) return rc;
+    if ((rc = occm_launch_stage<7>(sys, md, d, nullptr, 0.0, nullptr, nullptr, st))) return rc;
+    occm_rk45_control<<<rk->M, 128, 0, st>>>(d, sys->dev.chunks_per_member, sys->dev.ndof, rk->prob.t_eval, rk->prob.n_t_eval);
+    OCCM_LAUNCH_CHECK("occm_rk45_control");
+    const int n_save = rk->prob.save_idx ? rk->prob.n_save : (int)sys->dev.ndof;
+    const long long chunks = (long long)rk->M * ((n_save + OCCM_BLOCK - 1) / OCCM_BLOCK);
+    occm_rk45_output<<<occm_grid(sys, chunks, 8), OCCM_BLOCK, 0, st>>>(d, rk->M, sys->dev.ndof, n_save, rk->prob.save_idx,
+                                                                     rk->prob.t_eval, rk->prob.n_t_eval, rk->prob.out, rk->prob.out_t);
+    OCCM_LAUNCH_CHECK("occm_rk45_output");
+    return OCCM_OK;
+}
+
+extern "C" int occm_rk45_run(occm_rk45* rk, int64_t max_launch_steps, int32_t* n_running, void* stream) {
+    if (!rk) { occm_set_error("occm_rk45_run: null handle"); return OCCM_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    long long launched = 0;
+    int batch = 4;
+    int running = rk->M;
+    while (true) {
+        int todo = batch;
+        if (max_launch_steps > 0 && launched + todo > max_launch_steps) todo = (int)(max_launch_steps - launched);
+        for (int i = 0; i < todo; ++i) {
+            int rc = occm_rk45_launch_step(rk, st);
+            if (rc) return rc;
+        }
+        launched += todo;
+        occm_count_running<<<1, 256, 0, st>>>(rk->d.status, rk->M, rk->d.n_running);
+        OCCM_LAUNCH_CHECK("occm_count_running");
+        OCCM_CUDA_CHECK(cudaMemcpyAsync(rk->h_running, rk->d.n_running, sizeof(int), cudaMemcpyDeviceToHost, st));
+        OCCM_CUDA_CHECK(cudaStreamSynchronize(st));
+        running = *rk->h_running;
+        if (running == 0) break;
+        if (max_launch_steps > 0 && launched >= max_launch_steps) break;
+        if (batch < 64) batch *= 2;
+    }
+    rk->launched_steps += launched;
+    if (n_running) *n_running = running;
+    return OCCM_OK;
+}
+
+extern "C" int occm_rk45_resume(occm_rk45* rk, void* stream) {
+    if (!rk) { occm_set_error("occm_rk45_resume: null handle"); return OCCM_ERR_INVALID; }
+    occm_rk45_resume_kernel<<<(rk->M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rk->d, rk->M);
+    OCCM_LAUNCH_CHECK("occm_rk45_resume_kernel");
+    return OCCM_OK;
+}
+
+extern "C" int occm_rk45_stats(occm_rk45* rk, int32_t* status, int64_t* n_accepted, int64_t* n_rejected, int64_t* nfev,
+                               double* t, int32_t* n_rows, void* stream) {
+    if (!rk) { occm_set_error("occm_rk45_stats: null handle"); return OCCM_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int M = rk->M;
+    if (status)     OCCM_CUDA_CHECK(cudaMemcpyAsync(status, rk->d.status, M * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (n_accepted) OCCM_CUDA_CHECK(cudaMemcpyAsync(n_accepted, rk->d.n_acc, M * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    if (n_rejected) OCCM_CUDA_CHECK(cudaMemcpyAsync(n_rejected, rk->d.n_rej, M * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    if (nfev)       OCCM_CUDA_CHECK(cudaMemcpyAsync(nfev, rk->d.nfev, M * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    if (t)          OCCM_CUDA_CHECK(cudaMemcpyAsync(t, rk->d.t, M * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (n_rows) {
+        // t_eval mode: rows written so far = out_hi; all-steps mode: n_rows
+        OCCM_CUDA_CHECK(cudaMemcpyAsync(n_rows, rk->prob.t_eval ? rk->d.out_hi : rk->d.n_rows, M * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    OCCM_CUDA_CHECK(cudaStreamSynchronize(st));
+    return OCCM_OK;
+}
+
+extern "C" int occm_rk45_get_state(occm_rk45* rk, double* y_out, void* stream) {
+    if (!rk || !y_out) { occm_set_error("occm_rk45_get_state: null argument"); return OCCM_ERR_INVALID; }
+    const long long total = (long long)rk->M * rk->sys->dev.ndof;
+    const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    occm_rk45_gather_state<<<grid, 256, 0, (cudaStream_t)stream>>>(rk->d, rk->M, rk->sys->dev.ndof, y_out);
+    OCCM_LAUNCH_CHECK("occm_rk45_gather_state");
+    return OCCM_OK;
+}
+
+extern "C" int occm_rk45_free(occm_rk45* rk) {
+    if (!rk) return OCCM_OK;
+    if (rk->h_running) cudaFreeHost(rk->h_running);
+    free(rk);
+    return OCCM_OK;
+}

@@ -1,0 +1,189 @@
+"""
+Device-resident system: uploads a ``HostSystem`` once (torch CUDA tensors own the memory) and drives the
+C ABI of liboccm_b200.so.  PyTorch is plumbing here (allocation, streams, distributed); all arithmetic on the
+solver path runs in the hand-written CUDA kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .system_solvers.export import HostSystem
+
+STATUS_MESSAGES = {
+    1: "The solver successfully reached the end of the integration interval.",
+    2: "Paused: output buffer full.",
+    0: "Still running.",
+    -1: "Required step size is less than spacing between numbers.",
+    -2: "Non-finite error estimate.",
+    -3: "Step budget exhausted.",
+}
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.OccmError('no CUDA device: the B200 solver path has no CPU fallback')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+@dataclass
+class MemberParams:
+    """Per-member ensemble parameters (device tensors or None)."""
+    n_members: int
+    k_scale: Optional[torch.Tensor] = None   # [M, n_rxn]
+    q_scale: Optional[torch.Tensor] = None   # [M]
+    bc_scale: Optional[torch.Tensor] = None  # [M]
+
+    def c_struct(self) -> _lib.Members:
+        return _lib.Members(self.n_members, _ptr(self.k_scale), _ptr(self.q_scale), _ptr(self.bc_scale))
+
+
+@dataclass
+class Rk45Result:
+    t: np.ndarray              # [T] (t_eval mode) or list of per-member arrays ("all" mode)
+    y: torch.Tensor            # device [M, T, n_save]  (t_eval mode)
+    status: np.ndarray
+    n_accepted: np.ndarray
+    n_rejected: np.ndarray
+    nfev: np.ndarray
+    y_final: Optional[torch.Tensor] = None
+
+
+class DeviceSystem:
+    def __init__(self, host: HostSystem):
+        self.lib = _lib.load()
+        self.dev = _require_cuda()
+        self.host = host
+        i32 = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32), device=self.dev)
+        f64 = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.dev)
+        self.row_ptr, self.row_src, self.row_w = i32(host.row_ptr), i32(host.row_src), f64(host.row_w)
+        if self.row_src.numel() == 0:       # keep valid pointers for empty operators
+            self.row_src = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            self.row_w = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        self.a = f64(host.a)
+        self.pulse_ptr, self.pulse_fn, self.pulse_w = i32(host.pulse_ptr), i32(host.pulse_fn), f64(host.pulse_w)
+        blob = host.tables.pack()
+        self.tables = torch.as_tensor(blob, device=self.dev)
+        self.fields = f64(host.fields)
+        self.n_rxn = host.tables.n_rxn
+        desc = _lib.SystemDesc(1 if host.model == 'pfr' else 0, host.S, host.n_models, host.P,
+                               _ptr(self.row_ptr), _ptr(self.row_src), _ptr(self.row_w), _ptr(self.a),
+                               _ptr(self.pulse_ptr), _ptr(self.pulse_fn), _ptr(self.pulse_w),
+                               _ptr(self.tables), blob.nbytes, _ptr(self.fields),
+                               0 if host.fields is None else host.fields.shape[0])
+        h = C.c_void_p()
+        _lib.check(self.lib.occm_system_create(C.byref(h), C.byref(desc)))
+        self.handle = h
+        self.ndof = host.ndof
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                self.lib.occm_system_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ fused RHS
+    def rhs(self, y: torch.Tensor, t, members: Optional[MemberParams] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """dy[m] = ddt(t[m], y[m]); y: device [M, ndof] in device layout (point-major, species innermost)."""
+        assert y.is_cuda and y.dtype == torch.float64 and y.is_contiguous()
+        M = 1 if y.dim() == 1 else y.shape[0]
+        assert y.numel() == M * self.ndof
+        mem = members if members is not None else MemberParams(M)
+        assert mem.n_members == M
+        if out is None:
+            out = torch.empty_like(y)
+        ms = mem.c_struct()
+        if isinstance(t, torch.Tensor):
+            assert t.is_cuda and t.dtype == torch.float64 and t.numel() == M
+            _lib.check(self.lib.occm_rhs(self.handle, C.byref(ms), t.data_ptr(), 0.0, y.data_ptr(), out.data_ptr(), _stream()))
+        else:
+            _lib.check(self.lib.occm_rhs(self.handle, C.byref(ms), None, float(t), y.data_ptr(), out.data_ptr(), _stream()))
+        return out
+
+    # ------------------------------------------------------------------ RK45
+    def rk45(self, y0: torch.Tensor, t_span: Sequence[float], *, rtol: float, atol: float, first_step: float,
+             t_eval: Optional[Sequence[float]] = None, save_idx: Optional[torch.Tensor] = None,
+             members: Optional[MemberParams] = None, max_steps: int = 0, all_capacity: int = 4096,
+             return_final: bool = False) -> Rk45Result:
+        """Batched scipy-compatible RK45. y0: device [M, ndof] (device layout)."""
+        assert y0.is_cuda and y0.dtype == torch.float64 and y0.is_contiguous()
+        M = 1 if y0.dim() == 1 else y0.shape[0]
+        assert y0.numel() == M * self.ndof
+        mem = members if members is not None else MemberParams(M)
+        assert mem.n_members == M
+        n_save = self.ndof if save_idx is None else int(save_idx.numel())
+        if save_idx is not None:
+            assert save_idx.is_cuda and save_idx.dtype == torch.int32
+        lib = self.lib
+        ws_bytes = lib.occm_rk45_workspace_bytes(self.handle, M)
+        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=self.dev)
+        ws_ptr = (ws.data_ptr() + 255) & ~255
+        all_mode = t_eval is None
+        if all_mode:
+            T = int(all_capacity)
+            te = None
+        else:
+            te_np = np.ascontiguousarray(np.asarray(t_eval, dtype=np.float64))
+            if te_np.ndim != 1 or te_np.size == 0:
+                raise ValueError("`t_eval` must be 1-dimensional.")
+            if np.any(te_np < min(t_span)) or np.any(te_np > max(t_span)):
+                raise ValueError("Values in `t_eval` are not within `t_span`.")
+            if np.any(np.diff(te_np) <= 0):
+                raise ValueError("Values in `t_eval` are not properly sorted.")
+            T = te_np.size
+            te = torch.as_tensor(te_np, device=self.dev)
+        out = torch.empty((M, T, n_save), dtype=torch.float64, device=self.dev)
+        out_t = torch.empty((M, T), dtype=torch.float64, device=self.dev)
+        prob = _lib.Rk45Problem(float(t_span[0]), float(t_span[1]), float(first_step), float(rtol), float(atol),
+                                y0.data_ptr(), _ptr(te), T, _ptr(save_idx), n_save, out.data_ptr(), out_t.data_ptr(),
+                                int(max_steps))
+        ms = mem.c_struct()
+        handle = C.c_void_p()
+        _lib.check(lib.occm_rk45_init(C.byref(handle), self.handle, C.byref(ms), C.byref(prob), ws_ptr, ws_bytes, _stream()))
+        try:
+            status = np.zeros(M, dtype=np.int32); n_acc = np.zeros(M, dtype=np.int64); n_rej = np.zeros(M, dtype=np.int64)
+            nfev = np.zeros(M, dtype=np.int64); t_now = np.zeros(M); n_rows = np.zeros(M, dtype=np.int32)
+            running = C.c_int32(0)
+            ts_all = [[] for _ in range(M)]; ys_all = [[] for _ in range(M)]
+            while True:
+                _lib.check(lib.occm_rk45_run(handle, 0, C.byref(running), _stream()))
+                _lib.check(lib.occm_rk45_stats(handle, status.ctypes.data, n_acc.ctypes.data, n_rej.ctypes.data,
+                                               nfev.ctypes.data, t_now.ctypes.data, n_rows.ctypes.data, _stream()))
+                if not all_mode:
+                    break
+                # harvest the rows written so far, un-pause and continue
+                for m in range(M):
+                    r = int(n_rows[m])
+                    if r:
+                        ts_all[m].append(out_t[m, :r].cpu().numpy())
+                        ys_all[m].append(out[m, :r].clone())
+                if not np.any(status == 2):
+                    break
+                _lib.check(lib.occm_rk45_resume(handle, _stream()))
+            y_final = None
+            if return_final:
+                y_final = torch.empty((M, self.ndof), dtype=torch.float64, device=self.dev)
+                _lib.check(lib.occm_rk45_get_state(handle, y_final.data_ptr(), _stream()))
+                torch.cuda.current_stream().synchronize()
+        finally:
+            lib.occm_rk45_free(handle)
+        if all_mode:
+            t_res = [np.concatenate(x) if x else np.zeros(0) for x in ts_all]
+            y_res = [torch.cat(x) if x else out[m, :0] for m, x in enumerate(ys_all)]
+            return Rk45Result(t_res, y_res, status, n_acc, n_rej, nfev, y_final)
+        return Rk45Result(te_np, out, status, n_acc, n_rej, nfev, y_final)

@@ -1,0 +1,90 @@
+"""
+Device replacement for ``openccm.system_solvers`` (/root/reference/openccm/system_solvers/__init__.py:38-81).
+
+``solve_system(model, model_network, config_parser, cmesh)`` has the reference's signature and return value
+``(c[S, n_points, T], t[T], inlet_map, outlet_map)``; the time integration runs on the GPU through
+liboccm_b200.so.  Selection is by ``[SIMULATION] solver``:
+
+    B200-RK45   adaptive Dormand-Prince, step-for-step mirror of scipy's RK45
+    B200-BDF    variable-order BDF with Newton + preconditioned GMRES (stiff networks)
+
+Any other solver name raises here (this package has no CPU path); ``openccm_b200.dropin.install()`` forwards
+those names to the reference's own scipy path when the reference is importable.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .export import HostSystem, export_system
+from .helper_functions import generate_t_eval
+
+DEVICE_SOLVERS = ('B200-RK45', 'B200-BDF')
+
+
+def is_device_solver(name: str) -> bool:
+    return name.upper() in DEVICE_SOLVERS
+
+
+def solve_system(model: str, model_network, config_parser, cmesh, *, return_info: bool = False):
+    """Drop-in for openccm.system_solvers.solve_system (system_solvers/__init__.py:38-81)."""
+    import torch
+    from ..device import DeviceSystem, STATUS_MESSAGES
+
+    print("Solving simulation")
+    cp = config_parser
+    t_span = cp.get_list(['SIMULATION', 't_span'], float)
+    first_timestep = cp.get_item(['SIMULATION', 'first_timestep'], float)
+    atol = cp.get_item(['SIMULATION', 'atol'], float)
+    rtol = cp.get_item(['SIMULATION', 'rtol'], float)
+    solver = cp.get_item(['SIMULATION', 'solver'], str).upper()
+    assert first_timestep > 0                                  # cstr_system.py:95 / pfr_system.py:95
+    if solver not in DEVICE_SOLVERS:
+        raise ValueError(f"solver = {solver!r} is not a device solver; use one of {DEVICE_SOLVERS} "
+                         f"(this package has no CPU integration path)")
+    t_eval = generate_t_eval(cp)
+    model = model.lower()
+    host = export_system(model, model_network, cp, cmesh)
+    dev = DeviceSystem(host)
+    y0 = torch.as_tensor(host.to_device_layout(host.c0.reshape(-1)), device=dev.dev).reshape(1, -1)
+
+    if solver == 'B200-RK45':
+        res = dev.rk45(y0, t_span, rtol=rtol, atol=atol, first_step=first_timestep, t_eval=t_eval)
+    else:
+        from ..bdf import solve_bdf
+        res = solve_bdf(dev, y0, t_span, rtol=rtol, atol=atol, first_step=first_timestep, t_eval=t_eval)
+    status = int(res.status[0])
+    message = STATUS_MESSAGES.get(status, str(status))
+    if model == 'pfr':
+        assert status == 1, message                            # pfr_system.py:192 (the CSTR path does not check)
+    if t_eval is None:
+        ts = np.asarray(res.t[0]); y = res.y[0].cpu().numpy()
+    else:
+        n_rows = len(res.t) if status == 1 else int(np.searchsorted(res.t, res.t_reached[0], side='right')) \
+            if hasattr(res, 't_reached') else len(res.t)
+        ts = np.asarray(res.t)[:n_rows]; y = res.y[0, :n_rows].cpu().numpy()
+    # [T, n_points, S] -> [S, n_points, T]   (cstr_system.py:152-154)
+    c = np.ascontiguousarray(y.reshape(len(ts), host.n_points, host.S).transpose(2, 1, 0))
+
+    if model == 'pfr' and host.coupling is not None and len(host.coupling) and host.coupling[0, 0] > 0:
+        _dae_residual_warning(c, host, atol)                   # pfr_system.py:198-212
+    print("Done solving simulation")
+    out = (c, ts, dict(host.inlet_map), dict(host.outlet_map))
+    if return_info:
+        return out + (dict(status=status, message=message, nfev=int(res.nfev[0]), n_accepted=int(res.n_accepted[0]),
+                           n_rejected=int(res.n_rejected[0])),)
+    return out
+
+
+def _dae_residual_warning(c: np.ndarray, host: HostSystem, atol: float) -> None:
+    """How well the inlet-node algebraic constraint c_in = sum w c_out was kept (pfr_system.py:198-212)."""
+    cpl = host.coupling
+    S, _, T = c.shape
+    acc = np.zeros((S, host.n_points, T))
+    for s in range(S):
+        np.add.at(acc[s], cpl[:, 0], host.Q_weight[cpl[:, 1]][:, None] * c[s, cpl[:, 2], :])
+    nodes = np.unique(cpl[:, 0])
+    max_error = float(np.max(np.abs(acc[:, nodes, :] - c[:, nodes, :])))
+    if max_error > atol:
+        print(f"WARNING: Maximum absolute error in solving inlet BC for PFRs is {max_error:.3e} but absolute tolerance is {atol:.3e}.")

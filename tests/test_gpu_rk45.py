@@ -1,0 +1,47 @@
+"""GPU parity of the batched RK45 integrator (through the reference-shaped ``solve_system``) against the
+reference's golden solves.  Acceptance band of the north star: rtol 1e-6 / atol 1e-10 at every output time; the
+step-exact mirror is held to a much tighter band here (rtol 1e-9 / atol 1e-12)."""
+import numpy as np
+import pytest
+
+import cases as C
+from _util import load_golden, setup_case
+
+pytestmark = pytest.mark.gpu
+
+# Linear cases that sit at steady state for most of the interval: there the RK45 error estimate is pure round-off, the
+# step sequence is governed by noise, and scipy itself moves by ~1e-8 when its RHS is perturbed by 1e-16 relative
+# (measured in the build container).  They are held to the acceptance band only.
+ROUNDOFF_LIMITED = {'cstr_net9_tracer', 'cstr_reversible', 'pfr_chains_tracer'}
+
+RK_CASES = [n for n in sorted(C.CASES) if 'RK45' in C.CASES[n].get('solvers', ('RK45', 'LSODA'))]
+
+
+@pytest.mark.parametrize('name', RK_CASES)
+def test_solve_system_matches_reference_rk45(name, tmp_path):
+    from openccm_b200.system_solvers import solve_system
+    g = load_golden(name)
+    cp, cmesh, net, mn = setup_case(name, 'B200-RK45', tmp_path)
+    c, t, imap, omap, info = solve_system(C.CASES[name]['model'], mn, cp, cmesh, return_info=True)
+    assert info['status'] == 1
+    assert c.shape == g['c_RK45'].shape
+    np.testing.assert_allclose(t, g['t_RK45'], rtol=0, atol=1e-14)
+    ref = g['c_RK45']
+    # north-star acceptance band at every output time
+    assert np.all(np.abs(c - ref) <= 1e-10 + 1e-6 * np.abs(ref))
+    if name not in ROUNDOFF_LIMITED:
+        np.testing.assert_allclose(c, ref, rtol=1e-9, atol=2e-12)
+    assert abs(info['nfev'] - int(g['nfev_RK45'])) <= 12
+
+
+@pytest.mark.parametrize('name', ['cstr_irreversible', 'cstr_net12_nacl', 'pfr_net8', 'cstr_net20_timebc'])
+def test_all_steps_mode_reproduces_scipy_step_sequence(name, tmp_path):
+    from openccm_b200.system_solvers import solve_system
+    g = load_golden(name)
+    cp, cmesh, net, mn = setup_case(name, 'B200-RK45', tmp_path, t_eval='all')
+    c, t, *_ = solve_system(C.CASES[name]['model'], mn, cp, cmesh)
+    assert t.shape == g['t_RK45_all'].shape
+    # same number of accepted steps; step times agree up to the round-off sensitivity of the error estimate
+    # (a difference of small numbers at rtol 1e-8), the states are compared at (slightly) shifted times
+    np.testing.assert_allclose(t, g['t_RK45_all'], rtol=1e-5)
+    np.testing.assert_allclose(c, g['c_RK45_all'], rtol=2e-5, atol=1e-8)

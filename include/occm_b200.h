@@ -65,7 +65,7 @@ typedef enum {
  *         inlet node (j, 0): sum_k row_w[k] * Y_k,
  *         Y_k = d/dt c at the outlet node of PFR row_src[k] (recomputed in place)  if row_src[k] >= 0    pfr_system.py:313-314
  *             = bc_scale * g'_{b,s}(t)                                              otherwise             :191-196
- * pulse_*: CSR by model of smoothed point-mass sources applied to every non-inlet node of the model
+ * pulse_*: CSR by model of smoothed point-mass sources applied to every non-inlet node of the model (CSTR: the node)
  *          (boundary_and_initial_conditions.py:174-180); may be NULL.
  * tables:  packed mechanism blob (stoichiometry terms, rate-expression and boundary-function byte code), layout in
  *          openccm_b200/csrc/occm_tables.h; built on the host by openccm_b200/system_solvers/tables.py from the same
@@ -89,6 +89,13 @@ typedef struct {
     int32_t        tables_bytes;
     const double*  fields;    /* or NULL */
     int32_t        n_fields;
+    /* CSTR only, optional (ell_width = 0: CSR only): the first ell_width entries of every row again in ELL form,
+     * column-major [ell_width][n_models], so the kernel reaches them without the row_ptr indirection.
+     * ell_src: >= 0 source CSTR | -1-b boundary group | INT32_MIN padding | INT32_MIN+1 in the last column = "entries
+     * ell_width-1.. of this row continue in the CSR arrays". */
+    int32_t        ell_width;
+    const int32_t* ell_src;
+    const double*  ell_w;
 } occm_system_desc;
 
 /* Per-member parameters of an ensemble (all device pointers, any may be NULL = 1.0).

@@ -23,7 +23,8 @@ class SystemDesc(C.Structure):
     _fields_ = [('model', C.c_int32), ('n_species', C.c_int32), ('n_models', C.c_int32), ('points_per_model', C.c_int32),
                 ('row_ptr', C.c_void_p), ('row_src', C.c_void_p), ('row_w', C.c_void_p), ('a', C.c_void_p),
                 ('pulse_ptr', C.c_void_p), ('pulse_fn', C.c_void_p), ('pulse_w', C.c_void_p),
-                ('tables', C.c_void_p), ('tables_bytes', C.c_int32), ('fields', C.c_void_p), ('n_fields', C.c_int32)]
+                ('tables', C.c_void_p), ('tables_bytes', C.c_int32), ('fields', C.c_void_p), ('n_fields', C.c_int32),
+                ('ell_width', C.c_int32), ('ell_src', C.c_void_p), ('ell_w', C.c_void_p)]
 
 
 class Members(C.Structure):

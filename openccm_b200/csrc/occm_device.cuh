@@ -2,8 +2,10 @@
 //
 // Thread mapping used everywhere: one thread per flat state element e = point * S + species of one ensemble
 // member, consecutive threads = consecutive addresses (species innermost), so every own-element load/store of
-// y, K_i, ... is a fully coalesced 8-byte-per-lane access.  A CTA works on a "chunk" = OCCM_BLOCK consecutive
-// elements of one member; the stage state of the points the chunk touches is staged in shared memory so that
+// y, K_i, ... is a coalesced 8-byte-per-lane access.  A CTA works on "sub-chunks" of tc = OCCM_BLOCK / S whole
+// points (tc * S <= OCCM_BLOCK elements), E of them per loop trip for memory-level parallelism; because a
+// sub-chunk is a multiple of S elements, thread tid always owns species tid % S and keeps that species'
+// stoichiometric terms in registers.  The stage state of the sub-chunk's points is staged in shared memory so that
 // the reaction terms (which couple the S species of a point) and the PFR upwind difference read it from there.
 #pragma once
 #include <cuda_runtime.h>
@@ -17,6 +19,9 @@
 struct OccmSysDev {
     int model, S, n_models, P;
     long long n_points, ndof;
+    int tc;                     // points per sub-chunk = OCCM_BLOCK / S (every thread keeps one species)
+    int ell_k;                  // CSTR: ELL width (0 = CSR only)
+    const int* ell_src; const double* ell_w;   // column-major [ell_k][n_models]
     const int* row_ptr; const int* row_src; const double* row_w; const double* a;
     const int* pulse_ptr; const int* pulse_fn; const double* pulse_w;
     const int* tables; int tables_bytes;
@@ -136,10 +141,12 @@ __device__ __forceinline__ double occm_bc_value(const OccmTab& T, int b, int s, 
 }
 
 // Net reaction rate of species s at a point whose concentrations are row(0..S-1)
-// (the generated `_ddt[s, :] += ...` lines of system_solvers/reactions.py:450-455).
+// (the generated `_ddt[s, :] += ...` lines of system_solvers/reactions.py:450-455).  Generic table walk: used for
+// species whose terms do not fit the register-resident form below (more than OCCM_NT terms, total order above
+// OCCM_NF, or a byte-code rate factor such as Monod).
 template <class Row>
-__device__ __forceinline__ double occm_reaction(const OccmTab& T, int s, const Row& row, const double* ksc, double t,
-                                                long long point, const OccmSysDev& sys) {
+__device__ __noinline__ double occm_reaction_tables(const OccmTab& T, int s, const Row& row, const double* ksc, double t,
+                                                    int point, const OccmSysDev& sys) {
     double acc = 0.0;
     const int tb = T.term_ptr[s], te = T.term_ptr[s + 1];
     for (int k = tb; k < te; ++k) {
@@ -149,13 +156,70 @@ __device__ __forceinline__ double occm_reaction(const OccmTab& T, int s, const R
         for (int f = fb; f < fe; ++f) {
             const double x = row(T.fac_sp[f]);
             const int ord = T.fac_ord[f];
-            double p = x;
-            for (int q = 1; q < ord; ++q) p *= x;
-            v *= p;
+            for (int q = 0; q < ord; ++q) v *= x;
         }
         const int prog = T.term_prog[k];
-        if (prog >= 0) v *= occm_vm_eval(T, prog, row, t, point, sys.fields, sys.n_points);
+        if (prog >= 0) v *= occm_vm_eval(T, prog, row, t, (long long)point, sys.fields, sys.n_points);
         acc += v;
+    }
+    return acc;
+}
+
+// Register-resident reaction program of ONE species: a thread keeps its species for the whole kernel (chunks are a
+// multiple of S elements), so its stoichiometric terms are decoded from the shared-memory tables once.
+#define OCCM_NT 4   // terms
+#define OCCM_NF 3   // factor slots per term (a factor of order n occupies n slots)
+struct OccmRxnRegs {
+    double coeff[OCCM_NT];
+    unsigned meta[OCCM_NT];   // rxn | f0 << 8 | f1 << 16 | f2 << 24, factor 0xff = unused
+    int n;                    // number of terms, or -1: fall back to occm_reaction_tables
+};
+
+__device__ __forceinline__ OccmRxnRegs occm_rxn_regs(const OccmTab& T, int s) {
+    OccmRxnRegs R;
+#pragma unroll
+    for (int i = 0; i < OCCM_NT; ++i) { R.coeff[i] = 0.0; R.meta[i] = 0xffffff00u; }
+    const int tb = T.term_ptr[s], te = T.term_ptr[s + 1];
+    R.n = te - tb;
+    if (R.n > OCCM_NT) { R.n = -1; return R; }
+#pragma unroll
+    for (int i = 0; i < OCCM_NT; ++i) {
+        if (i < R.n) {
+            const int k = tb + i;
+            R.coeff[i] = T.term_coeff[k];
+            unsigned meta = (unsigned)T.term_rxn[k] & 0xffu;
+            if (T.term_rxn[k] > 255 || T.term_prog[k] >= 0) R.n = -1;
+            int slot = 0;
+            for (int f = T.fac_ptr[k]; f < T.fac_ptr[k + 1]; ++f)
+                for (int q = 0; q < T.fac_ord[f]; ++q) {
+                    if (slot < OCCM_NF) meta |= ((unsigned)T.fac_sp[f] & 0xffu) << (8 + 8 * slot);
+                    ++slot;
+                }
+            for (int q = slot; q < OCCM_NF; ++q) meta |= 0xffu << (8 + 8 * q);
+            if (slot > OCCM_NF) R.n = -1;
+            R.meta[i] = meta;
+        }
+    }
+    return R;
+}
+
+template <class Row>
+__device__ __forceinline__ double occm_reaction(const OccmRxnRegs& R, const OccmTab& T, int s, const Row& row,
+                                                const double* ksc, double t, int point, const OccmSysDev& sys) {
+    if (R.n < 0) return occm_reaction_tables(T, s, row, ksc, t, point, sys);
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < OCCM_NT; ++i) {
+        if (i < R.n) {
+            const unsigned m = R.meta[i];
+            double v = R.coeff[i];
+            if (ksc) v *= ksc[m & 0xffu];
+            const unsigned f0 = (m >> 8) & 0xffu, f1 = (m >> 16) & 0xffu, f2 = m >> 24;
+            if (f0 != 0xffu) v *= row((int)f0);
+            if (f1 != 0xffu) v *= row((int)f1);
+            if (f2 != 0xffu) v *= row((int)f2);
+            acc += v;
+        }
     }
     return acc;
 }
@@ -163,79 +227,47 @@ __device__ __forceinline__ double occm_reaction(const OccmTab& T, int s, const R
 __device__ __forceinline__ double occm_pulses(const OccmSysDev& sys, const OccmTab& T, int model, int s, double t) {
     double acc = 0.0;
     if (sys.pulse_ptr) {
-        for (int k = sys.pulse_ptr[model]; k < sys.pulse_ptr[model + 1]; ++k)
-            acc += sys.pulse_w[k] * occm_bc_value(T, sys.pulse_fn[k], s, t);
+        for (int k = __ldg(sys.pulse_ptr + model); k < __ldg(sys.pulse_ptr + model + 1); ++k)
+            acc += __ldg(sys.pulse_w + k) * occm_bc_value(T, __ldg(sys.pulse_fn + k), s, t);
     }
     return acc;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// d/dt of element (point p, species s).
-//   in(e)    : stage state at flat element e of this member, read from global memory (gathers)
-//   tile     : shared-memory copy of the stage state for elements [tile_lo, ...) covering this chunk's points
-// CSTR: cstr_system.py:194-203.   PFR: pfr_system.py:290-316.
-template <int MODEL, class In>
-__device__ __forceinline__ double occm_ddt_element(const OccmSysDev& sys, const OccmTab& T, const In& in,
-                                                   const double* tile, long long tile_lo, long long p, int s,
-                                                   double t, double qs, double bs, const double* ksc) {
-    const int S = sys.S;
-    const double* myrow = tile + (p * S - tile_lo);
-    auto row = [myrow](int sp) { return myrow[sp]; };
-    if (MODEL == 0) {   // CSTR
-        const int j = (int)p;
-        double acc = 0.0;
-        const int kb = __ldg(sys.row_ptr + j), ke = __ldg(sys.row_ptr + j + 1);
-        for (int k = kb; k < ke; ++k) {
-            const int src = __ldg(sys.row_src + k);
-            const double w = __ldg(sys.row_w + k);
-            if (src >= 0) acc += w * (src == j ? myrow[s] : in((long long)src * S + s));
-            else          acc += w * (bs * occm_bc_value(T, -1 - src, s, t));
-        }
-        return qs * acc + occm_pulses(sys, T, j, s, t) + occm_reaction(T, s, row, ksc, t, p, sys);
-    } else {
-        const int P = sys.P;
-        const int k = (int)(p / P);
-        const int i = (int)(p - (long long)k * P);
-        if (i > 0) {
-            const double conv = -(qs * __ldg(sys.a + k)) * (myrow[s] - myrow[s - S]);
-            return conv + occm_pulses(sys, T, k, s, t) + occm_reaction(T, s, row, ksc, t, p, sys);
-        }
-        double acc = 0.0;
-        const int eb = __ldg(sys.row_ptr + k), ee = __ldg(sys.row_ptr + k + 1);
-        for (int e = eb; e < ee; ++e) {
-            const int src = __ldg(sys.row_src + e);
-            const double w = __ldg(sys.row_w + e);
-            if (src >= 0) {
-                const long long o = (long long)P * (src + 1) - 1;   // outlet node of the upstream PFR
-                auto orow = [&in, o, S](int sp) { return in(o * S + sp); };
-                double d = -(qs * __ldg(sys.a + src)) * (in(o * S + s) - in((o - 1) * S + s));
-                d += occm_pulses(sys, T, src, s, t);
-                d += occm_reaction(T, s, orow, ksc, t, o, sys);
-                acc += w * d;
-            } else {
-                acc += w * (bs * occm_bc_value(T, -1 - src, s, t));
-            }
-        }
-        return acc;
-    }
+// ELL slot encoding of the CSTR transport operator (built by the host from the CSR rows)
+#define OCCM_ELL_EMPTY    ((int)0x80000000)        // padding
+#define OCCM_ELL_CONTINUE ((int)0x80000001)        // last column only: entries K-1.. of this row are in the CSR arrays
+
+// One CSR/ELL entry of a CSTR row: w * c[src, s]  or  w * bc_scale * g_{b,s}(t)   (cstr_system.py:121-135,197-199)
+template <class In>
+__device__ __forceinline__ double occm_cstr_entry(const OccmTab& T, const In& in, int src, double w, int j, int s, int S,
+                                                  double own, double t, double bs) {
+    if (src >= 0) return w * (src == j ? own : in(src * S + s));
+    return w * (bs * occm_bc_value(T, -1 - src, s, t));
 }
 
-// Chunk geometry: which points a chunk of OCCM_BLOCK elements starting at e0 touches and where its tile starts.
-struct OccmChunk {
-    long long e0, e1;        // element range [e0, e1)
-    long long tile_lo, tile_hi;  // staged element range
-};
-
-__device__ __forceinline__ OccmChunk occm_chunk(const OccmSysDev& sys, int ci) {
-    OccmChunk c;
-    c.e0 = (long long)ci * OCCM_BLOCK;
-    c.e1 = c.e0 + OCCM_BLOCK < sys.ndof ? c.e0 + OCCM_BLOCK : sys.ndof;
-    long long p_first = c.e0 / sys.S;
-    long long p_last = (c.e1 - 1) / sys.S;
-    if (sys.model == 1 && p_first > 0) p_first -= 1;       // upwind neighbour of the first point
-    c.tile_lo = p_first * sys.S;
-    c.tile_hi = (p_last + 1) * sys.S;
-    return c;
+// d/dt of the inlet node of PFR k: sum over inflowing connections of w * (d/dt of the upstream outlet node), plus the
+// differentiated domain boundary conditions (pfr_system.py:304-314).
+template <class In>
+__device__ __noinline__ double occm_pfr_inlet(const OccmSysDev& sys, const OccmTab& T, const OccmRxnRegs& R, const In& in,
+                                              int k, int s, double t, double qs, double bs, const double* ksc) {
+    const int S = sys.S, P = sys.P;
+    double acc = 0.0;
+    const int eb = __ldg(sys.row_ptr + k), ee = __ldg(sys.row_ptr + k + 1);
+    for (int e = eb; e < ee; ++e) {
+        const int src = __ldg(sys.row_src + e);
+        const double w = __ldg(sys.row_w + e);
+        if (src >= 0) {
+            const int o = P * (src + 1) - 1;                 // outlet node of the upstream PFR
+            auto orow = [&in, o, S](int sp) { return in(o * S + sp); };
+            double d = -(qs * __ldg(sys.a + src)) * (in(o * S + s) - in((o - 1) * S + s));
+            d += occm_pulses(sys, T, src, s, t);
+            d += occm_reaction(R, T, s, orow, ksc, t, o, sys);
+            acc += w * d;
+        } else {
+            acc += w * (bs * occm_bc_value(T, -1 - src, s, t));
+        }
+    }
+    return acc;
 }
 
 // deterministic block-wide sum (fixed tree), result valid in thread 0

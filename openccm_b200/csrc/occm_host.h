@@ -45,8 +45,8 @@ static inline OccmMemDev occm_mem_dev(const occm_members* mem, int fallback_M) {
 }
 
 // dynamic shared memory of the element kernels: tables + tile + k_scale row + reduction scratch
-static inline size_t occm_elem_smem(const occm_system* sys) {
-    return sys->smem_tables + sizeof(double) * (OCCM_BLOCK + 3 * sys->dev.S + sys->dev.n_rxn + 40);
+static inline size_t occm_elem_smem(const occm_system* sys, int E) {
+    return sys->smem_tables + sizeof(double) * ((size_t)E * (OCCM_BLOCK + OCCM_MAX_S) + sys->dev.n_rxn + 42);
 }
 
 // persistent grid: a multiple of the SM count, capped by the amount of work

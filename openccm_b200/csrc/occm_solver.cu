@@ -12,6 +12,8 @@
 #include <atomic>
 #include "occm_host.h"
 
+#define OCCM_E 2   // sub-chunks of tc points processed per loop trip of a CTA (memory-level parallelism)
+
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[1024] = "";
 static std::atomic<long long> g_launches{0};
@@ -57,14 +59,19 @@ extern "C" int occm_system_create(occm_system** out, const occm_system_desc* d) 
     v.tables = (const int*)d->tables; v.tables_bytes = d->tables_bytes;
     v.fields = d->fields; v.n_fields = d->n_fields;
     v.n_rxn = hdr[OCCM_H_NRXN];
-    v.chunks_per_member = (int)((ndof + OCCM_BLOCK - 1) / OCCM_BLOCK);
+    v.tc = OCCM_BLOCK / d->n_species;
+    v.chunks_per_member = (int)((n_points + (long long)OCCM_E * v.tc - 1) / ((long long)OCCM_E * v.tc));
+    v.ell_k = d->model == OCCM_MODEL_CSTR ? d->ell_width : 0;
+    v.ell_src = d->ell_src; v.ell_w = d->ell_w;
+    if (v.ell_k < 0 || v.ell_k > 64 || (v.ell_k > 0 && (!d->ell_src || !d->ell_w))) { occm_set_error("bad ELL description"); free(s); return OCCM_ERR_INVALID; }
+    if (ndof >= (1ll << 31)) { occm_set_error("ndof per member must fit in int32"); free(s); return OCCM_ERR_INVALID; }
     s->smem_tables = (size_t)d->tables_bytes;
     int dev = 0;
     OCCM_CUDA_CHECK(cudaGetDevice(&dev));
     OCCM_CUDA_CHECK(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev));
     int max_smem = 0;
     OCCM_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    if (occm_elem_smem(s) > (size_t)max_smem) {
+    if (occm_elem_smem(s, OCCM_E) > (size_t)max_smem) {
         occm_set_error("mechanism tables (%d B) do not fit in shared memory (%d B)", d->tables_bytes, max_smem);
         free(s);
         return OCCM_ERR_UNSUPPORTED;
@@ -124,30 +131,46 @@ struct occm_rk45 {
 
 // ------------------------------------------------------------------------------------------------ stage kernel
 // STAGE 0: plain RHS (y_in -> dy_out).  STAGE s in 2..7: Dormand-Prince stage s of rk_step (rk.py:14-71).
-template <int MODEL, int STAGE>
-__global__ void __launch_bounds__(OCCM_BLOCK)
+// E sub-chunks of tc points are processed per loop trip (independent loads of all E are issued before any is used).
+template <int STAGE>
+struct OccmStageIn {       // the stage state this kernel differentiates, as a function of the flat element index
+    const double* a; const double* b; double hb;
+    __device__ __forceinline__ double operator()(int e) const {
+        if (STAGE == 2) return __ldg(a + e) + (dp::A21 * __ldg(b + e)) * hb;   // y + h * a21 * K1 formed on the fly
+        return __ldg(a + e);
+    }
+};
+
+template <int MODEL, int STAGE, int E>
+__global__ void __launch_bounds__(OCCM_BLOCK, 2)
 occm_stage(const OccmSysDev sys, const OccmMemDev mem, const OccmRkDev rk, const double* __restrict__ t_dev, double t_scalar,
            const double* __restrict__ y_in, double* __restrict__ dy_out) {
     extern __shared__ double smem_d[];
     const OccmTab T = occm_load_tables(sys.tables, sys.tables_bytes, reinterpret_cast<int*>(smem_d));
+    const int S = sys.S, TC = sys.tc, CE = TC * S;
+    const int tstride = OCCM_BLOCK + OCCM_MAX_S;            // [halo point | sub-chunk]
     double* tile = smem_d + (sys.tables_bytes >> 3);
-    double* ksc_s = tile + OCCM_BLOCK + 3 * sys.S;
-    double* scratch = ksc_s + sys.n_rxn;
-    const int S = sys.S;
+    double* ksc_s = tile + E * tstride;
+    double* scratch = ksc_s + ((sys.n_rxn + 1) & ~1);
+    const int tid = threadIdx.x;
+    const bool lane_on = tid < CE;
+    const int pl = tid / S;
+    const int s = tid - pl * S;
+    const OccmRxnRegs R = occm_rxn_regs(T, lane_on ? s : 0);
+    const int n_points = (int)sys.n_points;
     const int cpm = sys.chunks_per_member;
-    const long long total = (long long)mem.M * cpm;
+    const unsigned total = (unsigned)mem.M * (unsigned)cpm;
 
-    for (long long c = blockIdx.x; c < total; c += gridDim.x) {
-        const int m = (int)(c / cpm);
-        const int ci = (int)(c - (long long)m * cpm);
+    for (unsigned c = blockIdx.x; c < total; c += gridDim.x) {
+        const int m = (int)(c / (unsigned)cpm);
+        const int ci = (int)(c - (unsigned)m * (unsigned)cpm);
         if (STAGE != 0 && rk.status[m] != OCCM_MEMBER_RUNNING) continue;   // uniform over the CTA
-        const OccmChunk ch = occm_chunk(sys, ci);
         const long long base = (long long)m * sys.ndof;
         const double qs = mem.q_scale ? __ldg(mem.q_scale + m) : 1.0;
         const double bs = mem.bc_scale ? __ldg(mem.bc_scale + m) : 1.0;
         const double* ksc = nullptr;
         if (mem.k_scale) {
-            for (int r = threadIdx.x; r < sys.n_rxn; r += OCCM_BLOCK) ksc_s[r] = __ldg(mem.k_scale + (long long)m * sys.n_rxn + r);
+            for (int r = tid; r < sys.n_rxn; r += OCCM_BLOCK) ksc_s[r] = __ldg(mem.k_scale + (long long)m * sys.n_rxn + r);
             ksc = ksc_s;
         }
         double t_stage, h = 0.0;
@@ -164,66 +187,137 @@ occm_stage(const OccmSysDev sys, const OccmMemDev mem, const OccmRkDev rk, const
             t_stage = STAGE == 2 ? t0 + dp::C2 * h : STAGE == 3 ? t0 + dp::C3 * h : STAGE == 4 ? t0 + dp::C4 * h
                     : STAGE == 5 ? t0 + dp::C5 * h : t0 + h;
         }
-        // the stage state this kernel differentiates
-        const double* sin_ = STAGE == 0 ? y_in + base
-                           : STAGE == 3 || STAGE == 5 ? rk.YS[0] + base
-                           : STAGE == 4 || STAGE == 6 ? rk.YS[1] + base
-                           : STAGE == 7 ? rk.Y[par ^ 1] + base : nullptr;
-        auto in = [=](long long e) -> double {
-            if (STAGE == 2) return __ldg(y + e) + (dp::A21 * __ldg(k1 + e)) * h;     // y + h * a21 * K1, formed on the fly
-            return __ldg(sin_ + e);
-        };
-        // stage the points of this chunk
-        for (long long e = ch.tile_lo + threadIdx.x; e < ch.tile_hi; e += OCCM_BLOCK) tile[e - ch.tile_lo] = in(e);
+        OccmStageIn<STAGE> in;
+        in.a = STAGE == 0 ? y_in + base : STAGE == 2 ? y
+             : STAGE == 3 || STAGE == 5 ? rk.YS[0] + base
+             : STAGE == 4 || STAGE == 6 ? rk.YS[1] + base : rk.Y[par ^ 1] + base;
+        in.b = k1; in.hb = h;
+
+        // ---- phase A: own values of all E sub-chunks -> shared tile
+        const int p0 = ci * (E * TC);
+        int pt[E]; bool ok[E]; double own[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            pt[i] = p0 + i * TC + pl;
+            ok[i] = lane_on && pt[i] < n_points;
+            own[i] = ok[i] ? in(pt[i] * S + s) : 0.0;
+        }
+        if (MODEL == 1 && tid < S) {           // upwind neighbour point of each sub-chunk's first point
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                const int pp = p0 + i * TC - 1;
+                tile[i * tstride + OCCM_MAX_S - S + tid] = (pp >= 0 && pp < n_points) ? in(pp * S + tid) : 0.0;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < E; ++i) tile[i * tstride + OCCM_MAX_S + tid] = own[i];
         __syncthreads();
 
-        const long long e = ch.e0 + threadIdx.x;
+        // ---- phase B: transport + reactions
+        double f[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) f[i] = 0.0;
+        if (MODEL == 0) {
+            const int K = sys.ell_k;
+            const int N = sys.n_models;
+#pragma unroll 4
+            for (int k = 0; k < K; ++k) {
+                int src[E]; double w[E];
+#pragma unroll
+                for (int i = 0; i < E; ++i) {
+                    src[i] = ok[i] ? __ldg(sys.ell_src + (long long)k * N + pt[i]) : OCCM_ELL_EMPTY;
+                    w[i] = ok[i] ? __ldg(sys.ell_w + (long long)k * N + pt[i]) : 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < E; ++i) {
+                    if (src[i] == OCCM_ELL_EMPTY) continue;
+                    if (src[i] == OCCM_ELL_CONTINUE) {       // rare: row longer than the ELL width
+                        for (int q = __ldg(sys.row_ptr + pt[i]) + K - 1; q < __ldg(sys.row_ptr + pt[i] + 1); ++q)
+                            f[i] += occm_cstr_entry(T, in, __ldg(sys.row_src + q), __ldg(sys.row_w + q), pt[i], s, S, own[i], t_stage, bs);
+                    } else {
+                        f[i] += occm_cstr_entry(T, in, src[i], w[i], pt[i], s, S, own[i], t_stage, bs);
+                    }
+                }
+            }
+            if (K == 0) {                                     // CSR only
+#pragma unroll
+                for (int i = 0; i < E; ++i)
+                    if (ok[i])
+                        for (int q = __ldg(sys.row_ptr + pt[i]); q < __ldg(sys.row_ptr + pt[i] + 1); ++q)
+                            f[i] += occm_cstr_entry(T, in, __ldg(sys.row_src + q), __ldg(sys.row_w + q), pt[i], s, S, own[i], t_stage, bs);
+            }
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                if (!ok[i]) continue;
+                const double* myrow = tile + i * tstride + OCCM_MAX_S + pl * S;
+                auto row = [myrow](int sp) { return myrow[sp]; };
+                f[i] = qs * f[i] + occm_pulses(sys, T, pt[i], s, t_stage) + occm_reaction(R, T, s, row, ksc, t_stage, pt[i], sys);
+            }
+        } else {
+            const int P = sys.P;
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                if (!ok[i]) continue;
+                const int k = pt[i] / P;
+                const int node = pt[i] - k * P;
+                if (node > 0) {
+                    const double* myrow = tile + i * tstride + OCCM_MAX_S + pl * S;
+                    auto row = [myrow](int sp) { return myrow[sp]; };
+                    const double conv = -(qs * __ldg(sys.a + k)) * (own[i] - myrow[s - S]);
+                    f[i] = conv + occm_pulses(sys, T, k, s, t_stage) + occm_reaction(R, T, s, row, ksc, t_stage, pt[i], sys);
+                } else {
+                    f[i] = occm_pfr_inlet(sys, T, R, in, k, s, t_stage, qs, bs, ksc);
+                }
+            }
+        }
+
+        // ---- phase C: stage epilogue (next stage state / y_new / error estimate)
         double err2 = 0.0;
-        if (e < ch.e1) {
-            const long long p = e / S;
-            const int s = (int)(e - p * S);
-            const double f = occm_ddt_element<MODEL>(sys, T, in, tile, ch.tile_lo, p, s, t_stage, qs, bs, ksc);
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            if (!ok[i]) continue;
+            const int e = pt[i] * S + s;
             if (STAGE == 0) {
-                dy_out[base + e] = f;
+                dy_out[base + e] = f[i];
             } else {
-                const double ye = __ldg(y + e), k1e = __ldg(k1 + e);
+                const double ye = STAGE == 2 ? __ldg(y + e) : __ldg(y + e), k1e = __ldg(k1 + e);
                 if (STAGE == 2) {
-                    rk.K2[base + e] = f;
-                    rk.YS[0][base + e] = ye + (dp::A31 * k1e + dp::A32 * f) * h;
+                    rk.K2[base + e] = f[i];
+                    rk.YS[0][base + e] = ye + (dp::A31 * k1e + dp::A32 * f[i]) * h;
                 } else if (STAGE == 3) {
-                    rk.K3[base + e] = f;
+                    rk.K3[base + e] = f[i];
                     const double k2 = __ldg(rk.K2 + base + e);
-                    rk.YS[1][base + e] = ye + (dp::A41 * k1e + dp::A42 * k2 + dp::A43 * f) * h;
+                    rk.YS[1][base + e] = ye + (dp::A41 * k1e + dp::A42 * k2 + dp::A43 * f[i]) * h;
                 } else if (STAGE == 4) {
-                    rk.K4[base + e] = f;
+                    rk.K4[base + e] = f[i];
                     const double k2 = __ldg(rk.K2 + base + e), k3 = __ldg(rk.K3 + base + e);
-                    rk.YS[0][base + e] = ye + (dp::A51 * k1e + dp::A52 * k2 + dp::A53 * k3 + dp::A54 * f) * h;
+                    rk.YS[0][base + e] = ye + (dp::A51 * k1e + dp::A52 * k2 + dp::A53 * k3 + dp::A54 * f[i]) * h;
                 } else if (STAGE == 5) {
-                    rk.K5[base + e] = f;
+                    rk.K5[base + e] = f[i];
                     const double k2 = __ldg(rk.K2 + base + e), k3 = __ldg(rk.K3 + base + e), k4 = __ldg(rk.K4 + base + e);
-                    rk.YS[1][base + e] = ye + (dp::A61 * k1e + dp::A62 * k2 + dp::A63 * k3 + dp::A64 * k4 + dp::A65 * f) * h;
+                    rk.YS[1][base + e] = ye + (dp::A61 * k1e + dp::A62 * k2 + dp::A63 * k3 + dp::A64 * k4 + dp::A65 * f[i]) * h;
                 } else if (STAGE == 6) {
-                    rk.K6[base + e] = f;
+                    rk.K6[base + e] = f[i];
                     const double k3 = __ldg(rk.K3 + base + e), k4 = __ldg(rk.K4 + base + e), k5 = __ldg(rk.K5 + base + e);
                     // y_new = y + h * dot(K[:-1].T, B)   (rk.py:64)
-                    rk.Y[par ^ 1][base + e] = ye + h * (dp::B1 * k1e + dp::B3 * k3 + dp::B4 * k4 + dp::B5 * k5 + dp::B6 * f);
+                    rk.Y[par ^ 1][base + e] = ye + h * (dp::B1 * k1e + dp::B3 * k3 + dp::B4 * k4 + dp::B5 * k5 + dp::B6 * f[i]);
                 } else {  // STAGE 7: f_new = K7, error estimate (rk.py:66-69, 157-162)
-                    rk.KF[par ^ 1][base + e] = f;
+                    rk.KF[par ^ 1][base + e] = f[i];
                     const double k3 = __ldg(rk.K3 + base + e), k4 = __ldg(rk.K4 + base + e), k5 = __ldg(rk.K5 + base + e),
                                  k6 = __ldg(rk.K6 + base + e);
-                    const double yn = tile[e - ch.tile_lo];
-                    const double err = (dp::E1 * k1e + dp::E3 * k3 + dp::E4 * k4 + dp::E5 * k5 + dp::E6 * k6 + dp::E7 * f) * h;
+                    const double yn = own[i];
+                    const double err = (dp::E1 * k1e + dp::E3 * k3 + dp::E4 * k4 + dp::E5 * k5 + dp::E6 * k6 + dp::E7 * f[i]) * h;
                     const double scale = rk.atol + fmax(fabs(ye), fabs(yn)) * rk.rtol;
                     const double q = err / scale;
-                    err2 = q * q;
+                    err2 += q * q;
                 }
             }
         }
         if (STAGE == 7) {
             const double sum = occm_block_sum(err2, scratch);   // contains __syncthreads
-            if (threadIdx.x == 0) rk.err_partial[(long long)m * cpm + ci] = sum;
+            if (tid == 0) rk.err_partial[(long long)m * cpm + ci] = sum;
         } else {
-            __syncthreads();   // tile is overwritten by the next chunk
+            __syncthreads();   // tile is overwritten by the next trip
         }
     }
 }
@@ -405,23 +499,31 @@ __global__ void occm_rk45_write_initial(const double* __restrict__ y0, int M, lo
 }
 
 // ------------------------------------------------------------------------------------------------ launch helpers
+template <int MODEL, int STAGE>
+static int occm_launch_stage_m(const occm_system* sys, const OccmMemDev& mem, const OccmRkDev& rk, const double* t_dev,
+                               double t_scalar, const double* y_in, double* dy_out, cudaStream_t st) {
+    static size_t smem_limit = 48 * 1024;   // the default opt-out limit; raise it only when needed
+    static int ctas_per_sm = 0;
+    const size_t smem = occm_elem_smem(sys, OCCM_E);
+    auto kern = occm_stage<MODEL, STAGE, OCCM_E>;
+    if (smem > smem_limit) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_limit = smem; }
+    if (ctas_per_sm == 0) {
+        OCCM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, OCCM_BLOCK, smem));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    const long long chunks = (long long)mem.M * sys->dev.chunks_per_member;
+    if (chunks >= (1ll << 31)) { occm_set_error("too many chunks (%lld) for one launch", chunks); return OCCM_ERR_INVALID; }
+    const int grid = occm_grid(sys, chunks, ctas_per_sm);   // persistent CTAs: a multiple of the SM count
+    kern<<<grid, OCCM_BLOCK, smem, st>>>(sys->dev, mem, rk, t_dev, t_scalar, y_in, dy_out);
+    OCCM_LAUNCH_CHECK("occm_stage");
+    return OCCM_OK;
+}
+
 template <int STAGE>
 static int occm_launch_stage(const occm_system* sys, const OccmMemDev& mem, const OccmRkDev& rk, const double* t_dev,
                              double t_scalar, const double* y_in, double* dy_out, cudaStream_t st) {
-    const size_t smem = occm_elem_smem(sys);
-    const long long chunks = (long long)mem.M * sys->dev.chunks_per_member;
-    const int grid = occm_grid(sys, chunks, 8);
-    if (sys->dev.model == OCCM_MODEL_CSTR) {
-        static size_t smem_limit = 48 * 1024;   // the default opt-out limit; raise it only when needed
-        if (smem > smem_limit) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(occm_stage<0, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_limit = smem; }
-        occm_stage<0, STAGE><<<grid, OCCM_BLOCK, smem, st>>>(sys->dev, mem, rk, t_dev, t_scalar, y_in, dy_out);
-    } else {
-        static size_t smem_limit = 48 * 1024;   // the default opt-out limit; raise it only when needed
-        if (smem > smem_limit) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(occm_stage<1, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_limit = smem; }
-        occm_stage<1, STAGE><<<grid, OCCM_BLOCK, smem, st>>>(sys->dev, mem, rk, t_dev, t_scalar, y_in, dy_out);
-    }
-    OCCM_LAUNCH_CHECK("occm_stage");
-    return OCCM_OK;
+    return sys->dev.model == OCCM_MODEL_CSTR ? occm_launch_stage_m<0, STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st)
+                                             : occm_launch_stage_m<1, STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st);
 }
 
 extern "C" int occm_rhs(const occm_system* sys, const occm_members* mem, const double* t_dev, double t_scalar,

@@ -39,6 +39,35 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+ELL_EMPTY = -2 ** 31
+ELL_CONTINUE = -2 ** 31 + 1
+
+
+def ell_from_csr(row_ptr: np.ndarray, row_src: np.ndarray, row_w: np.ndarray, coverage: float = 0.98, max_width: int = 8):
+    """ELL copy of the leading entries of every CSR row (column-major [K][N]).
+
+    K = the smallest width that holds ``coverage`` of the rows completely (capped); longer rows keep K-1 entries in
+    ELL and flag the last column so the kernel continues in the CSR arrays."""
+    row_ptr = np.asarray(row_ptr, dtype=np.int64)
+    n = len(row_ptr) - 1
+    deg = np.diff(row_ptr)
+    if n == 0 or deg.max(initial=0) == 0:
+        return 0, None, None
+    k = int(min(max_width, max(1, np.quantile(deg, coverage, method='higher'))))
+    if deg.max() <= max_width:
+        k = int(deg.max()) if deg.max() - k <= 1 else k
+    src = np.full((k, n), ELL_EMPTY, dtype=np.int64)
+    w = np.zeros((k, n), dtype=np.float64)
+    long_rows = deg > k
+    for col in range(k):
+        take = (deg > col) & ~(long_rows & (col == k - 1))
+        idx = row_ptr[:-1][take] + col
+        src[col, take] = row_src[idx]
+        w[col, take] = row_w[idx]
+    src[k - 1, long_rows] = ELL_CONTINUE
+    return k, src.astype(np.int32), w
+
+
 @dataclass
 class MemberParams:
     """Per-member ensemble parameters (device tensors or None)."""
@@ -79,11 +108,16 @@ class DeviceSystem:
         self.tables = torch.as_tensor(blob, device=self.dev)
         self.fields = f64(host.fields)
         self.n_rxn = host.tables.n_rxn
+        self.ell_k, self.ell_src, self.ell_w = 0, None, None
+        if host.model != 'pfr':
+            k, es, ew = ell_from_csr(host.row_ptr, host.row_src, host.row_w)
+            self.ell_k, self.ell_src, self.ell_w = k, i32(es), f64(ew)
         desc = _lib.SystemDesc(1 if host.model == 'pfr' else 0, host.S, host.n_models, host.P,
                                _ptr(self.row_ptr), _ptr(self.row_src), _ptr(self.row_w), _ptr(self.a),
                                _ptr(self.pulse_ptr), _ptr(self.pulse_fn), _ptr(self.pulse_w),
                                _ptr(self.tables), blob.nbytes, _ptr(self.fields),
-                               0 if host.fields is None else host.fields.shape[0])
+                               0 if host.fields is None else host.fields.shape[0],
+                               self.ell_k, _ptr(self.ell_src), _ptr(self.ell_w))
         h = C.c_void_p()
         _lib.check(self.lib.occm_system_create(C.byref(h), C.byref(desc)))
         self.handle = h

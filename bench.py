@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""
+Benchmark of the reactive-transport hot path (BASELINE.json metric:
+"compartment-species RHS evals/s & ensemble ODE solves/s").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--members-per-gpu M] [--impl reference]
+
+Workload (config.workload): C4 of SURVEY.md §8(d) — synthetic 1e5-CSTR network, 10 species, second-order mechanism,
+rate-constant / inflow / initial-condition ensemble, t in [0, 10], 101 outputs, rtol 1e-6 / atol 1e-10, RK45.
+Weak scaling: every GPU integrates `members_per_gpu` members (512 by default: 4096 members at 8 GPUs, the north-star
+configuration); a "step" is one complete ensemble solve of the rank's members.
+
+  value  : compartment-species RHS evaluations per second achieved inside the solves, whole job
+           (sum over members of nfev * N * S, divided by the max-over-ranks device time), inputs resident in HBM.
+  e2e    : the same metric through the public host API (EnsembleSolver.solve with HOST numpy arrays: upload of the
+           network tables, parameters and initial state, solve, download of the recorded outlet concentrations).
+  roofline: the dominant kernel = the fused Dormand-Prince stage kernel (stage 5: reads the stage state, y, K1..K4,
+           writes K5 and the next stage state), timed live with CUDA events on the launching stream.
+  cpu_baseline / --impl reference: the oracle port of the reference's CPU path (numpy/scipy.sparse restatement of
+           cstr_system.ddt + scipy.integrate.solve_ivp RK45) on a bounded member sample, all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+import numpy as np
+
+METRIC = "compartment-species RHS evals/s (inside ensemble RK45 solves)"
+UNIT = "evals/s"
+WORKLOAD = ("C4: synthetic 1e5-CSTR network (ring + random permutation edges), 10 species, 5 second-order reactions, "
+            "k/inflow/IC ensemble, t in [0,10], 101 outputs, rtol 1e-6 atol 1e-10, RK45")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--members-per-gpu', type=int, default=512)
+    ap.add_argument('--n-cstr', type=int, default=100_000)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--cpu-sample-members', type=int, default=0, help='members of the CPU baseline sample (0 = auto)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def build_workload(args):
+    from openccm_b200.workloads import cstr_ensemble_workload
+    return cstr_ensemble_workload(n_cstr=args.n_cstr)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200',
+                                          '-i', str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([v.strip() for v in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith('active') and 'not' not in v.lower():
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU / reference arm
+def _cpu_member_job(payload):
+    """One ensemble member through the oracle port (scipy RK45 around the sparse restated ddt)."""
+    (n_cstr, m, k_row, q, ic) = payload
+    import scipy.integrate
+    try:                                   # one BLAS thread per worker process: the pool already uses every core
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle import openccm_oracle as O
+    model, net, cp, cmesh, sys_o = _cpu_system(n_cstr)
+    # apply the member's scales the way the device does: k_scale per reaction, q_scale on transport, ic on y0
+    fun = _scaled_fun(sys_o, cp, k_row, q)
+    t_eval = O.generate_t_eval(cp)
+    t0 = time.perf_counter()
+    res = scipy.integrate.solve_ivp(fun, cp.get_list(['SIMULATION', 't_span'], float), sys_o.y0 * ic, method='RK45',
+                                    rtol=cp.get_item(['SIMULATION', 'rtol'], float), atol=cp.get_item(['SIMULATION', 'atol'], float),
+                                    first_step=cp.get_item(['SIMULATION', 'first_timestep'], float), t_eval=t_eval)
+    return res.nfev, time.perf_counter() - t0, res.status
+
+
+_CPU_CACHE = {}
+
+
+def _cpu_system(n_cstr):
+    if n_cstr not in _CPU_CACHE:
+        from oracle import openccm_oracle as O
+        from openccm_b200.workloads import cstr_ensemble_workload
+        model, net, cp, cmesh = cstr_ensemble_workload(n_cstr=n_cstr, solver='RK45')
+        sys_o = O.build_cstr(net.to_model_network(), cp, cmesh, sparse=True)
+        _CPU_CACHE[n_cstr] = (model, net, cp, cmesh, sys_o)
+    return _CPU_CACHE[n_cstr]
+
+
+def _scaled_fun(sys_o, cp, k_row, q):
+    """ddt of one member: q * (A c + b) + r(c; k * k_row), built from the oracle's pieces."""
+    from oracle import openccm_oracle as O
+    S, N = sys_o.c_shape
+    A = sys_o.extra['A']
+    species = cp.get_list(['SIMULATION', 'specie_names'], str)
+    rx = O.make_reactions_scaled(cp, species, k_row)
+    bcs = sys_o.extra['bcs']
+
+    def fun(t, y):
+        c = y.reshape(S, N)
+        d = np.ascontiguousarray((A @ c.T).T)
+        bcs(t, d)
+        d *= q
+        rx(c, d)
+        return d.ravel()
+    return fun
+
+
+def cpu_baseline(args, n_members_sample, k_scale, q_scale, ic_scale, budget_s=25.0):
+    """Oracle port on the host cores: members in a process pool. Returns (evals/s, cores, description)."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    N, S = args.n_cstr, 10
+    n = n_members_sample or max(cores, 8)
+    jobs = [(args.n_cstr, m, k_scale[m], float(q_scale[m]), float(ic_scale[m])) for m in range(n)]
+    t0 = time.perf_counter()
+    with mp.get_context('fork').Pool(min(cores, n)) as pool:
+        out = pool.map(_cpu_member_job, jobs)
+    wall = time.perf_counter() - t0
+    nfev = sum(o[0] for o in out)
+    procs = min(cores, n)
+    # members run concurrently, n / procs rounds: parallel solve time = rounds * slowest member (setup excluded)
+    rounds = -(-n // procs)
+    solve_wall = rounds * max(o[1] for o in out)
+    return nfev * N * S / solve_wall, procs, (f"{n} members of the same ensemble, scipy RK45 + scipy.sparse restated ddt, "
+                                              f"{procs} processes; solve time {solve_wall:.1f}s (wall incl. setup {wall:.1f}s)")
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference itself is pure Python
+    with a dense N x N operator that cannot hold N = 1e5) on all host cores, bounded sample per step."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from openccm_b200 import synthetic as syn
+    cores = os.cpu_count() or 1
+    n = args.cpu_sample_members or cores
+    from oracle import openccm_oracle as O
+    _, _, cp_ref, _, _ = _cpu_system(args.n_cstr)
+    n_rxn = len(O.read_reactions_file(cp_ref.get_item(['SIMULATION', 'reactions_file_path'], str))[0])
+    ks, qs, ics = syn.ensemble_sweeps(max(n, 1), n_rxn)
+    vals, walls = [], []
+    desc = ''
+    for i in range(args.warmup + args.steps):
+        v, used, desc = cpu_baseline(args, n, ks, qs, ics)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "members_per_step": n, "note": "bounded sample of the ensemble per step"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ device arm
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from openccm_b200 import _lib, synthetic as syn
+    from openccm_b200.device import MemberParams
+    from openccm_b200.ensemble import EnsembleSolver
+
+    world_size = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    lib = _lib.load()
+
+    model, net, cp, cmesh = build_workload(args)
+    solver = EnsembleSolver(model, net, cp, cmesh)
+    host = solver.host
+    N, S, ndof = host.n_models, host.S, host.ndof
+    M_loc = args.members_per_gpu
+    M_glob = M_loc * world_size
+    ks_all, qs_all, ics_all = syn.ensemble_sweeps(M_glob, host.tables.n_rxn)
+    lo, hi = rank * M_loc, (rank + 1) * M_loc
+    ks, qs, ics = ks_all[lo:hi], qs_all[lo:hi], ics_all[lo:hi]
+    save_idx = solver.outlet_save_idx()
+    te = np.asarray(solver.t_eval)
+    dev = solver.upload()
+    device = dev.dev
+
+    # ---- device-resident inputs for `value`
+    mem = MemberParams(M_loc, torch.as_tensor(ks, device=device), torch.as_tensor(qs, device=device), None)
+    c0_dev = torch.as_tensor(host.to_device_layout(host.c0.reshape(-1)), device=device)
+    y0 = (torch.as_tensor(ics, device=device)[:, None] * c0_dev[None, :]).contiguous()
+    save_dev = torch.as_tensor(save_idx, dtype=torch.int32, device=device)
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_solve():
+        with dev.open_rk45(y0, solver.t_span, rtol=solver.rtol, atol=solver.atol, first_step=solver.first_step,
+                           t_eval=te, save_idx=save_dev, members=mem) as run:
+            run.run(); run.stats()
+            return int(run.nfev.sum()), int(run.n_acc.sum() + run.n_rej.sum()), np.array(run.status)
+
+    for _ in range(args.warmup):
+        one_solve()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.occm_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    nfev_total = 0
+    for _ in range(args.steps):
+        nfev, attempts, status = one_solve()
+        nfev_total += nfev
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.occm_launch_count() - launches0
+    assert np.all(status == 1), f'members failed: {np.unique(status)}'
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=device)
+    work = torch.tensor([float(nfev_total)], dtype=torch.float64, device=device)
+    if world_size > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    ms_max = float(t_ms.item())
+    evals = float(work.item()) * N * S
+    value = evals / (ms_max * 1e-3)
+    solves_per_s = M_glob * args.steps / (ms_max * 1e-3)
+
+    # ---- e2e through the host API (host numpy in, host numpy out), copies inside the timed region
+    solver_e2e = EnsembleSolver(model, net, cp, cmesh, host=host)
+    def e2e_step():
+        solver_e2e.dev = None                      # re-upload tables every step
+        r = solver_e2e.solve(M_loc, k_scale=ks, q_scale=qs, ic_scale=ics, save=save_idx, gather=False)
+        return r
+    for _ in range(min(args.warmup, 1)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    nfev_e2e = 0
+    for _ in range(args.steps):
+        r = e2e_step()
+        nfev_e2e += int(r.nfev.sum())
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    w_e = torch.tensor([float(nfev_e2e)], dtype=torch.float64, device=device)
+    if world_size > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX); dist.all_reduce(w_e, op=dist.ReduceOp.SUM)
+    e2e_value = float(w_e.item()) * N * S / float(t_e.item())
+    blob_bytes = host.tables.pack().nbytes
+    h2d = (host.row_ptr.nbytes + host.row_src.nbytes + host.row_w.nbytes) * 2 + blob_bytes + host.c0.nbytes + \
+        ks.nbytes + qs.nbytes + ics.nbytes + save_idx.nbytes + te.nbytes
+    d2h = M_loc * len(te) * len(save_idx) * 8 + M_loc * (4 + 3 * 8)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel (rank 0): fused stage-5 kernel, live CUDA-event timing
+    roof = None
+    plain = None
+    if rank == 0:
+        with dev.open_rk45(y0, solver.t_span, rtol=solver.rtol, atol=solver.atol, first_step=solver.first_step,
+                           t_eval=te, save_idx=save_dev, members=mem) as run:
+            run.run(max_launch_steps=2)            # buffers hold a genuine mid-solve state
+            run.time_stage(5, 3)
+            ms5 = run.time_stage(5, 10)
+            stage_ms = {s: run.time_stage(s, 5) for s in (2, 3, 4, 5, 6, 7)}
+        nnz = len(host.row_src)
+        csr_bytes = 12 * nnz + 4 * (N + 1)
+        alg5 = M_loc * ndof * 8 * 8 + csr_bytes          # 6 vector reads + 2 vector writes per element, CSR once
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak = float(peaks.get('hbm_gbs', 6650.0))
+        ach = alg5 / (ms5 * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "occm_stage<CSTR, stage 5>", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                "ms_per_launch": ms5, "alg_bytes_per_launch": alg5,
+                "stage_ms": stage_ms}
+        # plain fused RHS (16 B per compartment-species eval)
+        dy = torch.empty_like(y0)
+        for _ in range(3):
+            dev.rhs(y0, 0.0, mem, out=dy)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            dev.rhs(y0, 0.0, mem, out=dy)
+        e1.record(); torch.cuda.synchronize()
+        ms_r = e0.elapsed_time(e1) / 10
+        alg_r = M_loc * ndof * 16 + csr_bytes
+        plain = {"ms_per_launch": ms_r, "evals_per_s": M_loc * ndof / (ms_r * 1e-3), "achieved_gbs": alg_r / (ms_r * 1e-3) / 1e9,
+                 "frac": alg_r / (ms_r * 1e-3) / 1e9 / peak}
+        del dy
+
+    cpu = None
+    if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
+        try:
+            v, used, desc = cpu_baseline(args, args.cpu_sample_members, ks_all, qs_all, ics_all)
+            cpu = {"value": v, "unit": UNIT, "cores": used, "kind": "port", "sample": desc}
+        except Exception as exc:           # the baseline must never take the bench line down
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc!r}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "members_per_gpu": M_loc, "members_total": M_glob, "n_cstr": N, "n_species": S,
+                           "l2": f"inputs larger than L2: {11 * M_loc * ndof * 8 / 2**30:.1f} GiB of state vectors per GPU",
+                           "parallelism": f"members sharded over {world_size} GPU(s), no data-path collective"},
+                "ode_solves_per_s": solves_per_s, "rhs_evals_total": evals,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "solves_per_s": M_glob * args.steps / float(t_e.item())},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "plain_rhs": plain, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -165,6 +165,23 @@ int occm_rk45_stats(occm_rk45* rk, int32_t* status, int64_t* n_accepted, int64_t
 /* Copy the current state y[m][ndof] out of the workspace (device to device). */
 int occm_rk45_get_state(occm_rk45* rk, double* y_out, void* stream);
 int occm_rk45_free(occm_rk45* rk);
+/*
+ * Residence-time distribution from recorded outlet concentrations.
+ * Replaces `postprocessing.analysis.network_to_rtd` (postprocessing/analysis.py:34-103):
+ *   F_s(t) = sum_k out[m][t][sel_idx[k]] * sel_w[k] (over entries with sel_species[k] == s) / q_in_total,
+ *   E_s = np.gradient(F_s, t, edge_order=2);  rtd[m][s][t] = (t, E, F).
+ * Additionally moments[m][s] = (m0, mean, variance) of E by the trapezoid rule (not computed by the reference).
+ * out: device [n_members][n_times][n_save] as written by occm_rk45 / occm_bdf; t: device [n_times], or
+ * [n_members][n_times] when t_per_member != 0.
+ */
+int occm_rtd(const double* out, int32_t n_members, int32_t n_times, int32_t n_save, const double* t, int32_t t_per_member,
+             const int32_t* sel_idx, const double* sel_w, const int32_t* sel_species, int32_t n_sel, int32_t n_species,
+             double q_in_total, double* rtd, double* moments, void* stream);
+
+/* Development/measurement aid: launch Dormand-Prince stage kernel `stage` (2..7) `reps` times back to back on the
+ * handle's current buffers and return the mean duration (CUDA events on `stream`). Leaves y, t, h untouched. */
+int occm_rk45_time_stage(occm_rk45* rk, int32_t stage, int32_t reps, float* ms_per_launch, void* stream);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t occm_launch_count(void);
 

@@ -56,6 +56,9 @@ SIGNATURES = {
                                   C.c_void_p]),
     'occm_rk45_get_state': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'occm_rk45_free': (C.c_int, [C.c_void_p]),
+    'occm_rk45_time_stage': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_void_p]),
+    'occm_rtd': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                           C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -708,6 +708,35 @@ extern "C" int occm_rk45_get_state(occm_rk45* rk, double* y_out, void* stream) {
     return OCCM_OK;
 }
 
+extern "C" int occm_rk45_time_stage(occm_rk45* rk, int32_t stage, int32_t reps, float* ms_per_launch, void* stream) {
+    if (!rk || !ms_per_launch || reps < 1 || stage < 2 || stage > 7) { occm_set_error("occm_rk45_time_stage: bad argument"); return OCCM_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const occm_system* sys = rk->sys;
+    const OccmMemDev md = occm_mem_dev(rk->has_mem ? &rk->mem : nullptr, 1);
+    cudaEvent_t e0, e1;
+    OCCM_CUDA_CHECK(cudaEventCreate(&e0));
+    OCCM_CUDA_CHECK(cudaEventCreate(&e1));
+    OCCM_CUDA_CHECK(cudaEventRecord(e0, st));
+    int rc = OCCM_OK;
+    for (int i = 0; i < reps && rc == OCCM_OK; ++i) {
+        switch (stage) {
+            case 2: rc = occm_launch_stage<2>(sys, md, rk->d, nullptr, 0.0, nullptr, nullptr, st); break;
+            case 3: rc = occm_launch_stage<3>(sys, md, rk->d, nullptr, 0.0, nullptr, nullptr, st); break;
+            case 4: rc = occm_launch_stage<4>(sys, md, rk->d, nullptr, 0.0, nullptr, nullptr, st); break;
+            case 5: rc = occm_launch_stage<5>(sys, md, rk->d, nullptr, 0.0, nullptr, nullptr, st); break;
+            case 6: rc = occm_launch_stage<6>(sys, md, rk->d, nullptr, 0.0, nullptr, nullptr, st); break;
+            default: rc = occm_launch_stage<7>(sys, md, rk->d, nullptr, 0.0, nullptr, nullptr, st); break;
+        }
+    }
+    OCCM_CUDA_CHECK(cudaEventRecord(e1, st));
+    OCCM_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    OCCM_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms_per_launch = ms / reps;
+    return rc;
+}
+
 extern "C" int occm_rk45_free(occm_rk45* rk) {
     if (!rk) return OCCM_OK;
     if (rk->h_running) cudaFreeHost(rk->h_running);

@@ -150,27 +150,41 @@ class DeviceSystem:
         return out
 
     # ------------------------------------------------------------------ RK45
-    def rk45(self, y0: torch.Tensor, t_span: Sequence[float], *, rtol: float, atol: float, first_step: float,
-             t_eval: Optional[Sequence[float]] = None, save_idx: Optional[torch.Tensor] = None,
-             members: Optional[MemberParams] = None, max_steps: int = 0, all_capacity: int = 4096,
-             return_final: bool = False) -> Rk45Result:
+    def open_rk45(self, y0: torch.Tensor, t_span: Sequence[float], *, rtol: float, atol: float, first_step: float,
+                  t_eval: Optional[Sequence[float]] = None, save_idx: Optional[torch.Tensor] = None,
+                  members: Optional[MemberParams] = None, max_steps: int = 0, all_capacity: int = 4096) -> "Rk45Run":
+        return Rk45Run(self, y0, t_span, rtol=rtol, atol=atol, first_step=first_step, t_eval=t_eval, save_idx=save_idx,
+                       members=members, max_steps=max_steps, all_capacity=all_capacity)
+
+    def rk45(self, y0: torch.Tensor, t_span: Sequence[float], *, return_final: bool = False, **kw) -> Rk45Result:
         """Batched scipy-compatible RK45. y0: device [M, ndof] (device layout)."""
+        with self.open_rk45(y0, t_span, **kw) as run:
+            return run.solve(return_final=return_final)
+
+
+class Rk45Run:
+    """One batched RK45 integration: owns the workspace / output tensors and the C handle."""
+
+    def __init__(self, system: DeviceSystem, y0: torch.Tensor, t_span, *, rtol, atol, first_step, t_eval, save_idx,
+                 members, max_steps, all_capacity):
         assert y0.is_cuda and y0.dtype == torch.float64 and y0.is_contiguous()
-        M = 1 if y0.dim() == 1 else y0.shape[0]
-        assert y0.numel() == M * self.ndof
-        mem = members if members is not None else MemberParams(M)
-        assert mem.n_members == M
-        n_save = self.ndof if save_idx is None else int(save_idx.numel())
+        self.sys = system
+        lib = self.lib = system.lib
+        M = self.M = 1 if y0.dim() == 1 else y0.shape[0]
+        assert y0.numel() == M * system.ndof
+        self.members = members if members is not None else MemberParams(M)
+        assert self.members.n_members == M
+        self.n_save = system.ndof if save_idx is None else int(save_idx.numel())
         if save_idx is not None:
             assert save_idx.is_cuda and save_idx.dtype == torch.int32
-        lib = self.lib
-        ws_bytes = lib.occm_rk45_workspace_bytes(self.handle, M)
-        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=self.dev)
-        ws_ptr = (ws.data_ptr() + 255) & ~255
-        all_mode = t_eval is None
-        if all_mode:
+        self.save_idx = save_idx
+        ws_bytes = lib.occm_rk45_workspace_bytes(system.handle, M)
+        self.ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=system.dev)
+        ws_ptr = (self.ws.data_ptr() + 255) & ~255
+        self.all_mode = t_eval is None
+        if self.all_mode:
             T = int(all_capacity)
-            te = None
+            self.te = None; self.te_np = None
         else:
             te_np = np.ascontiguousarray(np.asarray(t_eval, dtype=np.float64))
             if te_np.ndim != 1 or te_np.size == 0:
@@ -180,44 +194,74 @@ class DeviceSystem:
             if np.any(np.diff(te_np) <= 0):
                 raise ValueError("Values in `t_eval` are not properly sorted.")
             T = te_np.size
-            te = torch.as_tensor(te_np, device=self.dev)
-        out = torch.empty((M, T, n_save), dtype=torch.float64, device=self.dev)
-        out_t = torch.empty((M, T), dtype=torch.float64, device=self.dev)
+            self.te_np = te_np
+            self.te = torch.as_tensor(te_np, device=system.dev)
+        self.T = T
+        self.out = torch.empty((M, T, self.n_save), dtype=torch.float64, device=system.dev)
+        self.out_t = torch.empty((M, T), dtype=torch.float64, device=system.dev)
         prob = _lib.Rk45Problem(float(t_span[0]), float(t_span[1]), float(first_step), float(rtol), float(atol),
-                                y0.data_ptr(), _ptr(te), T, _ptr(save_idx), n_save, out.data_ptr(), out_t.data_ptr(),
-                                int(max_steps))
-        ms = mem.c_struct()
-        handle = C.c_void_p()
-        _lib.check(lib.occm_rk45_init(C.byref(handle), self.handle, C.byref(ms), C.byref(prob), ws_ptr, ws_bytes, _stream()))
-        try:
-            status = np.zeros(M, dtype=np.int32); n_acc = np.zeros(M, dtype=np.int64); n_rej = np.zeros(M, dtype=np.int64)
-            nfev = np.zeros(M, dtype=np.int64); t_now = np.zeros(M); n_rows = np.zeros(M, dtype=np.int32)
-            running = C.c_int32(0)
-            ts_all = [[] for _ in range(M)]; ys_all = [[] for _ in range(M)]
-            while True:
-                _lib.check(lib.occm_rk45_run(handle, 0, C.byref(running), _stream()))
-                _lib.check(lib.occm_rk45_stats(handle, status.ctypes.data, n_acc.ctypes.data, n_rej.ctypes.data,
-                                               nfev.ctypes.data, t_now.ctypes.data, n_rows.ctypes.data, _stream()))
-                if not all_mode:
-                    break
-                # harvest the rows written so far, un-pause and continue
-                for m in range(M):
-                    r = int(n_rows[m])
-                    if r:
-                        ts_all[m].append(out_t[m, :r].cpu().numpy())
-                        ys_all[m].append(out[m, :r].clone())
-                if not np.any(status == 2):
-                    break
-                _lib.check(lib.occm_rk45_resume(handle, _stream()))
-            y_final = None
-            if return_final:
-                y_final = torch.empty((M, self.ndof), dtype=torch.float64, device=self.dev)
-                _lib.check(lib.occm_rk45_get_state(handle, y_final.data_ptr(), _stream()))
-                torch.cuda.current_stream().synchronize()
-        finally:
-            lib.occm_rk45_free(handle)
-        if all_mode:
+                                y0.data_ptr(), _ptr(self.te), T, _ptr(save_idx), self.n_save, self.out.data_ptr(),
+                                self.out_t.data_ptr(), int(max_steps))
+        self._ms = self.members.c_struct()
+        self.handle = C.c_void_p()
+        _lib.check(lib.occm_rk45_init(C.byref(self.handle), system.handle, C.byref(self._ms), C.byref(prob), ws_ptr,
+                                      ws_bytes, _stream()))
+        self.status = np.zeros(M, dtype=np.int32); self.n_acc = np.zeros(M, dtype=np.int64)
+        self.n_rej = np.zeros(M, dtype=np.int64); self.nfev = np.zeros(M, dtype=np.int64)
+        self.t_now = np.zeros(M); self.n_rows = np.zeros(M, dtype=np.int32)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def close(self):
+        if self.handle:
+            self.lib.occm_rk45_free(self.handle)
+            self.handle = C.c_void_p()
+
+    def run(self, max_launch_steps: int = 0) -> int:
+        running = C.c_int32(0)
+        _lib.check(self.lib.occm_rk45_run(self.handle, int(max_launch_steps), C.byref(running), _stream()))
+        return running.value
+
+    def stats(self):
+        _lib.check(self.lib.occm_rk45_stats(self.handle, self.status.ctypes.data, self.n_acc.ctypes.data,
+                                            self.n_rej.ctypes.data, self.nfev.ctypes.data, self.t_now.ctypes.data,
+                                            self.n_rows.ctypes.data, _stream()))
+
+    def time_stage(self, stage: int, reps: int = 10) -> float:
+        ms = C.c_float(0.0)
+        _lib.check(self.lib.occm_rk45_time_stage(self.handle, int(stage), int(reps), C.byref(ms), _stream()))
+        return float(ms.value)
+
+    def final_state(self) -> torch.Tensor:
+        y = torch.empty((self.M, self.sys.ndof), dtype=torch.float64, device=self.sys.dev)
+        _lib.check(self.lib.occm_rk45_get_state(self.handle, y.data_ptr(), _stream()))
+        torch.cuda.current_stream().synchronize()
+        return y
+
+    def solve(self, return_final: bool = False) -> Rk45Result:
+        M = self.M
+        ts_all = [[] for _ in range(M)]; ys_all = [[] for _ in range(M)]
+        while True:
+            self.run()
+            self.stats()
+            if not self.all_mode:
+                break
+            for m in range(M):                       # harvest the rows written so far, un-pause and continue
+                r = int(self.n_rows[m])
+                if r:
+                    ts_all[m].append(self.out_t[m, :r].cpu().numpy())
+                    ys_all[m].append(self.out[m, :r].clone())
+            if not np.any(self.status == 2):
+                break
+            _lib.check(self.lib.occm_rk45_resume(self.handle, _stream()))
+        y_final = self.final_state() if return_final else None
+        st = (self.status.copy(), self.n_acc.copy(), self.n_rej.copy(), self.nfev.copy())
+        if self.all_mode:
             t_res = [np.concatenate(x) if x else np.zeros(0) for x in ts_all]
-            y_res = [torch.cat(x) if x else out[m, :0] for m, x in enumerate(ys_all)]
-            return Rk45Result(t_res, y_res, status, n_acc, n_rej, nfev, y_final)
-        return Rk45Result(te_np, out, status, n_acc, n_rej, nfev, y_final)
+            y_res = [torch.cat(x) if x else self.out[m, :0] for m, x in enumerate(ys_all)]
+            return Rk45Result(t_res, y_res, *st, y_final)
+        return Rk45Result(self.te_np, self.out, *st, y_final)

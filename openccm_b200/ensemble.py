@@ -1,0 +1,225 @@
+"""
+Batched ensembles (rate-constant, inflow, boundary-value and initial-condition sweeps) sharded member-wise over GPUs.
+
+The reference has no ensemble API: sweeps are Python loops that call ``run`` again
+(/root/reference/examples/simple_reactors/cstr/irreversible/cstr_analysis.py:60-65).  Here all members of a rank
+advance together in the batched kernels, each with its own time and step size; ranks never exchange data during
+the integration.  ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) is used only to gather the recorded
+observables and to reduce RTD statistics.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .system_solvers.export import HostSystem, export_system
+from .system_solvers.helper_functions import generate_t_eval
+
+
+# ------------------------------------------------------------------------------------------------ sharding helpers
+def world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n_members: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous block of members owned by ``rank`` (sizes differ by at most one)."""
+    return n_members * rank // world_size, n_members * (rank + 1) // world_size
+
+
+def gather_members(local: torch.Tensor, n_members: int) -> torch.Tensor:
+    """All-gather per-member rows (axis 0) from every rank, in member order. Works on CUDA (NCCL) and CPU (gloo)."""
+    rank, ws = world()
+    if ws == 1:
+        return local
+    per_rank = [shard_bounds(n_members, r, ws) for r in range(ws)]
+    n_max = max(hi - lo for lo, hi in per_rank)
+    pad = torch.zeros((n_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(parts, pad)
+    return torch.cat([parts[r][:hi - lo] for r, (lo, hi) in enumerate(per_rank)], dim=0)
+
+
+def reduce_statistics(local: torch.Tensor, n_members: int) -> Dict[str, torch.Tensor]:
+    """Ensemble mean / min / max / variance over the member axis (axis 0) across all ranks via all_reduce."""
+    rank, ws = world()
+    s1 = local.sum(0); s2 = (local * local).sum(0)
+    if local.shape[0]:
+        mn = local.min(0).values; mx = local.max(0).values
+    else:
+        mn = torch.full_like(s1, float('inf')); mx = torch.full_like(s1, float('-inf'))
+    if ws > 1:
+        dist.all_reduce(s1, op=dist.ReduceOp.SUM); dist.all_reduce(s2, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    mean = s1 / n_members
+    return dict(mean=mean, min=mn, max=mx, var=(s2 / n_members - mean * mean).clamp_min(0.0))
+
+
+# ------------------------------------------------------------------------------------------------ results
+@dataclass
+class EnsembleResult:
+    t: np.ndarray                       # [T]
+    y: Optional[np.ndarray]             # [M (or local M), T, n_save], device layout of the saved elements
+    save_idx: np.ndarray                # flat device-layout element index (p * S + s) of each saved column
+    status: np.ndarray
+    nfev: np.ndarray
+    n_accepted: np.ndarray
+    n_rejected: np.ndarray
+    rtd: Optional[np.ndarray] = None    # [M, S, T, 3]
+    moments: Optional[np.ndarray] = None        # [M, S, 3]  (m0, mean, variance)
+    moment_stats: Optional[Dict[str, np.ndarray]] = None
+    timing: Dict[str, float] = field(default_factory=dict)
+    local_range: Tuple[int, int] = (0, 0)
+
+
+class EnsembleSolver:
+    """Export once (host), upload once per rank, solve any number of parameter batches."""
+
+    def __init__(self, model: str, model_network, config_parser, cmesh, host: Optional[HostSystem] = None):
+        t0 = time.perf_counter()
+        self.cp = config_parser
+        self.model = model.lower()
+        self.host = host if host is not None else export_system(self.model, model_network, config_parser, cmesh)
+        self.cmesh = cmesh
+        self.setup_s = time.perf_counter() - t0
+        self.dev = None
+        self.t_span = config_parser.get_list(['SIMULATION', 't_span'], float)
+        self.rtol = config_parser.get_item(['SIMULATION', 'rtol'], float)
+        self.atol = config_parser.get_item(['SIMULATION', 'atol'], float)
+        self.first_step = config_parser.get_item(['SIMULATION', 'first_timestep'], float)
+        self.solver = config_parser.get_item(['SIMULATION', 'solver'], str).upper()
+        self.t_eval = generate_t_eval(config_parser)
+        if self.t_eval is None:
+            raise ValueError("ensembles need explicit output times (t_eval = 'dt, linear' | 'log, n' | list)")
+
+    # -- what to record
+    def outlet_save_idx(self) -> np.ndarray:
+        """All species at the outlet node of every model linked to the RTD outlet boundary."""
+        from .postprocessing.analysis import outlet_selection
+        out_id = self.cmesh.grouped_bcs.id(self.cp.get_item(['POST-PROCESSING', 'outlet_bc_name'], str))
+        idx, _, _ = outlet_selection(self.host.outlet_map.get(out_id, []), self.host.flows, self.host.P, self.host.S)
+        return idx
+
+    def upload(self):
+        from .device import DeviceSystem
+        if self.dev is None:
+            self.dev = DeviceSystem(self.host)
+        return self.dev
+
+    def members_per_batch(self, n_save: int, T: int, reserve: float = 0.85) -> int:
+        free, _ = torch.cuda.mem_get_info()
+        per_member = 11 * self.host.ndof * 8 + 2 * T * max(n_save, 1) * 8 + 4096
+        return max(1, int(free * reserve // per_member))
+
+    def solve(self, n_members: int, *, k_scale: Optional[np.ndarray] = None, q_scale: Optional[np.ndarray] = None,
+              bc_scale: Optional[np.ndarray] = None, ic_scale: Optional[np.ndarray] = None,
+              y0: Optional[Union[np.ndarray, torch.Tensor]] = None, save: Union[str, np.ndarray] = 'outlets',
+              rtd: bool = False, batch: Optional[int] = None, gather: bool = True, to_host: bool = True) -> EnsembleResult:
+        """Solve ``n_members`` systems that share the network but differ in the given per-member scales.
+
+        All array arguments are HOST arrays indexed by the global member id (each rank reads its own block).
+        ``y0`` ([M, ndof], reference layout per member) overrides ``ic_scale * c0``."""
+        from .device import MemberParams
+        from .postprocessing.analysis import outlet_selection, rtd_on_device
+        tm: Dict[str, float] = {}
+        t_start = time.perf_counter()
+        sysd = self.upload()
+        device = sysd.dev
+        host = self.host
+        rank, ws = world()
+        lo, hi = shard_bounds(n_members, rank, ws)
+        M_loc = hi - lo
+        if isinstance(save, str):
+            save_idx = None if save == 'all' else self.outlet_save_idx()
+        else:
+            save_idx = np.asarray(save, dtype=np.int32)
+        n_save = host.ndof if save_idx is None else len(save_idx)
+        save_dev = None if save_idx is None else torch.as_tensor(save_idx, dtype=torch.int32, device=device)
+        te = np.asarray(self.t_eval, dtype=np.float64)
+        T = len(te)
+        batch = batch or self.members_per_batch(n_save, T)
+        c0_dev = torch.as_tensor(host.to_device_layout(host.c0.reshape(-1)), device=device)
+
+        def dev_slice(a, b_lo, b_hi, cols=None):
+            if a is None:
+                return None
+            a = np.asarray(a, dtype=np.float64)
+            return torch.as_tensor(np.ascontiguousarray(a[b_lo:b_hi]), device=device)
+
+        y_parts, status, nfev, nacc, nrej, rtd_parts, mom_parts = [], [], [], [], [], [], []
+        if self.solver != 'B200-RK45' and self.solver != 'B200-BDF':
+            raise ValueError(f'solver {self.solver!r} is not a device solver')
+        for b_lo in range(lo, hi, batch):
+            b_hi = min(hi, b_lo + batch)
+            mb = b_hi - b_lo
+            mem = MemberParams(mb, dev_slice(k_scale, b_lo, b_hi), dev_slice(q_scale, b_lo, b_hi), dev_slice(bc_scale, b_lo, b_hi))
+            if y0 is not None:
+                yb = y0[b_lo:b_hi]
+                if isinstance(yb, torch.Tensor):
+                    yb = yb.to(device)
+                else:
+                    yb = torch.as_tensor(np.ascontiguousarray(yb), device=device)
+                # reference layout [S, n_points] -> device layout [n_points, S]
+                yb = yb.reshape(mb, host.S, host.n_points).transpose(1, 2).contiguous().reshape(mb, -1)
+            elif ic_scale is not None:
+                yb = (dev_slice(ic_scale, b_lo, b_hi)[:, None] * c0_dev[None, :]).contiguous()
+            else:
+                yb = c0_dev[None, :].expand(mb, -1).contiguous()
+            if self.solver == 'B200-RK45':
+                res = sysd.rk45(yb, self.t_span, rtol=self.rtol, atol=self.atol, first_step=self.first_step, t_eval=te,
+                                save_idx=save_dev, members=mem)
+            else:
+                from .bdf import solve_bdf
+                res = solve_bdf(sysd, yb, self.t_span, rtol=self.rtol, atol=self.atol, first_step=self.first_step,
+                                t_eval=te, save_idx=save_dev, members=mem)
+            y_parts.append(res.y)
+            status.append(res.status); nfev.append(res.nfev); nacc.append(res.n_accepted); nrej.append(res.n_rejected)
+            if rtd:
+                in_id = self.cmesh.grouped_bcs.id(self.cp.get_item(['POST-PROCESSING', 'inlet_bc_name'], str))
+                out_id = self.cmesh.grouped_bcs.id(self.cp.get_item(['POST-PROCESSING', 'outlet_bc_name'], str))
+                q_in = float(sum(host.flows[c] for _, c in host.inlet_map[in_id]))
+                idx, w, sp = outlet_selection(host.outlet_map[out_id], host.flows, host.P, host.S)
+                if save_idx is None:
+                    pos = idx
+                else:
+                    lookup = {int(e): i for i, e in enumerate(save_idx)}
+                    pos = np.array([lookup[int(e)] for e in idx], dtype=np.int32)
+                r, mo = rtd_on_device(res.y, torch.as_tensor(te, device=device), torch.as_tensor(pos, dtype=torch.int32, device=device),
+                                      torch.as_tensor(w, device=device), torch.as_tensor(sp, device=device), host.S, q_in)
+                rtd_parts.append(r); mom_parts.append(mo)
+        tm['solve_s'] = time.perf_counter() - t_start
+
+        cat = lambda parts, shape: torch.cat(parts, 0) if parts else torch.zeros(shape, dtype=torch.float64, device=device)
+        y_loc = cat(y_parts, (0, T, n_save))
+        st_loc = torch.as_tensor(np.concatenate(status) if status else np.zeros(0, np.int32), device=device)
+        cnt_loc = torch.as_tensor(np.stack([np.concatenate(nfev), np.concatenate(nacc), np.concatenate(nrej)], 1)
+                                  if nfev else np.zeros((0, 3), np.int64), device=device)
+        rtd_loc = cat(rtd_parts, (0, host.S, T, 3)) if rtd else None
+        mom_loc = cat(mom_parts, (0, host.S, 3)) if rtd else None
+        stats = None
+        if rtd:
+            stats = {k: v.cpu().numpy() for k, v in reduce_statistics(mom_loc, n_members).items()}
+        if gather and ws > 1:
+            y_loc = gather_members(y_loc, n_members)
+            st_loc = gather_members(st_loc, n_members)
+            cnt_loc = gather_members(cnt_loc, n_members)
+            if rtd:
+                rtd_loc = gather_members(rtd_loc, n_members); mom_loc = gather_members(mom_loc, n_members)
+        tm['total_s'] = time.perf_counter() - t_start
+        cnt = cnt_loc.cpu().numpy()
+        to_np = (lambda x: None if x is None else x.cpu().numpy()) if to_host else (lambda x: x)
+        return EnsembleResult(te, to_np(y_loc), np.arange(host.ndof, dtype=np.int32) if save_idx is None else save_idx,
+                              st_loc.cpu().numpy(), cnt[:, 0], cnt[:, 1], cnt[:, 2], to_np(rtd_loc), to_np(mom_loc), stats, tm,
+                              (lo, hi))
+
+
+def solve_ensemble(model: str, model_network, config_parser, cmesh, n_members: int, **kw) -> EnsembleResult:
+    """One-call form: export, upload, solve."""
+    return EnsembleSolver(model, model_network, config_parser, cmesh).solve(n_members, **kw)

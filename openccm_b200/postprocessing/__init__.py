@@ -1,0 +1,1 @@
+from .analysis import network_to_rtd, rtd_on_device  # noqa: F401

@@ -146,6 +146,10 @@ class EnsembleSolver:
         T = len(te)
         batch = batch or self.members_per_batch(n_save, T)
         c0_dev = torch.as_tensor(host.to_device_layout(host.c0.reshape(-1)), device=device)
+        # PFR: the inlet-node part of c0 is the folded boundary value (scales with bc_scale, not with ic_scale)
+        c0_bc_dev = None
+        if host.c0_bc is not None and np.any(host.c0_bc):
+            c0_bc_dev = torch.as_tensor(host.to_device_layout(host.c0_bc.reshape(-1)), device=device)
 
         def dev_slice(a, b_lo, b_hi, cols=None):
             if a is None:
@@ -168,10 +172,14 @@ class EnsembleSolver:
                     yb = torch.as_tensor(np.ascontiguousarray(yb), device=device)
                 # reference layout [S, n_points] -> device layout [n_points, S]
                 yb = yb.reshape(mb, host.S, host.n_points).transpose(1, 2).contiguous().reshape(mb, -1)
-            elif ic_scale is not None:
-                yb = (dev_slice(ic_scale, b_lo, b_hi)[:, None] * c0_dev[None, :]).contiguous()
             else:
-                yb = c0_dev[None, :].expand(mb, -1).contiguous()
+                ones = torch.ones(mb, dtype=torch.float64, device=device)
+                ic_b = dev_slice(ic_scale, b_lo, b_hi) if ic_scale is not None else ones
+                if c0_bc_dev is None:
+                    yb = (ic_b[:, None] * c0_dev[None, :]).contiguous()
+                else:
+                    bc_b = dev_slice(bc_scale, b_lo, b_hi) if bc_scale is not None else ones
+                    yb = (ic_b[:, None] * (c0_dev - c0_bc_dev)[None, :] + bc_b[:, None] * c0_bc_dev[None, :]).contiguous()
             if self.solver == 'B200-RK45':
                 res = sysd.rk45(yb, self.t_span, rtol=self.rtol, atol=self.atol, first_step=self.first_step, t_eval=te,
                                 save_idx=save_dev, members=mem)

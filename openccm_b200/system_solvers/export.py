@@ -48,6 +48,8 @@ class HostSystem:
     coupling: Optional[np.ndarray] = None     # [n, 3] (inlet node, connection, outlet node)
     Q_weight: Optional[np.ndarray] = None
     fields: Optional[np.ndarray] = None       # [n_fields, n_points]
+    c0_bc: Optional[np.ndarray] = None        # [S, n_points] part of c0 that is the folded PFR boundary value (scales with
+                                              # the boundary values, not with the initial condition, in ensembles)
 
     @property
     def S(self) -> int:
@@ -194,6 +196,7 @@ class BCPlan:
     points: List[np.ndarray] = field(default_factory=list)
     weights: List[np.ndarray] = field(default_factory=list)
     is_pulse: List[bool] = field(default_factory=list)
+    c0_bc: Optional[np.ndarray] = None
 
 
 def boundary_conditions(c0: np.ndarray, cp, species: List[str], bc_string: str, points_for_bc: Dict[int, np.ndarray],
@@ -265,8 +268,10 @@ def boundary_conditions(c0: np.ndarray, cp, species: List[str], bc_string: str, 
             plan.exprs[g][i_specie] = eqn.diff(T_SYM)
             for_eval.append((g, i_specie, eqn))
             c0[i_specie, plan.points[g]] = 0                  # :199
+    plan.c0_bc = np.zeros_like(c0)
     for g, i_specie, eqn in for_eval:                         # :202-207
-        np.add.at(c0[i_specie], plan.points[g], plan.weights[g] * float(eqn.evalf(subs={'t': t0})))
+        np.add.at(plan.c0_bc[i_specie], plan.points[g], plan.weights[g] * float(eqn.evalf(subs={'t': t0})))
+    c0 += plan.c0_bc
 
     order = sorted(range(len(plan.names)), key=lambda k: plan.names[k])
     for attr in ('names', 'ids', 'exprs', 'points', 'weights', 'is_pulse'):
@@ -384,7 +389,8 @@ def export_system(model: str, network, cp, cmesh, fields: Optional[Dict[str, np.
     if p_rows:
         pulse_ptr, pulse_fn, pulse_w = _csr_from_entries(N, np.concatenate(p_rows), np.concatenate(p_fn), np.concatenate(p_w))
     return HostSystem('pfr', species, N, P, row_ptr, row_src, row_w, Q_pfr / dV, pulse_ptr, pulse_fn, pulse_w, tables, c0,
-                      inlet_map, outlet_map, Q, coupling=coupling, Q_weight=Q_weight, fields=_stack_fields(fields, n_points))
+                      inlet_map, outlet_map, Q, coupling=coupling, Q_weight=Q_weight, fields=_stack_fields(fields, n_points),
+                      c0_bc=plan.c0_bc)
 
 
 def _stack_fields(fields: Optional[Dict[str, np.ndarray]], n_points: int) -> Optional[np.ndarray]:

@@ -89,13 +89,14 @@ typedef struct {
     int32_t        tables_bytes;
     const double*  fields;    /* or NULL */
     int32_t        n_fields;
-    /* CSTR only, optional (ell_width = 0: CSR only): the first ell_width entries of every row again in ELL form,
-     * column-major [ell_width][n_models], so the kernel reaches them without the row_ptr indirection.
-     * ell_src: >= 0 source CSTR | -1-b boundary group | INT32_MIN padding | INT32_MIN+1 in the last column = "entries
-     * ell_width-1.. of this row continue in the CSR arrays". */
+    /* CSTR only, optional (ell_width = 0: every row walks the CSR arrays): an ELL copy of the rows, column-major
+     * [ell_width][n_models], so the kernel reaches index and weight without the row_ptr indirection. Rows with fewer
+     * entries are padded with (own index, weight 0). Rows that do not fit (more entries than ell_width, a boundary
+     * entry, a pulse source) must have point_flags = 1 and are evaluated from the CSR arrays instead. */
     int32_t        ell_width;
     const int32_t* ell_src;
     const double*  ell_w;
+    const uint8_t* point_flags; /* [n_points] or NULL: 1 = evaluate this point on the generic path */
 } occm_system_desc;
 
 /* Per-member parameters of an ensemble (all device pointers, any may be NULL = 1.0).

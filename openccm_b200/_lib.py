@@ -11,7 +11,7 @@ import os
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'csrc', 'liboccm_b200.so')
+LIB_PATH = os.environ.get('OCCM_B200_LIB', os.path.join(HERE, 'csrc', 'liboccm_b200.so'))   # override: kernel experiments
 ABI_VERSION = 1
 
 
@@ -24,7 +24,7 @@ class SystemDesc(C.Structure):
                 ('row_ptr', C.c_void_p), ('row_src', C.c_void_p), ('row_w', C.c_void_p), ('a', C.c_void_p),
                 ('pulse_ptr', C.c_void_p), ('pulse_fn', C.c_void_p), ('pulse_w', C.c_void_p),
                 ('tables', C.c_void_p), ('tables_bytes', C.c_int32), ('fields', C.c_void_p), ('n_fields', C.c_int32),
-                ('ell_width', C.c_int32), ('ell_src', C.c_void_p), ('ell_w', C.c_void_p)]
+                ('ell_width', C.c_int32), ('ell_src', C.c_void_p), ('ell_w', C.c_void_p), ('point_flags', C.c_void_p)]
 
 
 class Members(C.Structure):

@@ -21,7 +21,9 @@ struct OccmSysDev {
     long long n_points, ndof;
     int tc;                     // points per sub-chunk = OCCM_BLOCK / S (every thread keeps one species)
     int ell_k;                  // CSTR: ELL width (0 = CSR only)
-    const int* ell_src; const double* ell_w;   // column-major [ell_k][n_models]
+    const int* ell_src; const double* ell_w;   // column-major [ell_k][n_models]; padding = (own row, weight 0)
+    const unsigned char* point_flags;          // [n_points] 1 = take the generic (CSR / table-walk) path
+    int fast_ok;                               // mechanism fits the register-resident reaction form
     const int* row_ptr; const int* row_src; const double* row_w; const double* a;
     const int* pulse_ptr; const int* pulse_fn; const double* pulse_w;
     const int* tables; int tables_bytes;
@@ -43,11 +45,8 @@ struct OccmTab {
     const int* prog_ptr; const int* code; const double* consts; const int* bc_prog;
 };
 
-// Stage the blob into shared memory (all threads) and build the views. `smem` must be 8-byte aligned.
-__device__ __forceinline__ OccmTab occm_load_tables(const int* __restrict__ blob, int bytes, int* smem) {
-    const int words = bytes >> 2;
-    for (int i = threadIdx.x; i < words; i += blockDim.x) smem[i] = __ldg(blob + i);
-    __syncthreads();
+// Views into a shared-memory copy of the blob.
+__device__ __forceinline__ OccmTab occm_tab_views(const int* smem) {
     OccmTab T;
     const char* base = reinterpret_cast<const char*>(smem);
     T.S = smem[OCCM_H_S]; T.n_rxn = smem[OCCM_H_NRXN]; T.n_bc = smem[OCCM_H_NBC];
@@ -63,6 +62,13 @@ __device__ __forceinline__ OccmTab occm_load_tables(const int* __restrict__ blob
     T.consts     = reinterpret_cast<const double*>(base + smem[OCCM_H_OFF_CONST]);
     T.bc_prog    = reinterpret_cast<const int*>(base + smem[OCCM_H_OFF_BC_PROG]);
     return T;
+}
+
+// Stage the blob into shared memory (all threads). `smem` must be 8-byte aligned. Ends with __syncthreads().
+__device__ __forceinline__ void occm_load_tables(const int* __restrict__ blob, int bytes, int* smem) {
+    const int words = bytes >> 2;
+    for (int i = threadIdx.x; i < words; i += blockDim.x) smem[i] = __ldg(blob + i);
+    __syncthreads();
 }
 
 __device__ __forceinline__ double occm_powi(double x, int n) {
@@ -141,12 +147,12 @@ __device__ __forceinline__ double occm_bc_value(const OccmTab& T, int b, int s, 
 }
 
 // Net reaction rate of species s at a point whose concentrations are row(0..S-1)
-// (the generated `_ddt[s, :] += ...` lines of system_solvers/reactions.py:450-455).  Generic table walk: used for
-// species whose terms do not fit the register-resident form below (more than OCCM_NT terms, total order above
-// OCCM_NF, or a byte-code rate factor such as Monod).
+// (the generated `_ddt[s, :] += ...` lines of system_solvers/reactions.py:450-455).  Generic table walk: used on the
+// cold path and for mechanisms that do not fit the register-resident form below (more than OCCM_NT terms per species,
+// total order above OCCM_NF, or a byte-code rate factor such as Monod).
 template <class Row>
-__device__ __noinline__ double occm_reaction_tables(const OccmTab& T, int s, const Row& row, const double* ksc, double t,
-                                                    int point, const OccmSysDev& sys) {
+__device__ __forceinline__ double occm_reaction_tables(const OccmTab& T, int s, const Row& row, const double* ksc, double t,
+                                                       int point, const OccmSysDev& sys) {
     double acc = 0.0;
     const int tb = T.term_ptr[s], te = T.term_ptr[s + 1];
     for (int k = tb; k < te; ++k) {
@@ -165,59 +171,54 @@ __device__ __noinline__ double occm_reaction_tables(const OccmTab& T, int s, con
     return acc;
 }
 
-// Register-resident reaction program of ONE species: a thread keeps its species for the whole kernel (chunks are a
-// multiple of S elements), so its stoichiometric terms are decoded from the shared-memory tables once.
-#define OCCM_NT 4   // terms
+// Register-resident reaction program of ONE species.  A thread keeps its species for the whole kernel (sub-chunks are a
+// multiple of S elements), so its stoichiometric terms are decoded from the shared-memory tables once.  Unused terms
+// have coefficient 0 and unused factor slots point at column S of the staged row, which always holds 1.0, so the
+// evaluation is branch free.
+#define OCCM_NT 4   // terms per species
 #define OCCM_NF 3   // factor slots per term (a factor of order n occupies n slots)
 struct OccmRxnRegs {
     double coeff[OCCM_NT];
-    unsigned meta[OCCM_NT];   // rxn | f0 << 8 | f1 << 16 | f2 << 24, factor 0xff = unused
-    int n;                    // number of terms, or -1: fall back to occm_reaction_tables
+    unsigned meta[OCCM_NT];   // rxn | f0 << 8 | f1 << 16 | f2 << 24
 };
 
-__device__ __forceinline__ OccmRxnRegs occm_rxn_regs(const OccmTab& T, int s) {
+__device__ __forceinline__ OccmRxnRegs occm_rxn_regs(const OccmTab& T, int s, int S) {
     OccmRxnRegs R;
-#pragma unroll
-    for (int i = 0; i < OCCM_NT; ++i) { R.coeff[i] = 0.0; R.meta[i] = 0xffffff00u; }
-    const int tb = T.term_ptr[s], te = T.term_ptr[s + 1];
-    R.n = te - tb;
-    if (R.n > OCCM_NT) { R.n = -1; return R; }
+    const unsigned pad = (unsigned)S;
+    const int tb = T.term_ptr[s], n = T.term_ptr[s + 1] - tb;
 #pragma unroll
     for (int i = 0; i < OCCM_NT; ++i) {
-        if (i < R.n) {
+        R.coeff[i] = 0.0;
+        unsigned meta = (pad << 8) | (pad << 16) | (pad << 24);
+        if (i < n) {
             const int k = tb + i;
             R.coeff[i] = T.term_coeff[k];
-            unsigned meta = (unsigned)T.term_rxn[k] & 0xffu;
-            if (T.term_rxn[k] > 255 || T.term_prog[k] >= 0) R.n = -1;
+            meta = (unsigned)T.term_rxn[k] & 0xffu;
             int slot = 0;
             for (int f = T.fac_ptr[k]; f < T.fac_ptr[k + 1]; ++f)
                 for (int q = 0; q < T.fac_ord[f]; ++q) {
                     if (slot < OCCM_NF) meta |= ((unsigned)T.fac_sp[f] & 0xffu) << (8 + 8 * slot);
                     ++slot;
                 }
-            for (int q = slot; q < OCCM_NF; ++q) meta |= 0xffu << (8 + 8 * q);
-            if (slot > OCCM_NF) R.n = -1;
-            R.meta[i] = meta;
+            for (int q = slot; q < OCCM_NF; ++q) meta |= pad << (8 + 8 * q);
         }
+        R.meta[i] = meta;
     }
     return R;
 }
 
-template <class Row>
-__device__ __forceinline__ double occm_reaction(const OccmRxnRegs& R, const OccmTab& T, int s, const Row& row,
-                                                const double* ksc, double t, int point, const OccmSysDev& sys) {
-    if (R.n < 0) return occm_reaction_tables(T, s, row, ksc, t, point, sys);
+// `row` points at the staged concentrations of the point (row[S] == 1.0); coeffm = coeff * k_scale[rxn]
+__device__ __forceinline__ double occm_reaction_fast(const double (&coeffm)[OCCM_NT], const unsigned (&meta)[OCCM_NT],
+                                                     const double* row, int nt_u, int nf_u) {
     double acc = 0.0;
 #pragma unroll
     for (int i = 0; i < OCCM_NT; ++i) {
-        if (i < R.n) {
-            const unsigned m = R.meta[i];
-            double v = R.coeff[i];
-            if (ksc) v *= ksc[m & 0xffu];
-            const unsigned f0 = (m >> 8) & 0xffu, f1 = (m >> 16) & 0xffu, f2 = m >> 24;
-            if (f0 != 0xffu) v *= row((int)f0);
-            if (f1 != 0xffu) v *= row((int)f1);
-            if (f2 != 0xffu) v *= row((int)f2);
+        if (i < nt_u) {                              // uniform bound: no divergence
+            const unsigned m = meta[i];
+            double v = coeffm[i];
+            if (nf_u > 0) v *= row[(m >> 8) & 0xffu];
+            if (nf_u > 1) v *= row[(m >> 16) & 0xffu];
+            if (nf_u > 2) v *= row[m >> 24];
             acc += v;
         }
     }
@@ -233,41 +234,56 @@ __device__ __forceinline__ double occm_pulses(const OccmSysDev& sys, const OccmT
     return acc;
 }
 
-// ELL slot encoding of the CSTR transport operator (built by the host from the CSR rows)
-#define OCCM_ELL_EMPTY    ((int)0x80000000)        // padding
-#define OCCM_ELL_CONTINUE ((int)0x80000001)        // last column only: entries K-1.. of this row are in the CSR arrays
-
-// One CSR/ELL entry of a CSTR row: w * c[src, s]  or  w * bc_scale * g_{b,s}(t)   (cstr_system.py:121-135,197-199)
-template <class In>
-__device__ __forceinline__ double occm_cstr_entry(const OccmTab& T, const In& in, int src, double w, int j, int s, int S,
-                                                  double own, double t, double bs) {
-    if (src >= 0) return w * (src == j ? own : in(src * S + s));
-    return w * (bs * occm_bc_value(T, -1 - src, s, t));
-}
-
-// d/dt of the inlet node of PFR k: sum over inflowing connections of w * (d/dt of the upstream outlet node), plus the
-// differentiated domain boundary conditions (pfr_system.py:304-314).
-template <class In>
-__device__ __noinline__ double occm_pfr_inlet(const OccmSysDev& sys, const OccmTab& T, const OccmRxnRegs& R, const In& in,
-                                              int k, int s, double t, double qs, double bs, const double* ksc) {
-    const int S = sys.S, P = sys.P;
-    double acc = 0.0;
-    const int eb = __ldg(sys.row_ptr + k), ee = __ldg(sys.row_ptr + k + 1);
-    for (int e = eb; e < ee; ++e) {
-        const int src = __ldg(sys.row_src + e);
-        const double w = __ldg(sys.row_w + e);
-        if (src >= 0) {
-            const int o = P * (src + 1) - 1;                 // outlet node of the upstream PFR
-            auto orow = [&in, o, S](int sp) { return in(o * S + sp); };
-            double d = -(qs * __ldg(sys.a + src)) * (in(o * S + s) - in((o - 1) * S + s));
-            d += occm_pulses(sys, T, src, s, t);
-            d += occm_reaction(R, T, s, orow, ksc, t, o, sys);
-            acc += w * d;
-        } else {
-            acc += w * (bs * occm_bc_value(T, -1 - src, s, t));
+// ---------------------------------------------------------------------------------------------------------
+// Cold path: d/dt of element (point p, species s) by walking the CSR rows and the mechanism tables.  Taken for points
+// whose `point_flags` bit is set (rows with a domain-boundary entry, a pulse source or more entries than the ELL
+// width), for PFR inlet nodes, and for every point when the mechanism does not fit the register fast path.
+//   in(e)  : stage state at flat element e of this member (global memory)
+//   myrow  : staged concentrations of point p (shared memory), prevrow: those of point p - 1 (PFR upwind neighbour)
+// CSTR: cstr_system.py:194-203.   PFR: pfr_system.py:290-316.
+template <int MODEL, class In>
+__device__ __noinline__ double occm_point_generic(const OccmSysDev& sys, const int* tab_smem, const In& in,
+                                                  const double* myrow, const double* prevrow, int p, int s, double t,
+                                                  double qs, double bs, const double* ksc) {
+    const OccmTab T = occm_tab_views(tab_smem);
+    const int S = sys.S;
+    auto row = [myrow](int sp) { return myrow[sp]; };
+    if (MODEL == 0) {
+        double acc = 0.0;
+        const int kb = __ldg(sys.row_ptr + p), ke = __ldg(sys.row_ptr + p + 1);
+        for (int k = kb; k < ke; ++k) {
+            const int src = __ldg(sys.row_src + k);
+            const double w = __ldg(sys.row_w + k);
+            if (src >= 0) acc += w * (src == p ? myrow[s] : in(src * S + s));
+            else          acc += w * (bs * occm_bc_value(T, -1 - src, s, t));
         }
+        return qs * acc + occm_pulses(sys, T, p, s, t) + occm_reaction_tables(T, s, row, ksc, t, p, sys);
+    } else {
+        const int P = sys.P;
+        const int k = p / P;
+        const int node = p - k * P;
+        if (node > 0) {
+            const double conv = -(qs * __ldg(sys.a + k)) * (myrow[s] - prevrow[s]);
+            return conv + occm_pulses(sys, T, k, s, t) + occm_reaction_tables(T, s, row, ksc, t, p, sys);
+        }
+        double acc = 0.0;
+        const int eb = __ldg(sys.row_ptr + k), ee = __ldg(sys.row_ptr + k + 1);
+        for (int e = eb; e < ee; ++e) {
+            const int src = __ldg(sys.row_src + e);
+            const double w = __ldg(sys.row_w + e);
+            if (src >= 0) {
+                const int o = P * (src + 1) - 1;                 // outlet node of the upstream PFR
+                auto orow = [&in, o, S](int sp) { return in(o * S + sp); };
+                double d = -(qs * __ldg(sys.a + src)) * (in(o * S + s) - in((o - 1) * S + s));
+                d += occm_pulses(sys, T, src, s, t);
+                d += occm_reaction_tables(T, s, orow, ksc, t, o, sys);
+                acc += w * d;
+            } else {
+                acc += w * (bs * occm_bc_value(T, -1 - src, s, t));
+            }
+        }
+        return acc;
     }
-    return acc;
 }
 
 // deterministic block-wide sum (fixed tree), result valid in thread 0

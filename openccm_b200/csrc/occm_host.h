@@ -46,7 +46,8 @@ static inline OccmMemDev occm_mem_dev(const occm_members* mem, int fallback_M) {
 
 // dynamic shared memory of the element kernels: tables + tile + k_scale row + reduction scratch
 static inline size_t occm_elem_smem(const occm_system* sys, int E) {
-    return sys->smem_tables + sizeof(double) * ((size_t)E * (OCCM_BLOCK + OCCM_MAX_S) + sys->dev.n_rxn + 42);
+    const size_t tile = (size_t)E * (sys->dev.tc + 1) * (sys->dev.S + 1);     // [halo row | tc rows] x (S + 1) per sub-chunk
+    return sys->smem_tables + sizeof(double) * (tile + sys->dev.n_rxn + (size_t)sys->dev.S * 4 + 44);
 }
 
 // persistent grid: a multiple of the SM count, capped by the amount of work

@@ -12,7 +12,20 @@
 #include <atomic>
 #include "occm_host.h"
 
-#define OCCM_E 2   // sub-chunks of tc points processed per loop trip of a CTA (memory-level parallelism)
+#ifndef OCCM_E
+#define OCCM_E 2          // sub-chunks of tc points per loop trip of a CTA in the Dormand-Prince stage kernels
+#endif
+#define OCCM_KREG 4       // ELL columns the hot path keeps in registers (wider rows take the generic path)
+#ifndef OCCM_E0
+#define OCCM_E0 2         // the plain RHS kernel has one HBM read per element: more sub-chunks per trip
+#endif
+#ifndef OCCM_MIN_CTAS
+#define OCCM_MIN_CTAS 2   // stage kernels: register budget 65536 / (256 * 2) = 128 per thread (measured best on B200)
+#endif
+#ifndef OCCM_MIN_CTAS0
+#define OCCM_MIN_CTAS0 4  // plain RHS kernel: 64 registers per thread
+#endif
+#define OCCM_EMAX (OCCM_E > OCCM_E0 ? OCCM_E : OCCM_E0)
 
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[1024] = "";
@@ -60,10 +73,13 @@ extern "C" int occm_system_create(occm_system** out, const occm_system_desc* d) 
     v.fields = d->fields; v.n_fields = d->n_fields;
     v.n_rxn = hdr[OCCM_H_NRXN];
     v.tc = OCCM_BLOCK / d->n_species;
-    v.chunks_per_member = (int)((n_points + (long long)OCCM_E * v.tc - 1) / ((long long)OCCM_E * v.tc));
+    v.chunks_per_member = (int)((n_points + (long long)OCCM_E * v.tc - 1) / ((long long)OCCM_E * v.tc));   // Dormand-Prince stage kernels (err_partial layout)
     v.ell_k = d->model == OCCM_MODEL_CSTR ? d->ell_width : 0;
     v.ell_src = d->ell_src; v.ell_w = d->ell_w;
-    if (v.ell_k < 0 || v.ell_k > 64 || (v.ell_k > 0 && (!d->ell_src || !d->ell_w))) { occm_set_error("bad ELL description"); free(s); return OCCM_ERR_INVALID; }
+    v.point_flags = d->point_flags;
+    v.fast_ok = hdr[OCCM_H_MAX_TERMS] <= OCCM_NT && hdr[OCCM_H_MAX_SLOTS] <= OCCM_NF && !hdr[OCCM_H_ANY_PROG] && hdr[OCCM_H_NRXN] <= 255;
+    if (d->model == OCCM_MODEL_CSTR && (v.ell_k == 0 || !d->point_flags)) v.fast_ok = 0;   // no ELL copy: CSR walk for every row
+    if (v.ell_k < 0 || v.ell_k > OCCM_KREG || (v.ell_k > 0 && (!d->ell_src || !d->ell_w))) { occm_set_error("bad ELL description"); free(s); return OCCM_ERR_INVALID; }
     if (ndof >= (1ll << 31)) { occm_set_error("ndof per member must fit in int32"); free(s); return OCCM_ERR_INVALID; }
     s->smem_tables = (size_t)d->tables_bytes;
     int dev = 0;
@@ -71,7 +87,7 @@ extern "C" int occm_system_create(occm_system** out, const occm_system_desc* d) 
     OCCM_CUDA_CHECK(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev));
     int max_smem = 0;
     OCCM_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    if (occm_elem_smem(s, OCCM_E) > (size_t)max_smem) {
+    if (occm_elem_smem(s, OCCM_EMAX) > (size_t)max_smem) {
         occm_set_error("mechanism tables (%d B) do not fit in shared memory (%d B)", d->tables_bytes, max_smem);
         free(s);
         return OCCM_ERR_UNSUPPORTED;
@@ -131,7 +147,11 @@ struct occm_rk45 {
 
 // ------------------------------------------------------------------------------------------------ stage kernel
 // STAGE 0: plain RHS (y_in -> dy_out).  STAGE s in 2..7: Dormand-Prince stage s of rk_step (rk.py:14-71).
-// E sub-chunks of tc points are processed per loop trip (independent loads of all E are issued before any is used).
+//
+// Hot path per element (CSTR): one coalesced own load, K (ELL width) index/weight loads + K row gathers that hit L2
+// (a member's state is a few MB), the reaction terms from registers + the staged row, the stage epilogue (own loads of
+// y, K_i; stores of K_s and the next stage state).  No branches except the per-point `flags` test that routes the rare
+// rows with boundary / pulse / overflow entries to the generic path.
 template <int STAGE>
 struct OccmStageIn {       // the stage state this kernel differentiates, as a function of the flat element index
     const double* a; const double* b; double hb;
@@ -141,38 +161,126 @@ struct OccmStageIn {       // the stage state this kernel differentiates, as a f
     }
 };
 
+// Own-element operands of the stage epilogue, loaded at the top of a trip so that all HBM reads of a trip are in
+// flight together.
+struct OccmOps { double ye, k1, ka, kb, kc, kd; };
+
+template <int STAGE>
+__device__ __forceinline__ OccmOps occm_load_ops(const OccmRkDev& rk, const double* y, const double* k1, long long base, int e) {
+    OccmOps o;
+    o.ye = o.k1 = o.ka = o.kb = o.kc = o.kd = 0.0;
+    if (STAGE == 0) return o;
+    o.ye = __ldg(y + e); o.k1 = __ldg(k1 + e);
+    if (STAGE == 3) { o.ka = __ldg(rk.K2 + base + e); }
+    if (STAGE == 4) { o.ka = __ldg(rk.K2 + base + e); o.kb = __ldg(rk.K3 + base + e); }
+    if (STAGE == 5) { o.ka = __ldg(rk.K2 + base + e); o.kb = __ldg(rk.K3 + base + e); o.kc = __ldg(rk.K4 + base + e); }
+    if (STAGE == 6) { o.ka = __ldg(rk.K3 + base + e); o.kb = __ldg(rk.K4 + base + e); o.kc = __ldg(rk.K5 + base + e); }
+    if (STAGE == 7) { o.ka = __ldg(rk.K3 + base + e); o.kb = __ldg(rk.K4 + base + e); o.kc = __ldg(rk.K5 + base + e); o.kd = __ldg(rk.K6 + base + e); }
+    return o;
+}
+
+// Stores K_s and the next stage state (rk.py:59-69); stage 7 returns the squared scaled error of the element.
+template <int STAGE>
+__device__ __forceinline__ double occm_finish(const OccmRkDev& rk, const OccmOps& o, double f, double h, int par, long long base,
+                                              int e, double y_new_own, double* __restrict__ dy_out) {
+    if (STAGE == 0) { dy_out[base + e] = f; return 0.0; }
+    if (STAGE == 2) {
+        rk.K2[base + e] = f;
+        rk.YS[0][base + e] = o.ye + (dp::A31 * o.k1 + dp::A32 * f) * h;
+    } else if (STAGE == 3) {
+        rk.K3[base + e] = f;
+        rk.YS[1][base + e] = o.ye + (dp::A41 * o.k1 + dp::A42 * o.ka + dp::A43 * f) * h;
+    } else if (STAGE == 4) {
+        rk.K4[base + e] = f;
+        rk.YS[0][base + e] = o.ye + (dp::A51 * o.k1 + dp::A52 * o.ka + dp::A53 * o.kb + dp::A54 * f) * h;
+    } else if (STAGE == 5) {
+        rk.K5[base + e] = f;
+        rk.YS[1][base + e] = o.ye + (dp::A61 * o.k1 + dp::A62 * o.ka + dp::A63 * o.kb + dp::A64 * o.kc + dp::A65 * f) * h;
+    } else if (STAGE == 6) {
+        rk.K6[base + e] = f;
+        // y_new = y + h * dot(K[:-1].T, B)   (rk.py:64)
+        rk.Y[par ^ 1][base + e] = o.ye + h * (dp::B1 * o.k1 + dp::B3 * o.ka + dp::B4 * o.kb + dp::B5 * o.kc + dp::B6 * f);
+    } else {  // STAGE 7: f_new = K7, error estimate (rk.py:66-69, 157-162)
+        rk.KF[par ^ 1][base + e] = f;
+        const double err = (dp::E1 * o.k1 + dp::E3 * o.ka + dp::E4 * o.kb + dp::E5 * o.kc + dp::E6 * o.kd + dp::E7 * f) * h;
+        const double scale = rk.atol + fmax(fabs(o.ye), fabs(y_new_own)) * rk.rtol;
+        const double q = err / scale;
+        return q * q;
+    }
+    return 0.0;
+}
+
+// Cold path of one element: generic evaluation + epilogue (kept out of line so the hot loop carries no call and few
+// live values: everything it needs is rebuilt from (member, parity)).
+template <int MODEL, int STAGE>
+__device__ __noinline__ double occm_cold_element(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk,
+                                                 const int* tab_s, const double* y_in, const double* myrow, int p, int s,
+                                                 double t_stage, int m, const double* ksc, double* dy_out) {
+    const long long base = (long long)m * sys.ndof;
+    const int RS = sys.S + 1;
+    double h = 0.0; int par = 0;
+    const double* y = nullptr; const double* k1 = nullptr;
+    if (STAGE != 0) { h = rk.h[m]; par = rk.parity[m]; y = rk.Y[par] + base; k1 = rk.KF[par] + base; }
+    OccmStageIn<STAGE> in;
+    in.a = STAGE == 0 ? y_in + base : STAGE == 2 ? y
+         : STAGE == 3 || STAGE == 5 ? rk.YS[0] + base
+         : STAGE == 4 || STAGE == 6 ? rk.YS[1] + base : rk.Y[par ^ 1] + base;
+    in.b = k1; in.hb = h;
+    const double qs = mem.q_scale ? __ldg(mem.q_scale + m) : 1.0;
+    const double bs = mem.bc_scale ? __ldg(mem.bc_scale + m) : 1.0;
+    const int e = p * sys.S + s;
+    const double f = occm_point_generic<MODEL>(sys, tab_s, in, myrow, myrow - RS, p, s, t_stage, qs, bs, ksc);
+    const OccmOps o = occm_load_ops<STAGE>(rk, y, k1, base, e);
+    return occm_finish<STAGE>(rk, o, f, h, par, base, e, myrow[s], dy_out);
+}
+
 template <int MODEL, int STAGE, int E>
-__global__ void __launch_bounds__(OCCM_BLOCK, 2)
-occm_stage(const OccmSysDev sys, const OccmMemDev mem, const OccmRkDev rk, const double* __restrict__ t_dev, double t_scalar,
-           const double* __restrict__ y_in, double* __restrict__ dy_out) {
+__global__ void __launch_bounds__(OCCM_BLOCK, (STAGE == 0 ? OCCM_MIN_CTAS0 : OCCM_MIN_CTAS))
+occm_stage(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmMemDev mem, const __grid_constant__ OccmRkDev rk,
+           const double* __restrict__ t_dev, double t_scalar, const double* __restrict__ y_in, double* __restrict__ dy_out) {
     extern __shared__ double smem_d[];
-    const OccmTab T = occm_load_tables(sys.tables, sys.tables_bytes, reinterpret_cast<int*>(smem_d));
-    const int S = sys.S, TC = sys.tc, CE = TC * S;
-    const int tstride = OCCM_BLOCK + OCCM_MAX_S;            // [halo point | sub-chunk]
+    int* tab_s = reinterpret_cast<int*>(smem_d);
+    occm_load_tables(sys.tables, sys.tables_bytes, tab_s);
+    const int S = sys.S, TC = sys.tc, RS = S + 1;           // staged rows carry a trailing 1.0
+    const int tst = (TC + 1) * RS;                           // [upwind halo row | TC rows] per sub-chunk
     double* tile = smem_d + (sys.tables_bytes >> 3);
-    double* ksc_s = tile + E * tstride;
-    double* scratch = ksc_s + ((sys.n_rxn + 1) & ~1);
+    double* ksc_s = tile + E * tst;                          // k_scale row of the current member (or ones)
+    double* rxc_s = ksc_s + ((sys.n_rxn + 1) & ~1);          // padded per-species coefficients [S][OCCM_NT]
+    double* scratch = rxc_s + S * OCCM_NT;
     const int tid = threadIdx.x;
-    const bool lane_on = tid < CE;
+    const bool lane_on = tid < TC * S;
     const int pl = tid / S;
     const int s = tid - pl * S;
-    const OccmRxnRegs R = occm_rxn_regs(T, lane_on ? s : 0);
+    const int nt_u = tab_s[OCCM_H_MAX_TERMS], nf_u = tab_s[OCCM_H_MAX_SLOTS];
+    const bool fast = sys.fast_ok != 0;
+    unsigned meta[OCCM_NT];
+    {
+        const OccmTab T = occm_tab_views(tab_s);
+        const OccmRxnRegs R = occm_rxn_regs(T, lane_on ? s : 0, S);
+#pragma unroll
+        for (int q = 0; q < OCCM_NT; ++q) { meta[q] = R.meta[q]; if (lane_on && pl == 0) rxc_s[s * OCCM_NT + q] = R.coeff[q]; }
+    }
+    for (int r = tid; r < E * (TC + 1); r += OCCM_BLOCK) tile[r * RS + S] = 1.0;
+    for (int r = tid; r < sys.n_rxn; r += OCCM_BLOCK) ksc_s[r] = 1.0;
     const int n_points = (int)sys.n_points;
     const int cpm = sys.chunks_per_member;
-    const unsigned total = (unsigned)mem.M * (unsigned)cpm;
+    const int K = sys.ell_k, N = sys.n_models;
+    double* const myslot = tile + (pl + 1) * RS + s;         // my slot inside sub-chunk 0's tile
+    const double* const myrow0 = tile + (pl + 1) * RS;
+    __syncthreads();
 
-    for (unsigned c = blockIdx.x; c < total; c += gridDim.x) {
-        const int m = (int)(c / (unsigned)cpm);
-        const int ci = (int)(c - (unsigned)m * (unsigned)cpm);
+    // (member, chunk) cursor of this CTA: advanced by gridDim.x chunks per trip without a division in the loop
+    int m = (int)(blockIdx.x / (unsigned)cpm);
+    int ci = (int)(blockIdx.x - (unsigned)m * (unsigned)cpm);
+    const int step_m = (int)(gridDim.x / (unsigned)cpm), step_c = (int)(gridDim.x - (unsigned)step_m * (unsigned)cpm);
+    int coeff_m = -1;                                        // member whose k_scale is folded into coeffm
+    double coeffm[OCCM_NT];
+#pragma unroll
+    for (int q = 0; q < OCCM_NT; ++q) coeffm[q] = 0.0;
+
+    for (; m < mem.M; m += step_m, ci += step_c, m += (ci >= cpm), ci -= (ci >= cpm) ? cpm : 0) {
         if (STAGE != 0 && rk.status[m] != OCCM_MEMBER_RUNNING) continue;   // uniform over the CTA
         const long long base = (long long)m * sys.ndof;
-        const double qs = mem.q_scale ? __ldg(mem.q_scale + m) : 1.0;
-        const double bs = mem.bc_scale ? __ldg(mem.bc_scale + m) : 1.0;
-        const double* ksc = nullptr;
-        if (mem.k_scale) {
-            for (int r = tid; r < sys.n_rxn; r += OCCM_BLOCK) ksc_s[r] = __ldg(mem.k_scale + (long long)m * sys.n_rxn + r);
-            ksc = ksc_s;
-        }
         double t_stage, h = 0.0;
         int par = 0;
         const double* y = nullptr; const double* k1 = nullptr;
@@ -193,131 +301,95 @@ occm_stage(const OccmSysDev sys, const OccmMemDev mem, const OccmRkDev rk, const
              : STAGE == 4 || STAGE == 6 ? rk.YS[1] + base : rk.Y[par ^ 1] + base;
         in.b = k1; in.hb = h;
 
-        // ---- phase A: own values of all E sub-chunks -> shared tile
+        // ---- phase A: every load whose address is known up front is issued here: own stage values, epilogue
+        //      operands, point flags and the ELL index / weight columns
         const int p0 = ci * (E * TC);
-        int pt[E]; bool ok[E]; double own[E];
+        int pt[E]; double own[E]; unsigned slow[E]; OccmOps ops[E];
+        int esrc[E][OCCM_KREG]; double ew[E][OCCM_KREG];
 #pragma unroll
         for (int i = 0; i < E; ++i) {
             pt[i] = p0 + i * TC + pl;
-            ok[i] = lane_on && pt[i] < n_points;
-            own[i] = ok[i] ? in(pt[i] * S + s) : 0.0;
+            if (!(lane_on && pt[i] < n_points)) pt[i] = -1;
+            const bool v = pt[i] >= 0;
+            own[i] = v ? in(pt[i] * S + s) : 0.0;
+            slow[i] = (v && sys.point_flags) ? (unsigned)__ldg(sys.point_flags + pt[i]) : 0u;
+            if (v) ops[i] = occm_load_ops<STAGE>(rk, y, k1, base, pt[i] * S + s);
+            if (MODEL == 0) {
+                const int* cs = sys.ell_src + (v ? pt[i] : 0);
+                const double* cw = sys.ell_w + (v ? pt[i] : 0);
+#pragma unroll
+                for (int k = 0; k < OCCM_KREG; ++k) {
+                    const bool on = v && k < K;
+                    esrc[i][k] = on ? __ldg(cs + k * N) : 0;
+                    ew[i][k] = on ? __ldg(cw + k * N) : 0.0;
+                }
+            }
         }
+        if (mem.k_scale && coeff_m != m && tid < sys.n_rxn) ksc_s[tid] = __ldg(mem.k_scale + (long long)m * sys.n_rxn + tid);
         if (MODEL == 1 && tid < S) {           // upwind neighbour point of each sub-chunk's first point
 #pragma unroll
             for (int i = 0; i < E; ++i) {
                 const int pp = p0 + i * TC - 1;
-                tile[i * tstride + OCCM_MAX_S - S + tid] = (pp >= 0 && pp < n_points) ? in(pp * S + tid) : 0.0;
+                tile[i * tst + tid] = (pp >= 0 && pp < n_points) ? in(pp * S + tid) : 0.0;
             }
         }
 #pragma unroll
-        for (int i = 0; i < E; ++i) tile[i * tstride + OCCM_MAX_S + tid] = own[i];
+        for (int i = 0; i < E; ++i) if (lane_on) myslot[i * tst] = own[i];
         __syncthreads();
 
-        // ---- phase B: transport + reactions
-        double f[E];
-#pragma unroll
-        for (int i = 0; i < E; ++i) f[i] = 0.0;
+        // ---- phase B: all row gathers of the trip in flight together (they hit L2: a member's state is a few MB)
+        double g[E][OCCM_KREG];
         if (MODEL == 0) {
-            const int K = sys.ell_k;
-            const int N = sys.n_models;
-#pragma unroll 4
-            for (int k = 0; k < K; ++k) {
-                int src[E]; double w[E];
 #pragma unroll
-                for (int i = 0; i < E; ++i) {
-                    src[i] = ok[i] ? __ldg(sys.ell_src + (long long)k * N + pt[i]) : OCCM_ELL_EMPTY;
-                    w[i] = ok[i] ? __ldg(sys.ell_w + (long long)k * N + pt[i]) : 0.0;
-                }
+            for (int i = 0; i < E; ++i)
 #pragma unroll
-                for (int i = 0; i < E; ++i) {
-                    if (src[i] == OCCM_ELL_EMPTY) continue;
-                    if (src[i] == OCCM_ELL_CONTINUE) {       // rare: row longer than the ELL width
-                        for (int q = __ldg(sys.row_ptr + pt[i]) + K - 1; q < __ldg(sys.row_ptr + pt[i] + 1); ++q)
-                            f[i] += occm_cstr_entry(T, in, __ldg(sys.row_src + q), __ldg(sys.row_w + q), pt[i], s, S, own[i], t_stage, bs);
-                    } else {
-                        f[i] += occm_cstr_entry(T, in, src[i], w[i], pt[i], s, S, own[i], t_stage, bs);
-                    }
-                }
-            }
-            if (K == 0) {                                     // CSR only
-#pragma unroll
-                for (int i = 0; i < E; ++i)
-                    if (ok[i])
-                        for (int q = __ldg(sys.row_ptr + pt[i]); q < __ldg(sys.row_ptr + pt[i] + 1); ++q)
-                            f[i] += occm_cstr_entry(T, in, __ldg(sys.row_src + q), __ldg(sys.row_w + q), pt[i], s, S, own[i], t_stage, bs);
-            }
-#pragma unroll
-            for (int i = 0; i < E; ++i) {
-                if (!ok[i]) continue;
-                const double* myrow = tile + i * tstride + OCCM_MAX_S + pl * S;
-                auto row = [myrow](int sp) { return myrow[sp]; };
-                f[i] = qs * f[i] + occm_pulses(sys, T, pt[i], s, t_stage) + occm_reaction(R, T, s, row, ksc, t_stage, pt[i], sys);
-            }
-        } else {
-            const int P = sys.P;
-#pragma unroll
-            for (int i = 0; i < E; ++i) {
-                if (!ok[i]) continue;
-                const int k = pt[i] / P;
-                const int node = pt[i] - k * P;
-                if (node > 0) {
-                    const double* myrow = tile + i * tstride + OCCM_MAX_S + pl * S;
-                    auto row = [myrow](int sp) { return myrow[sp]; };
-                    const double conv = -(qs * __ldg(sys.a + k)) * (own[i] - myrow[s - S]);
-                    f[i] = conv + occm_pulses(sys, T, k, s, t_stage) + occm_reaction(R, T, s, row, ksc, t_stage, pt[i], sys);
-                } else {
-                    f[i] = occm_pfr_inlet(sys, T, R, in, k, s, t_stage, qs, bs, ksc);
-                }
-            }
+                for (int k = 0; k < OCCM_KREG; ++k)
+                    g[i][k] = (pt[i] >= 0 && k < K && ew[i][k] != 0.0) ? in(esrc[i][k] * S + s) : 0.0;
         }
+        if (coeff_m != m) {                     // uniform: fold the member's rate-constant scales into the coefficients
+#pragma unroll
+            for (int q = 0; q < OCCM_NT; ++q) coeffm[q] = rxc_s[s * OCCM_NT + q] * ksc_s[meta[q] & 0xffu];
+            coeff_m = m;
+        }
+        const double qs = mem.q_scale ? __ldg(mem.q_scale + m) : 1.0;
 
-        // ---- phase C: stage epilogue (next stage state / y_new / error estimate)
         double err2 = 0.0;
+        unsigned any_slow = 0;
 #pragma unroll
         for (int i = 0; i < E; ++i) {
-            if (!ok[i]) continue;
-            const int e = pt[i] * S + s;
-            if (STAGE == 0) {
-                dy_out[base + e] = f[i];
+            if (pt[i] < 0) continue;
+            const double* myrow = myrow0 + i * tst;
+            double f;
+            if (MODEL == 0) {
+                if (!fast || slow[i]) { slow[i] = 1; any_slow = 1; continue; }
+                const double r = occm_reaction_fast(coeffm, meta, myrow, nt_u, nf_u);   // while the gathers fly
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < OCCM_KREG; ++k) acc += ew[i][k] * g[i][k];
+                f = qs * acc + r;
             } else {
-                const double ye = STAGE == 2 ? __ldg(y + e) : __ldg(y + e), k1e = __ldg(k1 + e);
-                if (STAGE == 2) {
-                    rk.K2[base + e] = f[i];
-                    rk.YS[0][base + e] = ye + (dp::A31 * k1e + dp::A32 * f[i]) * h;
-                } else if (STAGE == 3) {
-                    rk.K3[base + e] = f[i];
-                    const double k2 = __ldg(rk.K2 + base + e);
-                    rk.YS[1][base + e] = ye + (dp::A41 * k1e + dp::A42 * k2 + dp::A43 * f[i]) * h;
-                } else if (STAGE == 4) {
-                    rk.K4[base + e] = f[i];
-                    const double k2 = __ldg(rk.K2 + base + e), k3 = __ldg(rk.K3 + base + e);
-                    rk.YS[0][base + e] = ye + (dp::A51 * k1e + dp::A52 * k2 + dp::A53 * k3 + dp::A54 * f[i]) * h;
-                } else if (STAGE == 5) {
-                    rk.K5[base + e] = f[i];
-                    const double k2 = __ldg(rk.K2 + base + e), k3 = __ldg(rk.K3 + base + e), k4 = __ldg(rk.K4 + base + e);
-                    rk.YS[1][base + e] = ye + (dp::A61 * k1e + dp::A62 * k2 + dp::A63 * k3 + dp::A64 * k4 + dp::A65 * f[i]) * h;
-                } else if (STAGE == 6) {
-                    rk.K6[base + e] = f[i];
-                    const double k3 = __ldg(rk.K3 + base + e), k4 = __ldg(rk.K4 + base + e), k5 = __ldg(rk.K5 + base + e);
-                    // y_new = y + h * dot(K[:-1].T, B)   (rk.py:64)
-                    rk.Y[par ^ 1][base + e] = ye + h * (dp::B1 * k1e + dp::B3 * k3 + dp::B4 * k4 + dp::B5 * k5 + dp::B6 * f[i]);
-                } else {  // STAGE 7: f_new = K7, error estimate (rk.py:66-69, 157-162)
-                    rk.KF[par ^ 1][base + e] = f[i];
-                    const double k3 = __ldg(rk.K3 + base + e), k4 = __ldg(rk.K4 + base + e), k5 = __ldg(rk.K5 + base + e),
-                                 k6 = __ldg(rk.K6 + base + e);
-                    const double yn = own[i];
-                    const double err = (dp::E1 * k1e + dp::E3 * k3 + dp::E4 * k4 + dp::E5 * k5 + dp::E6 * k6 + dp::E7 * f[i]) * h;
-                    const double scale = rk.atol + fmax(fabs(ye), fabs(yn)) * rk.rtol;
-                    const double q = err / scale;
-                    err2 += q * q;
-                }
+                const int P = sys.P;
+                const int k = pt[i] / P;
+                const int node = pt[i] - k * P;
+                if (!fast || slow[i] || node == 0) { slow[i] = 1; any_slow = 1; continue; }
+                const double conv = -(qs * __ldg(sys.a + k)) * (own[i] - myrow[s - RS]);
+                f = conv + occm_reaction_fast(coeffm, meta, myrow, nt_u, nf_u);
             }
+            err2 += occm_finish<STAGE>(rk, ops[i], f, h, par, base, pt[i] * S + s, own[i], dy_out);
+        }
+        // ---- cold path (rows with boundary / pulse / overflow entries, PFR inlet nodes, table-walk mechanisms)
+        if (any_slow) {
+#pragma unroll 1
+            for (int i = 0; i < E; ++i)
+                if (pt[i] >= 0 && slow[i])
+                    err2 += occm_cold_element<MODEL, STAGE>(sys, mem, rk, tab_s, y_in, myrow0 + i * tst, pt[i], s, t_stage, m,
+                                                            mem.k_scale ? ksc_s : nullptr, dy_out);
         }
         if (STAGE == 7) {
             const double sum = occm_block_sum(err2, scratch);   // contains __syncthreads
             if (tid == 0) rk.err_partial[(long long)m * cpm + ci] = sum;
         } else {
-            __syncthreads();   // tile is overwritten by the next trip
+            __syncthreads();   // tile / ksc_s are overwritten by the next trip
         }
     }
 }
@@ -504,17 +576,20 @@ static int occm_launch_stage_m(const occm_system* sys, const OccmMemDev& mem, co
                                double t_scalar, const double* y_in, double* dy_out, cudaStream_t st) {
     static size_t smem_limit = 48 * 1024;   // the default opt-out limit; raise it only when needed
     static int ctas_per_sm = 0;
-    const size_t smem = occm_elem_smem(sys, OCCM_E);
-    auto kern = occm_stage<MODEL, STAGE, OCCM_E>;
+    constexpr int E = STAGE == 0 ? OCCM_E0 : OCCM_E;
+    const size_t smem = occm_elem_smem(sys, E);
+    auto kern = occm_stage<MODEL, STAGE, E>;
     if (smem > smem_limit) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_limit = smem; }
     if (ctas_per_sm == 0) {
         OCCM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, OCCM_BLOCK, smem));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
-    const long long chunks = (long long)mem.M * sys->dev.chunks_per_member;
+    OccmSysDev dev = sys->dev;
+    dev.chunks_per_member = (int)((dev.n_points + (long long)E * dev.tc - 1) / ((long long)E * dev.tc));
+    const long long chunks = (long long)mem.M * dev.chunks_per_member;
     if (chunks >= (1ll << 31)) { occm_set_error("too many chunks (%lld) for one launch", chunks); return OCCM_ERR_INVALID; }
     const int grid = occm_grid(sys, chunks, ctas_per_sm);   // persistent CTAs: a multiple of the SM count
-    kern<<<grid, OCCM_BLOCK, smem, st>>>(sys->dev, mem, rk, t_dev, t_scalar, y_in, dy_out);
+    kern<<<grid, OCCM_BLOCK, smem, st>>>(dev, mem, rk, t_dev, t_scalar, y_in, dy_out);
     OCCM_LAUNCH_CHECK("occm_stage");
     return OCCM_OK;
 }

@@ -28,6 +28,9 @@ enum {
     OCCM_H_OFF_CODE,        // int32 [n_code]   op | (arg << 8)
     OCCM_H_OFF_CONST,       // double[n_const]
     OCCM_H_OFF_BC_PROG,     // int32 [n_bc * S] program id of g_{b,s}(t) or -1 (no condition given: contributes 0)
+    OCCM_H_MAX_TERMS,       // max number of terms of any species (uniform unroll bound of the register fast path)
+    OCCM_H_MAX_SLOTS,       // max total order (factor slots) of any term
+    OCCM_H_ANY_PROG,        // 1 if any term carries a byte-code factor
     OCCM_H_WORDS = 32
 };
 

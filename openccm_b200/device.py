@@ -39,33 +39,36 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-ELL_EMPTY = -2 ** 31
-ELL_CONTINUE = -2 ** 31 + 1
+def ell_from_csr(row_ptr: np.ndarray, row_src: np.ndarray, row_w: np.ndarray, pulse_ptr: Optional[np.ndarray] = None,
+                 coverage: float = 0.98, max_width: int = 4):
+    """ELL copy of the CSR rows (column-major [K][N]) plus the per-row flag of the rows it cannot represent.
 
-
-def ell_from_csr(row_ptr: np.ndarray, row_src: np.ndarray, row_w: np.ndarray, coverage: float = 0.98, max_width: int = 8):
-    """ELL copy of the leading entries of every CSR row (column-major [K][N]).
-
-    K = the smallest width that holds ``coverage`` of the rows completely (capped); longer rows keep K-1 entries in
-    ELL and flag the last column so the kernel continues in the CSR arrays."""
+    K = the smallest width that holds ``coverage`` of the rows (capped at ``max_width``).  Rows that are longer,
+    contain a boundary entry (src < 0) or carry a pulse source are flagged: the kernel evaluates them from the CSR
+    arrays.  Short rows are padded with (own index, weight 0) so the fast path needs no branch."""
     row_ptr = np.asarray(row_ptr, dtype=np.int64)
     n = len(row_ptr) - 1
     deg = np.diff(row_ptr)
-    if n == 0 or deg.max(initial=0) == 0:
-        return 0, None, None
-    k = int(min(max_width, max(1, np.quantile(deg, coverage, method='higher'))))
-    if deg.max() <= max_width:
-        k = int(deg.max()) if deg.max() - k <= 1 else k
-    src = np.full((k, n), ELL_EMPTY, dtype=np.int64)
+    flags = np.zeros(n, dtype=np.uint8)
+    has_bc = np.zeros(n, dtype=bool)
+    if len(row_src):
+        rows = np.repeat(np.arange(n), deg)
+        has_bc[np.unique(rows[np.asarray(row_src) < 0])] = True
+    k = int(min(max_width, max(1, np.quantile(deg, coverage, method='higher')))) if n else 1
+    if n and deg.max() <= max_width and deg.max() - k <= 1:
+        k = int(max(1, deg.max()))
+    flags[(deg > k) | has_bc] = 1
+    if pulse_ptr is not None:
+        flags[np.diff(np.asarray(pulse_ptr, dtype=np.int64)) > 0] = 1
+    src = np.tile(np.arange(n, dtype=np.int64), (k, 1))
     w = np.zeros((k, n), dtype=np.float64)
-    long_rows = deg > k
+    good = flags == 0
     for col in range(k):
-        take = (deg > col) & ~(long_rows & (col == k - 1))
+        take = good & (deg > col)
         idx = row_ptr[:-1][take] + col
         src[col, take] = row_src[idx]
         w[col, take] = row_w[idx]
-    src[k - 1, long_rows] = ELL_CONTINUE
-    return k, src.astype(np.int32), w
+    return k, src.astype(np.int32), w, flags
 
 
 @dataclass
@@ -110,14 +113,19 @@ class DeviceSystem:
         self.n_rxn = host.tables.n_rxn
         self.ell_k, self.ell_src, self.ell_w = 0, None, None
         if host.model != 'pfr':
-            k, es, ew = ell_from_csr(host.row_ptr, host.row_src, host.row_w)
+            k, es, ew, flags = ell_from_csr(host.row_ptr, host.row_src, host.row_w, host.pulse_ptr)
             self.ell_k, self.ell_src, self.ell_w = k, i32(es), f64(ew)
+        else:
+            flags = np.zeros(host.n_points, dtype=np.uint8)
+            if host.pulse_ptr is not None:       # every node of a PFR with a pulse source takes the generic path
+                flags[np.repeat(np.diff(host.pulse_ptr) > 0, host.P)] = 1
+        self.point_flags = torch.as_tensor(flags, device=self.dev)
         desc = _lib.SystemDesc(1 if host.model == 'pfr' else 0, host.S, host.n_models, host.P,
                                _ptr(self.row_ptr), _ptr(self.row_src), _ptr(self.row_w), _ptr(self.a),
                                _ptr(self.pulse_ptr), _ptr(self.pulse_fn), _ptr(self.pulse_w),
                                _ptr(self.tables), blob.nbytes, _ptr(self.fields),
                                0 if host.fields is None else host.fields.shape[0],
-                               self.ell_k, _ptr(self.ell_src), _ptr(self.ell_w))
+                               self.ell_k, _ptr(self.ell_src), _ptr(self.ell_w), _ptr(self.point_flags))
         h = C.c_void_p()
         _lib.check(self.lib.occm_system_create(C.byref(h), C.byref(desc)))
         self.handle = h

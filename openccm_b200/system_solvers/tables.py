@@ -35,7 +35,7 @@ MAGIC = 0x4F43434D
 H_WORDS = 32
 (H_MAGIC, H_BYTES, H_S, H_NRXN, H_NTERM, H_NFAC, H_NPROG, H_NCODE, H_NCONST, H_NBC, H_NFIELD,
  H_OFF_TERM_PTR, H_OFF_TERM_COEFF, H_OFF_TERM_RXN, H_OFF_TERM_PROG, H_OFF_FAC_PTR, H_OFF_FAC_SP, H_OFF_FAC_ORD,
- H_OFF_PROG_PTR, H_OFF_CODE, H_OFF_CONST, H_OFF_BC_PROG) = range(22)
+ H_OFF_PROG_PTR, H_OFF_CODE, H_OFF_CONST, H_OFF_BC_PROG, H_MAX_TERMS, H_MAX_SLOTS, H_ANY_PROG) = range(25)
 
 _FUNCS = {sp.sin: 'SIN', sp.cos: 'COS', sp.tan: 'TAN', sp.exp: 'EXP', sp.log: 'LOG', sp.Abs: 'ABS', sp.tanh: 'TANH',
           sp.sinh: 'SINH', sp.cosh: 'COSH', sp.asin: 'ASIN', sp.acos: 'ACOS', sp.atan: 'ATAN', sp.sign: 'SIGN',
@@ -408,6 +408,9 @@ class MechanismTables:
         header[[H_MAGIC, H_S, H_NRXN, H_NTERM, H_NFAC, H_NPROG, H_NCODE, H_NCONST, H_NBC, H_NFIELD]] = [
             MAGIC, S, self.n_rxn, len(terms), len(fac_sp), len(progs), len(code), len(consts), len(self.bc_groups),
             len(self.fields)]
+        header[H_MAX_TERMS] = int(np.diff(term_ptr).max()) if len(terms) else 0
+        header[H_MAX_SLOTS] = max((sum(o for _, o in tm.factors) for tm in terms), default=0)
+        header[H_ANY_PROG] = int(any(tm.prog >= 0 for tm in terms))
         chunks = [header.tobytes()]
         off = header.nbytes
         for slot, arr in sections:

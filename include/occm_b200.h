@@ -167,6 +167,44 @@ int occm_rk45_stats(occm_rk45* rk, int32_t* status, int64_t* n_accepted, int64_t
 int occm_rk45_get_state(occm_rk45* rk, double* y_out, void* stream);
 int occm_rk45_free(occm_rk45* rk);
 /*
+ * Variable-order BDF/NDF (orders 1..5) for stiff networks — step-size / order control of scipy.integrate.BDF
+ * (scipy/integrate/_ivp/bdf.py:36-70,310-455) batched over members; the Newton systems (I - c J) dy = b are solved by
+ * right-preconditioned restarted GMRES with a matrix-free Jacobian action (directional difference of the fused RHS) and an
+ * on-the-fly S x S block-Jacobi preconditioner, instead of scipy's dense finite-difference Jacobian + LU.
+ * Replaces `solve_ivp(..., method='BDF' | 'LSODA' | 'Radau')` at cstr_system.py:151 / pfr_system.py:191 on stiff networks.
+ */
+typedef struct {
+    double t0, t_bound;
+    double first_step;
+    double rtol, atol;
+    const double* y0;         /* device [n_members][ndof] */
+    const double* t_eval;     /* device [n_t_eval] ascending or NULL ("all": every accepted step) */
+    int32_t n_t_eval;         /* with t_eval == NULL: row capacity of `out` per member incl. the initial state */
+    const int32_t* save_idx;  /* device [n_save] or NULL = all ndof */
+    int32_t n_save;
+    double* out;              /* device [n_members][n_t_eval][n_save or ndof] */
+    double* out_t;            /* device [n_members][n_t_eval] */
+    int64_t max_steps;        /* accepted + rejected attempts per member, 0 = unlimited */
+    const double* tdiag;      /* device [n_models]: transport diagonal (CSTR: Q_div_v[j,j]; PFR: -Q_pfr/dV) for the preconditioner */
+    int32_t gmres_restart;    /* Krylov dimension per Newton solve (0 = 30) */
+    double lin_tol_factor;    /* GMRES stops at |r|_rms <= factor * newton_tol in error-weight scaling (0 = 0.01) */
+} occm_bdf_problem;
+
+typedef struct occm_bdf occm_bdf;
+
+size_t occm_bdf_workspace_bytes(const occm_system* sys, int32_t n_members, int32_t gmres_restart);
+int occm_bdf_init(occm_bdf** out, const occm_system* sys, const occm_members* mem, const occm_bdf_problem* prob,
+                  void* workspace, size_t workspace_bytes, void* stream);
+/* Advance until every member is finished / failed / paused (or for at most max_attempts step attempts if > 0). */
+int occm_bdf_run(occm_bdf* bdf, int64_t max_attempts, int32_t* n_running, void* stream);
+int occm_bdf_resume(occm_bdf* bdf, void* stream);
+/* HOST arrays, any may be NULL. nfev counts Newton and Jacobian-action RHS evaluations. */
+int occm_bdf_stats(occm_bdf* bdf, int32_t* status, int64_t* n_accepted, int64_t* n_rejected, int64_t* nfev, int64_t* n_gmres,
+                   int64_t* n_newton_fail, double* t, int32_t* n_rows, int32_t* order, void* stream);
+int occm_bdf_get_state(occm_bdf* bdf, double* y_out, void* stream);
+int occm_bdf_free(occm_bdf* bdf);
+
+/*
  * Residence-time distribution from recorded outlet concentrations.
  * Replaces `postprocessing.analysis.network_to_rtd` (postprocessing/analysis.py:34-103):
  *   F_s(t) = sum_k out[m][t][sel_idx[k]] * sel_w[k] (over entries with sel_species[k] == s) / q_in_total,

@@ -1,0 +1,111 @@
+"""
+Host wrapper of the batched BDF integrator (occm_bdf_* in include/occm_b200.h).
+
+Replaces ``solve_ivp(..., method='BDF'/'LSODA')`` on stiff networks (the reference's default solver is LSODA,
+config_functions/expanded_config_parser.py:55, which spends >97 % of its RHS calls on dense finite-difference Jacobians,
+SURVEY.md §3.5).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .device import DeviceSystem, MemberParams, _ptr, _stream
+
+
+@dataclass
+class BdfResult:
+    t: object
+    y: object
+    status: np.ndarray
+    n_accepted: np.ndarray
+    n_rejected: np.ndarray
+    nfev: np.ndarray
+    n_gmres: np.ndarray
+    n_newton_fail: np.ndarray
+    y_final: Optional[torch.Tensor] = None
+
+
+def transport_diagonal(system: DeviceSystem) -> torch.Tensor:
+    """Diagonal of the transport operator per model: CSTR Q_div_v[j, j] (cstr_system.py:133-135), PFR -Q_pfr/dV."""
+    host = system.host
+    if host.model == 'pfr':
+        d = -np.asarray(host.a, dtype=np.float64)
+    else:
+        rows = np.repeat(np.arange(host.n_models), np.diff(host.row_ptr))
+        on_diag = host.row_src == rows
+        d = np.bincount(rows[on_diag], weights=host.row_w[on_diag], minlength=host.n_models)
+    return torch.as_tensor(np.ascontiguousarray(d), device=system.dev)
+
+
+def solve_bdf(system: DeviceSystem, y0: torch.Tensor, t_span: Sequence[float], *, rtol: float, atol: float, first_step: float,
+              t_eval: Optional[Sequence[float]] = None, save_idx: Optional[torch.Tensor] = None,
+              members: Optional[MemberParams] = None, max_steps: int = 0, gmres_restart: int = 30, lin_tol_factor: float = 0.0,
+              all_capacity: int = 4096, return_final: bool = False) -> BdfResult:
+    assert y0.is_cuda and y0.dtype == torch.float64 and y0.is_contiguous()
+    lib = system.lib
+    M = 1 if y0.dim() == 1 else y0.shape[0]
+    assert y0.numel() == M * system.ndof
+    mem = members if members is not None else MemberParams(M)
+    n_save = system.ndof if save_idx is None else int(save_idx.numel())
+    all_mode = t_eval is None
+    if all_mode:
+        T, te, te_np = int(all_capacity), None, None
+    else:
+        te_np = np.ascontiguousarray(np.asarray(t_eval, dtype=np.float64))
+        if np.any(te_np < min(t_span)) or np.any(te_np > max(t_span)):
+            raise ValueError("Values in `t_eval` are not within `t_span`.")
+        if np.any(np.diff(te_np) <= 0):
+            raise ValueError("Values in `t_eval` are not properly sorted.")
+        T = te_np.size
+        te = torch.as_tensor(te_np, device=system.dev)
+    out = torch.empty((M, T, n_save), dtype=torch.float64, device=system.dev)
+    out_t = torch.empty((M, T), dtype=torch.float64, device=system.dev)
+    tdiag = transport_diagonal(system)
+    ws_bytes = lib.occm_bdf_workspace_bytes(system.handle, M, gmres_restart)
+    ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=system.dev)
+    ws_ptr = (ws.data_ptr() + 255) & ~255
+    prob = _lib.BdfProblem(float(t_span[0]), float(t_span[1]), float(first_step), float(rtol), float(atol), y0.data_ptr(),
+                           _ptr(te), T, _ptr(save_idx), n_save, out.data_ptr(), out_t.data_ptr(), int(max_steps),
+                           tdiag.data_ptr(), int(gmres_restart), float(lin_tol_factor))
+    ms = mem.c_struct()
+    handle = C.c_void_p()
+    _lib.check(lib.occm_bdf_init(C.byref(handle), system.handle, C.byref(ms), C.byref(prob), ws_ptr, ws_bytes, _stream()))
+    try:
+        status = np.zeros(M, dtype=np.int32); order = np.zeros(M, dtype=np.int32); n_rows = np.zeros(M, dtype=np.int32)
+        i64 = lambda: np.zeros(M, dtype=np.int64)
+        n_acc, n_rej, nfev, n_gm, n_nf = i64(), i64(), i64(), i64(), i64()
+        t_now = np.zeros(M)
+        running = C.c_int32(0)
+        ts_all = [[] for _ in range(M)]; ys_all = [[] for _ in range(M)]
+        while True:
+            _lib.check(lib.occm_bdf_run(handle, 0, C.byref(running), _stream()))
+            _lib.check(lib.occm_bdf_stats(handle, status.ctypes.data, n_acc.ctypes.data, n_rej.ctypes.data, nfev.ctypes.data,
+                                          n_gm.ctypes.data, n_nf.ctypes.data, t_now.ctypes.data, n_rows.ctypes.data,
+                                          order.ctypes.data, _stream()))
+            if not all_mode:
+                break
+            for m in range(M):
+                r = int(n_rows[m])
+                if r:
+                    ts_all[m].append(out_t[m, :r].cpu().numpy()); ys_all[m].append(out[m, :r].clone())
+            if not np.any(status == 2):
+                break
+            _lib.check(lib.occm_bdf_resume(handle, _stream()))
+        y_final = None
+        if return_final:
+            y_final = torch.empty((M, system.ndof), dtype=torch.float64, device=system.dev)
+            _lib.check(lib.occm_bdf_get_state(handle, y_final.data_ptr(), _stream()))
+            torch.cuda.current_stream().synchronize()
+    finally:
+        lib.occm_bdf_free(handle)
+    if all_mode:
+        t_res = [np.concatenate(x) if x else np.zeros(0) for x in ts_all]
+        y_res = [torch.cat(x) if x else out[m, :0] for m, x in enumerate(ys_all)]
+        return BdfResult(t_res, y_res, status, n_acc, n_rej, nfev, n_gm, n_nf, y_final)
+    return BdfResult(te_np, out, status, n_acc, n_rej, nfev, n_gm, n_nf, y_final)

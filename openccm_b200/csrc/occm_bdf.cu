@@ -1,0 +1,958 @@
+// Batched variable-order BDF/NDF integrator with a Jacobian-free Newton-Krylov inner solve (sm_100a).
+//
+// Time stepping, error control and order selection follow scipy.integrate.BDF (scipy/integrate/_ivp/bdf.py:
+// compute_R / change_D :16-33, solve_bdf_system :36-70, _step_impl :310-455, BdfDenseOutput :458-483) member by member.
+// What differs from scipy is the linear algebra of the Newton iteration: scipy factorises I - c*J with a dense
+// finite-difference Jacobian (N_dof + 1 RHS calls and an O(N_dof^3) LU — the cost that dominates the reference on stiff
+// networks); here (I - c*J) dy = b is solved by right-preconditioned restarted GMRES in the error-weight
+// scaling of the Newton test, with
+//   * J*v by a directional difference of the fused RHS kernel (always the Jacobian at the current predictor, so the
+//     "stale Jacobian" bookkeeping of scipy disappears), and
+//   * a block-Jacobi preconditioner: per point the S x S block I - c*(transport diagonal + d r/d c) is rebuilt from the
+//     state and solved on the fly (nothing stored).
+// All members advance in lock step through the phases of a step attempt; per-member masks switch members off inside
+// the Newton and GMRES loops.  Reductions go through per-chunk partial sums added in a fixed order (deterministic).
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include "occm_host.h"
+
+#define BDF_MAX_ORDER 5
+#define BDF_NEWTON_MAXITER 4
+#define BDF_NVEC_D 8            // MAX_ORDER + 3 difference vectors
+#define BDF_CHUNK 2048          // elements per CTA trip of the streaming kernels (256 threads x 8)
+#define BDF_MAXDOT 48           // partial-sum slots per chunk (>= restart + 2)
+#define BDF_MIN_FACTOR 0.2
+#define BDF_MAX_FACTOR 10.0
+
+struct OccmBdfDev {
+    int M, S, P, model, nchunk, restart;
+    long long ndof, n_points, vstride;      // vstride = M * ndof
+    double* D;                               // [8][M][ndof]
+    double* y; double* psi; double* d; double* f; double* f2; double* z; double* w;
+    double* V;                               // [restart + 1][M][ndof]
+    double* t; double* h_abs; double* t_new; double* c; double* t_old_out;
+    int* order; int* n_equal; int* status; int* fresh;      // fresh: first attempt of a new step
+    int* newton_active; int* newton_k; int* converged; int* n_iter; double* dy_norm_old;
+    int* gmres_active; int* gmres_j; double* H; double* cs; double* sn; double* gv; double* ycoef; double* eps; double* ynorm;
+    double* RU; int* need_change; int* attempt_ok; double* safety; double* err_norm;
+    double* partial; double* norms;
+    int* accepted_now; int* out_lo; int* out_hi; int* n_rows;
+    long long* nfev; long long* n_acc; long long* n_rej; long long* n_newton_fail; long long* n_gmres; long long* n_precond;
+    int* counters;                           // [0] running, [1] newton active, [2] gmres active
+    double rtol, atol, t_bound, newton_tol, lin_tol;
+    long long max_steps;
+    const double* tdiag;                     // transport diagonal per model (CSTR: A_jj, PFR: -Q/dV)
+    const double* q_scale; const double* k_scale;
+};
+
+struct occm_bdf {
+    const occm_system* sys;
+    occm_members mem; bool has_mem;
+    occm_bdf_problem prob;
+    OccmBdfDev d;
+    int M;
+    int* h_counters;     // pinned host [4]
+};
+
+// ------------------------------------------------------------------------------------------------ small helpers
+__device__ __forceinline__ double bdf_next_up(double t) { return __longlong_as_double(__double_as_longlong(t) + 1ll); }
+
+__constant__ double c_kappa[6] = {0.0, -0.1850, -1.0 / 9, -0.0823, -0.0415, 0.0};
+
+__device__ __forceinline__ double bdf_gamma(int k) {      // gamma_k = sum_{j<=k} 1/j   (bdf.py:253)
+    double g = 0.0;
+    for (int j = 1; j <= k; ++j) g += 1.0 / j;
+    return g;
+}
+__device__ __forceinline__ double bdf_alpha(int k) { return (1.0 - c_kappa[k]) * bdf_gamma(k); }
+__device__ __forceinline__ double bdf_error_const(int k) { return c_kappa[k] * bdf_gamma(k) + 1.0 / (k + 1); }
+
+// R(order, factor) and RU = R(order, factor) @ R(order, 1)   (bdf.py:16-33); RU is (order+1)x(order+1), row-major 6x6
+__device__ void bdf_compute_R(int order, double factor, double (*Rm)[6]) {
+    for (int i = 0; i <= order; ++i)
+        for (int j = 0; j <= order; ++j) Rm[i][j] = 0.0;
+    for (int j = 0; j <= order; ++j) Rm[0][j] = 1.0;
+    for (int i = 1; i <= order; ++i)
+        for (int j = 1; j <= order; ++j) Rm[i][j] = Rm[i - 1][j] * ((i - 1 - factor * j) / i);   // cumprod down the rows
+}
+__device__ void bdf_set_change(const OccmBdfDev& b, int m, int order, double factor) {
+    double R[6][6], U[6][6];
+    bdf_compute_R(order, factor, R);
+    bdf_compute_R(order, 1.0, U);
+    double* RU = b.RU + (long long)m * 36;
+    for (int i = 0; i <= order; ++i)
+        for (int j = 0; j <= order; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k <= order; ++k) acc += R[i][k] * U[k][j];
+            RU[i * 6 + j] = acc;
+        }
+    b.need_change[m] = order + 1;      // number of difference rows to transform
+}
+
+// ------------------------------------------------------------------------------------------------ reductions
+__global__ void __launch_bounds__(128) bdf_reduce(const double* __restrict__ partial, int nchunk, int nvals, double* __restrict__ out,
+                                                  const int* __restrict__ mask) {
+    __shared__ double scratch[8];
+    const int m = blockIdx.x;
+    if (mask && !mask[m]) return;
+    for (int k = 0; k < nvals; ++k) {
+        double v = 0.0;
+        for (int i = threadIdx.x; i < nchunk; i += blockDim.x) v += partial[((long long)m * nchunk + i) * BDF_MAXDOT + k];
+        const double s = occm_block_sum(v, scratch);
+        if (threadIdx.x == 0) out[(long long)m * BDF_MAXDOT + k] = s;
+    }
+}
+
+// chunk iteration helper: CTA c handles elements [ci * BDF_CHUNK, ...) of member m
+#define BDF_FOR_CHUNKS(b, mask_expr)                                                              \
+    const long long total_chunks = (long long)(b).M * (b).nchunk;                                 \
+    for (long long cc = blockIdx.x; cc < total_chunks; cc += gridDim.x)                           \
+        if (int m = (int)(cc / (b).nchunk); true)                                                 \
+            if (mask_expr)                                                                        \
+                if (int ci = (int)(cc - (long long)m * (b).nchunk); true)
+
+#define BDF_ELEMS(b, ci, e) for (long long e = (long long)(ci) * BDF_CHUNK + threadIdx.x, e_end = min((long long)((ci) + 1) * BDF_CHUNK, (b).ndof); e < e_end; e += blockDim.x)
+
+// ------------------------------------------------------------------------------------------------ vector kernels
+__global__ void __launch_bounds__(256) bdf_change_D(const OccmBdfDev b) {
+    BDF_FOR_CHUNKS(b, b.need_change[m] > 0) {
+        const int n = b.need_change[m];
+        const double* RU = b.RU + (long long)m * 36;
+        BDF_ELEMS(b, ci, e) {
+            double v[6], r[6];
+            for (int j = 0; j < n; ++j) v[j] = b.D[j * b.vstride + (long long)m * b.ndof + e];
+            for (int i = 0; i < n; ++i) {            // D[:o+1] = RU.T @ D[:o+1]
+                double acc = 0.0;
+                for (int j = 0; j < n; ++j) acc += RU[j * 6 + i] * v[j];
+                r[i] = acc;
+            }
+            for (int i = 0; i < n; ++i) b.D[i * b.vstride + (long long)m * b.ndof + e] = r[i];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bdf_predict(const OccmBdfDev b) {      // bdf.py:358-362
+    BDF_FOR_CHUNKS(b, b.status[m] == OCCM_MEMBER_RUNNING) {
+        const int o = b.order[m];
+        const double inv_alpha = 1.0 / bdf_alpha(o);
+        BDF_ELEMS(b, ci, e) {
+            const long long g = (long long)m * b.ndof + e;
+            double yp = b.D[g], ps = 0.0;
+            for (int i = 1; i <= o; ++i) {
+                const double di = b.D[i * b.vstride + g];
+                yp += di;
+                ps += di * bdf_gamma(i);
+            }
+            b.y[g] = yp; b.psi[g] = ps * inv_alpha; b.d[g] = 0.0;
+        }
+    }
+}
+
+// b~ = (c f - psi - d) / scale -> V[0];  partial[0] = |b~|^2, partial[1] = |y|^2     (bdf.py:46, scaled by the error weights)
+__global__ void __launch_bounds__(256) bdf_newton_rhs(const OccmBdfDev b) {
+    __shared__ double scratch[8];
+    BDF_FOR_CHUNKS(b, b.newton_active[m]) {
+        const double c = b.c[m];
+        double s0 = 0.0, s1 = 0.0;
+        BDF_ELEMS(b, ci, e) {
+            const long long g = (long long)m * b.ndof + e;
+            const double y = b.y[g], d = b.d[g];
+            const double scale = b.atol + b.rtol * fabs(y - d);
+            const double r = (c * b.f[g] - b.psi[g] - d) / scale;
+            b.V[g] = r;
+            s0 += r * r; s1 += y * y;
+        }
+        const double t0 = occm_block_sum(s0, scratch), t1 = occm_block_sum(s1, scratch);
+        if (threadIdx.x == 0) { double* p = b.partial + (cc * BDF_MAXDOT); p[0] = t0; p[1] = t1; }
+    }
+}
+
+// dst[m] *= alpha[m]  (dst = V[col])
+__global__ void __launch_bounds__(256) bdf_scale_col(const OccmBdfDev b, int col_from_j, const double* __restrict__ alpha) {
+    BDF_FOR_CHUNKS(b, b.gmres_active[m]) {
+        const int col = col_from_j ? b.gmres_j[m] : 0;
+        const double a = alpha[m];
+        double* v = b.V + col * b.vstride + (long long)m * b.ndof;
+        BDF_ELEMS(b, ci, e) v[e] *= a;
+    }
+}
+
+// ---- block-Jacobi preconditioner, one thread per point: out = (I - c (tau I + dr/dc))^{-1} (scale .* in)
+// The reaction Jacobian block is rebuilt from the state by one-sided differences of the mechanism tables.
+template <int MODEL>
+__global__ void __launch_bounds__(128) bdf_precond(const __grid_constant__ OccmSysDev sys, const OccmBdfDev b, const double* __restrict__ src,
+                                                   int src_is_V_col_j, double* __restrict__ dst, const int* __restrict__ mask, int want_norm) {
+    extern __shared__ double smem_d[];
+    __shared__ double scratch[8];
+    int* tab_s = reinterpret_cast<int*>(smem_d);
+    occm_load_tables(sys.tables, sys.tables_bytes, tab_s);
+    const OccmTab T = occm_tab_views(tab_s);
+    const int S = sys.S;
+    const int ppc = (int)((sys.n_points + b.nchunk - 1) / b.nchunk);      // points per chunk (same chunk count as the vector kernels)
+    const long long total = (long long)b.M * b.nchunk;
+    for (long long cc = blockIdx.x; cc < total; cc += gridDim.x) {
+        const int m = (int)(cc / b.nchunk);
+        if (!mask[m]) continue;
+        const int ci = (int)(cc - (long long)m * b.nchunk);
+        const double c = b.c[m];
+        const double qs = b.q_scale ? b.q_scale[m] : 1.0;
+        const double* ksc = b.k_scale ? b.k_scale + (long long)m * sys.n_rxn : nullptr;
+        const double* in = src + (src_is_V_col_j ? (long long)b.gmres_j[m] * b.vstride : 0) + (long long)m * b.ndof;
+        double zn = 0.0;
+        const long long p_end = min((long long)(ci + 1) * ppc, sys.n_points);
+        for (long long p = (long long)ci * ppc + threadIdx.x; p < p_end; p += blockDim.x) {
+            const long long g0 = (long long)m * b.ndof + p * S;
+            double cr[OCCM_MAX_S > 16 ? 16 : OCCM_MAX_S], r0[16], u[16], B[16 * 16];
+            bool inlet = false;
+            double tau;
+            if (MODEL == 0) tau = qs * b.tdiag[p];
+            else { const int k = (int)(p / sys.P); inlet = (p - (long long)k * sys.P) == 0; tau = qs * b.tdiag[k]; }
+            for (int s = 0; s < S; ++s) {
+                const double y = b.y[g0 + s], d = b.d[g0 + s];
+                cr[s] = y;
+                u[s] = (b.atol + b.rtol * fabs(y - d)) * in[p * S + s];
+            }
+            if (!inlet) {          // PFR inlet nodes have no self coupling (their block is the identity)
+                auto row = [&cr](int sp) { return cr[sp]; };
+                for (int s = 0; s < S; ++s) r0[s] = occm_reaction_tables(T, s, row, ksc, b.t_new[m], (int)p, sys);
+                for (int j = 0; j < S; ++j) {
+                    const double save = cr[j];
+                    const double dl = 1.4901161193847656e-08 * (fabs(save) + 1e-3);
+                    cr[j] = save + dl;
+                    for (int s = 0; s < S; ++s) {
+                        const double r1 = occm_reaction_tables(T, s, row, ksc, b.t_new[m], (int)p, sys);
+                        B[s * S + j] = -c * ((r1 - r0[s]) / dl);
+                    }
+                    cr[j] = save;
+                    B[j * S + j] += 1.0 - c * tau;
+                }
+                // Gaussian elimination with partial pivoting on the S x S block
+                for (int k = 0; k < S; ++k) {
+                    int piv = k; double best = fabs(B[k * S + k]);
+                    for (int i = k + 1; i < S; ++i) if (fabs(B[i * S + k]) > best) { best = fabs(B[i * S + k]); piv = i; }
+                    if (piv != k) {
+                        for (int j = k; j < S; ++j) { const double tmp = B[k * S + j]; B[k * S + j] = B[piv * S + j]; B[piv * S + j] = tmp; }
+                        const double tmp = u[k]; u[k] = u[piv]; u[piv] = tmp;
+                    }
+                    const double inv = 1.0 / B[k * S + k];
+                    for (int i = k + 1; i < S; ++i) {
+                        const double l = B[i * S + k] * inv;
+                        for (int j = k + 1; j < S; ++j) B[i * S + j] -= l * B[k * S + j];
+                        u[i] -= l * u[k];
+                    }
+                }
+                for (int k = S - 1; k >= 0; --k) {
+                    double acc = u[k];
+                    for (int j = k + 1; j < S; ++j) acc -= B[k * S + j] * u[j];
+                    u[k] = acc / B[k * S + k];
+                }
+            }
+            for (int s = 0; s < S; ++s) { dst[g0 + s] = u[s]; zn += u[s] * u[s]; }
+        }
+        if (want_norm) {
+            const double tz = occm_block_sum(zn, scratch);
+            if (threadIdx.x == 0) b.partial[cc * BDF_MAXDOT + 0] = tz;
+        }
+    }
+}
+
+// w~ = (z - c (f2 - f) / eps) / scale -> V[j+1];  partial[i] = <w~, V[i]>, i = 0..j
+__global__ void __launch_bounds__(256) bdf_arnoldi_w(const OccmBdfDev b) {
+    __shared__ double scratch[8];
+    BDF_FOR_CHUNKS(b, b.gmres_active[m]) {
+        const int j = b.gmres_j[m];
+        const double c = b.c[m], inv_eps = 1.0 / b.eps[m];
+        double dots[BDF_MAXDOT];
+        for (int i = 0; i <= j; ++i) dots[i] = 0.0;
+        BDF_ELEMS(b, ci, e) {
+            const long long g = (long long)m * b.ndof + e;
+            const double y = b.y[g], d = b.d[g];
+            const double scale = b.atol + b.rtol * fabs(y - d);
+            const double w = (b.z[g] - c * ((b.f2[g] - b.f[g]) * inv_eps)) / scale;
+            b.V[(long long)(j + 1) * b.vstride + g] = w;
+            for (int i = 0; i <= j; ++i) dots[i] += w * b.V[(long long)i * b.vstride + g];
+        }
+        for (int i = 0; i <= j; ++i) {
+            const double tsum = occm_block_sum(dots[i], scratch);
+            if (threadIdx.x == 0) b.partial[cc * BDF_MAXDOT + i] = tsum;
+        }
+    }
+}
+
+// V[j+1] -= sum_i h_i V[i]  (h_i = norms[m][i]);  partial[0] = |V[j+1]|^2, partial[1 + i] = <V[j+1], V[i]> (re-orthogonalisation)
+__global__ void __launch_bounds__(256) bdf_orth(const OccmBdfDev b, int second_pass) {
+    __shared__ double scratch[8];
+    BDF_FOR_CHUNKS(b, b.gmres_active[m]) {
+        const int j = b.gmres_j[m];
+        const double* h = b.norms + (long long)m * BDF_MAXDOT + (second_pass ? 1 : 0);
+        double s0 = 0.0;
+        double dots[BDF_MAXDOT];
+        for (int i = 0; i <= j; ++i) dots[i] = 0.0;
+        BDF_ELEMS(b, ci, e) {
+            const long long g = (long long)m * b.ndof + e;
+            double w = b.V[(long long)(j + 1) * b.vstride + g];
+            for (int i = 0; i <= j; ++i) w -= h[i] * b.V[(long long)i * b.vstride + g];
+            b.V[(long long)(j + 1) * b.vstride + g] = w;
+            s0 += w * w;
+            if (!second_pass) for (int i = 0; i <= j; ++i) dots[i] += w * b.V[(long long)i * b.vstride + g];
+        }
+        const double t0 = occm_block_sum(s0, scratch);
+        if (threadIdx.x == 0) b.partial[cc * BDF_MAXDOT + 0] = t0;
+        if (!second_pass)
+            for (int i = 0; i <= j; ++i) {
+                const double tsum = occm_block_sum(dots[i], scratch);
+                if (threadIdx.x == 0) b.partial[cc * BDF_MAXDOT + 1 + i] = tsum;
+            }
+    }
+}
+
+// w = sum_k ycoef[m][k] V[k], k < n_iter_gmres[m]   (solution in the Krylov basis, before the preconditioner)
+__global__ void __launch_bounds__(256) bdf_lincomb_V(const OccmBdfDev b) {
+    BDF_FOR_CHUNKS(b, b.newton_active[m]) {
+        const int n = b.gmres_j[m];             // number of Arnoldi vectors used
+        const double* yc = b.ycoef + (long long)m * BDF_MAXDOT;
+        BDF_ELEMS(b, ci, e) {
+            const long long g = (long long)m * b.ndof + e;
+            double acc = 0.0;
+            for (int k = 0; k < n; ++k) acc += yc[k] * b.V[(long long)k * b.vstride + g];
+            b.w[g] = acc;
+        }
+    }
+}
+
+// dy = z: partial[0] = |dy / scale|^2 (scale from y_predict = y - d);  y += dy;  d += dy      (bdf.py:47, 58-59)
+__global__ void __launch_bounds__(256) bdf_newton_update(const OccmBdfDev b) {
+    __shared__ double scratch[8];
+    BDF_FOR_CHUNKS(b, b.newton_active[m]) {
+        const bool zero = b.gmres_j[m] == 0;     // right-hand side already below the linear tolerance: dy = 0
+        double s0 = 0.0;
+        BDF_ELEMS(b, ci, e) {
+            const long long g = (long long)m * b.ndof + e;
+            const double y = b.y[g], d = b.d[g];
+            const double scale = b.atol + b.rtol * fabs(y - d);
+            const double dy = zero ? 0.0 : b.z[g];
+            const double q = dy / scale;
+            s0 += q * q;
+            b.y[g] = y + dy; b.d[g] = d + dy;
+        }
+        const double t0 = occm_block_sum(s0, scratch);
+        if (threadIdx.x == 0) b.partial[cc * BDF_MAXDOT + 0] = t0;
+    }
+}
+
+// partial[0] = |error_const[order] * d / (atol + rtol |y_new|)|^2        (bdf.py:394-396)
+__global__ void __launch_bounds__(256) bdf_error(const OccmBdfDev b) {
+    __shared__ double scratch[8];
+    BDF_FOR_CHUNKS(b, b.attempt_ok[m]) {
+        const double ec = bdf_error_const(b.order[m]);
+        double s0 = 0.0;
+        BDF_ELEMS(b, ci, e) {
+            const long long g = (long long)m * b.ndof + e;
+            const double q = ec * b.d[g] / (b.atol + b.rtol * fabs(b.y[g]));
+            s0 += q * q;
+        }
+        const double t0 = occm_block_sum(s0, scratch);
+        if (threadIdx.x == 0) b.partial[cc * BDF_MAXDOT + 0] = t0;
+    }
+}
+
+// accepted step: D[o+2] = d - D[o+1]; D[o+1] = d; D[i] += D[i+1] (i = o..0);                      (bdf.py:419-422)
+// partial[0] = |error_const[o-1] D[o] / scale|^2, partial[1] = |error_const[o+1] D[o+2] / scale|^2   (:427-437)
+__global__ void __launch_bounds__(256) bdf_update_D(const OccmBdfDev b) {
+    __shared__ double scratch[8];
+    BDF_FOR_CHUNKS(b, b.accepted_now[m]) {
+        const int o = b.order[m];
+        const double ecm = o > 1 ? bdf_error_const(o - 1) : 0.0, ecp = o < BDF_MAX_ORDER ? bdf_error_const(o + 1) : 0.0;
+        double s0 = 0.0, s1 = 0.0;
+        BDF_ELEMS(b, ci, e) {
+            const long long g = (long long)m * b.ndof + e;
+            const double d = b.d[g];
+            double Dv[BDF_NVEC_D];
+            for (int i = 0; i <= o + 1; ++i) Dv[i] = b.D[i * b.vstride + g];
+            Dv[o + 2] = d - Dv[o + 1];
+            Dv[o + 1] = d;
+            for (int i = o; i >= 0; --i) Dv[i] += Dv[i + 1];
+            for (int i = 0; i <= o + 2; ++i) b.D[i * b.vstride + g] = Dv[i];
+            const double scale = b.atol + b.rtol * fabs(b.y[g]);
+            const double qm = ecm * Dv[o] / scale, qp = ecp * Dv[o + 2] / scale;
+            s0 += qm * qm; s1 += qp * qp;
+        }
+        const double t0 = occm_block_sum(s0, scratch), t1 = occm_block_sum(s1, scratch);
+        if (threadIdx.x == 0) { b.partial[cc * BDF_MAXDOT + 0] = t0; b.partial[cc * BDF_MAXDOT + 1] = t1; }
+    }
+}
+
+// BdfDenseOutput (bdf.py:458-483) at the t_eval points inside the accepted step; "all" mode stores y_new.
+__global__ void __launch_bounds__(256) bdf_output(const OccmBdfDev b, int n_save, const int* __restrict__ save_idx,
+                                                  const double* __restrict__ t_eval, int n_t_eval, double* __restrict__ out,
+                                                  double* __restrict__ out_t) {
+    const int cps = (n_save + 255) / 256;
+    const long long total = (long long)b.M * cps;
+    for (long long cc = blockIdx.x; cc < total; cc += gridDim.x) {
+        const int m = (int)(cc / cps);
+        if (!b.accepted_now[m]) continue;
+        const int lo = b.out_lo[m], hi = t_eval ? b.out_hi[m] : lo + 1;
+        if (hi <= lo) continue;
+        const int i = (int)(cc - (long long)m * cps) * 256 + threadIdx.x;
+        if (i >= n_save) continue;
+        const long long e = save_idx ? save_idx[i] : i;
+        const long long g = (long long)m * b.ndof + e;
+        const double t = b.t[m];
+        if (!t_eval) {
+            out[((long long)m * n_t_eval + lo) * n_save + i] = b.D[g];
+            if (out_t && i == 0) out_t[(long long)m * n_t_eval + lo] = t;
+            continue;
+        }
+        const int o = b.order[m];
+        const double h = b.h_abs[m];
+        double Dv[6];
+        for (int k = 0; k <= o; ++k) Dv[k] = b.D[k * b.vstride + g];
+        for (int j = lo; j < hi; ++j) {
+            const double te = t_eval[j];
+            double p = 1.0, yv = Dv[0];
+            for (int k = 0; k < o; ++k) {                  // x_k = (t - (t_n - h k)) / (h (1 + k)); p = cumprod(x)
+                p *= (te - (t - h * k)) / (h * (1 + k));
+                yv += Dv[k + 1] * p;
+            }
+            out[((long long)m * n_t_eval + j) * n_save + i] = yv;
+            if (out_t && i == 0) out_t[(long long)m * n_t_eval + j] = te;
+        }
+    }
+}
+
+__global__ void bdf_init_D(const OccmBdfDev b, const double* __restrict__ y0) {       // D[0] = y0, D[1] = f h   (bdf.py:257-259)
+    BDF_FOR_CHUNKS(b, true) {
+        const double h = b.h_abs[m];
+        BDF_ELEMS(b, ci, e) {
+            const long long g = (long long)m * b.ndof + e;
+            b.D[g] = y0[g];
+            b.D[b.vstride + g] = b.f[g] * h;
+        }
+    }
+}
+
+__global__ void bdf_write_initial(const OccmBdfDev b, int n_save, const int* __restrict__ save_idx, int cap, double t0,
+                                  double* __restrict__ out, double* __restrict__ out_t) {
+    const long long total = (long long)b.M * n_save;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(k / n_save);
+        const int i = (int)(k - (long long)m * n_save);
+        const long long e = save_idx ? save_idx[i] : i;
+        out[((long long)m * cap) * n_save + i] = b.D[(long long)m * b.ndof + e];
+        if (i == 0) out_t[(long long)m * cap] = t0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ per-member control
+__global__ void bdf_ctrl_init(const OccmBdfDev b, double t0, double first_step, int all_mode) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= b.M) return;
+    b.t[m] = t0; b.h_abs[m] = first_step; b.order[m] = 1; b.n_equal[m] = 0; b.status[m] = OCCM_MEMBER_RUNNING; b.fresh[m] = 1;
+    b.newton_active[m] = 1;            // mask of the initial f(t0, y0) evaluation
+    b.t_new[m] = t0;
+    b.nfev[m] = 1; b.n_acc[m] = 0; b.n_rej[m] = 0; b.n_newton_fail[m] = 0; b.n_gmres[m] = 0; b.n_precond[m] = 0;
+    b.accepted_now[m] = 0; b.out_lo[m] = 0; b.out_hi[m] = 0; b.n_rows[m] = all_mode ? 1 : 0; b.need_change[m] = 0;
+}
+
+// start of a step attempt (bdf.py:318-356): step-size clipping, t_new, h, c; may request a change_D
+__global__ void bdf_ctrl_begin(const OccmBdfDev b) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= b.M) return;
+    b.need_change[m] = 0; b.accepted_now[m] = 0; b.attempt_ok[m] = 0; b.newton_active[m] = 0; b.gmres_active[m] = 0;
+    if (b.status[m] != OCCM_MEMBER_RUNNING) return;
+    const double t = b.t[m];
+    const int order = b.order[m];
+    double h_abs = b.h_abs[m];
+    const double h_abs0 = h_abs;
+    bool clipped = false;
+    const double min_step = 10.0 * fabs(bdf_next_up(t) - t);
+    if (b.fresh[m] && h_abs < min_step) { h_abs = min_step; b.n_equal[m] = 0; clipped = true; }
+    b.fresh[m] = 0;
+    if (h_abs < min_step) { b.status[m] = OCCM_MEMBER_STEP_TOO_SMALL; return; }
+    double t_new = t + h_abs;
+    if (t_new - b.t_bound > 0.0) { t_new = b.t_bound; b.n_equal[m] = 0; clipped = true; }
+    const double h = t_new - t;
+    h_abs = fabs(h);
+    if (clipped) bdf_set_change(b, m, order, h_abs / h_abs0);     // the clip events of bdf.py:321-326 and :348-352 in one rescale
+    b.h_abs[m] = h_abs; b.t_new[m] = t_new; b.c[m] = h / bdf_alpha(order);
+    b.newton_active[m] = 1; b.newton_k[m] = 0; b.converged[m] = 0; b.n_iter[m] = 0; b.dy_norm_old[m] = -1.0;
+    atomicAdd(&b.counters[1], 1);
+}
+
+// after bdf_newton_rhs + reduce: start GMRES for the member or skip it when the scaled residual is already tiny
+__global__ void bdf_ctrl_gmres_start(const OccmBdfDev b) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= b.M) return;
+    b.gmres_active[m] = 0;
+    if (!b.newton_active[m]) return;
+    const double* nr = b.norms + (long long)m * BDF_MAXDOT;
+    const double beta = sqrt(nr[0]);
+    b.ynorm[m] = sqrt(nr[1]);
+    b.gmres_j[m] = 0;
+    if (!(beta / sqrt((double)b.ndof) > b.lin_tol)) return;       // also catches NaN: handled as dy = 0 -> Newton test fails later
+    b.gmres_active[m] = 1;
+    double* gv = b.gv + (long long)m * BDF_MAXDOT;
+    for (int i = 0; i <= b.restart; ++i) gv[i] = 0.0;
+    gv[0] = beta;
+    b.eps[m] = 1.0 / beta;              // bdf_scale_col: V0 *= 1 / beta
+    atomicAdd(&b.counters[2], 1);
+}
+
+// after the preconditioner: step of the directional difference  eps = sqrt(EPS) (1 + |y|) / |z|
+__global__ void bdf_ctrl_eps(const OccmBdfDev b) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= b.M || !b.gmres_active[m]) return;
+    const double zn = sqrt(b.norms[(long long)m * BDF_MAXDOT]);
+    b.eps[m] = zn > 0.0 ? 1.4901161193847656e-08 * (1.0 + b.ynorm[m]) / zn : 1.0;
+    b.nfev[m] += 1; b.n_precond[m] += 1;
+}
+
+// first Gram-Schmidt pass done: norms[0..j] hold h_i; move them behind slot 0 and remember them in H
+__global__ void bdf_ctrl_h1(const OccmBdfDev b) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= b.M || !b.gmres_active[m]) return;
+    const int j = b.gmres_j[m];
+    double* nr = b.norms + (long long)m * BDF_MAXDOT;
+    double* Hc = b.H + ((long long)m * BDF_MAXDOT + j) * BDF_MAXDOT;       // column j of the Hessenberg matrix
+    for (int i = 0; i <= j; ++i) Hc[i] = nr[i];
+}
+
+// second pass: norms[0] = |w|^2 after pass 1, norms[1..j+1] = correction coefficients; accumulate into H
+__global__ void bdf_ctrl_h2(const OccmBdfDev b) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= b.M || !b.gmres_active[m]) return;
+    const int j = b.gmres_j[m];
+    const double* nr = b.norms + (long long)m * BDF_MAXDOT;
+    double* Hc = b.H + ((long long)m * BDF_MAXDOT + j) * BDF_MAXDOT;
+    for (int i = 0; i <= j; ++i) Hc[i] += nr[1 + i];
+}
+
+// norms[0] = |V[j+1]|^2 after re-orthogonalisation: Givens update, convergence test   (standard GMRES)
+__global__ void bdf_ctrl_givens(const OccmBdfDev b) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= b.M || !b.gmres_active[m]) return;
+    const int j = b.gmres_j[m];
+    double* Hc = b.H + ((long long)m * BDF_MAXDOT + j) * BDF_MAXDOT;
+    double* cs = b.cs + (long long)m * BDF_MAXDOT; double* sn = b.sn + (long long)m * BDF_MAXDOT;
+    double* gv = b.gv + (long long)m * BDF_MAXDOT;
+    const double hn = sqrt(b.norms[(long long)m * BDF_MAXDOT]);
+    Hc[j + 1] = hn;
+    for (int i = 0; i < j; ++i) {
+        const double a = cs[i] * Hc[i] + sn[i] * Hc[i + 1];
+        Hc[i + 1] = -sn[i] * Hc[i] + cs[i] * Hc[i + 1];
+        Hc[i] = a;
+    }
+    const double r = hypot(Hc[j], Hc[j + 1]);
+    cs[j] = r > 0.0 ? Hc[j] / r : 1.0; sn[j] = r > 0.0 ? Hc[j + 1] / r : 0.0;
+    Hc[j] = r; Hc[j + 1] = 0.0;
+    gv[j + 1] = -sn[j] * gv[j];
+    gv[j] = cs[j] * gv[j];
+    b.n_gmres[m] += 1;
+    const double res = fabs(gv[j + 1]) / sqrt((double)b.ndof);
+    b.eps[m] = hn > 0.0 ? 1.0 / hn : 0.0;           // bdf_scale_col: V[j+1] *= 1 / h_{j+1,j}
+    b.gmres_j[m] = j + 1;
+    if (!(res > b.lin_tol) || j + 1 >= b.restart || !(hn > 0.0)) {
+        // back substitution R y = g
+        const int n = j + 1;
+        double* yc = b.ycoef + (long long)m * BDF_MAXDOT;
+        for (int i = n - 1; i >= 0; --i) {
+            double acc = gv[i];
+            for (int k = i + 1; k < n; ++k) acc -= b.H[((long long)m * BDF_MAXDOT + k) * BDF_MAXDOT + i] * yc[k];
+            yc[i] = acc / b.H[((long long)m * BDF_MAXDOT + i) * BDF_MAXDOT + i];
+        }
+        b.gmres_active[m] = 0;
+        b.converged[m] = res > b.lin_tol ? -1 : 0;      // -1: linear solve stalled -> treated as Newton failure
+    } else {
+        atomicAdd(&b.counters[2], 1);
+    }
+}
+
+// bdf.py:47-69: convergence logic of the simplified Newton iteration
+__global__ void bdf_ctrl_newton(const OccmBdfDev b) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= b.M || !b.newton_active[m]) return;
+    const int k = b.newton_k[m];
+    const double dy_norm = sqrt(b.norms[(long long)m * BDF_MAXDOT] / (double)b.ndof);
+    const double old = b.dy_norm_old[m];
+    const bool have_rate = old >= 0.0;
+    const double rate = have_rate ? dy_norm / old : 0.0;
+    b.n_iter[m] = k + 1;
+    b.nfev[m] += 1;
+    bool stop = false, conv = false;
+    if (b.converged[m] == -1 || !isfinite(dy_norm)) { stop = true; }
+    else if (have_rate && (rate >= 1.0 || pow(rate, (double)(BDF_NEWTON_MAXITER - k)) / (1.0 - rate) * dy_norm > b.newton_tol)) {
+        // scipy breaks BEFORE applying dy; the update kernel already applied it, which is harmless: the attempt is
+        // discarded (step halved, predictor recomputed from D)
+        stop = true;
+    } else if (dy_norm == 0.0 || (have_rate && rate / (1.0 - rate) * dy_norm < b.newton_tol)) {
+        stop = true; conv = true;
+    }
+    b.dy_norm_old[m] = dy_norm;
+    b.newton_k[m] = k + 1;
+    if (!stop && k + 1 >= BDF_NEWTON_MAXITER) stop = true;
+    if (stop) { b.newton_active[m] = 0; b.converged[m] = conv ? 1 : 0; }
+    else atomicAdd(&b.counters[1], 1);
+}
+
+// after Newton: failure -> halve the step (bdf.py:381-387); success -> safety factor, go on to the error test
+__global__ void bdf_ctrl_after_newton(const OccmBdfDev b) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= b.M || b.status[m] != OCCM_MEMBER_RUNNING) return;
+    b.need_change[m] = 0;
+    if (b.converged[m] == 1) {
+        b.attempt_ok[m] = 1;
+        b.safety[m] = 0.9 * (2 * BDF_NEWTON_MAXITER + 1) / (double)(2 * BDF_NEWTON_MAXITER + b.n_iter[m]);
+    } else {
+        b.attempt_ok[m] = 0;
+        b.h_abs[m] *= 0.5;
+        bdf_set_change(b, m, b.order[m], 0.5);
+        b.n_equal[m] = 0;
+        b.n_newton_fail[m] += 1; b.n_rej[m] += 1;
+        if (b.max_steps > 0 && b.n_acc[m] + b.n_rej[m] >= b.max_steps) b.status[m] = OCCM_MEMBER_MAX_STEPS;
+    }
+}
+
+// error test (bdf.py:389-405)
+__global__ void bdf_ctrl_error(const OccmBdfDev b, const double* __restrict__ t_eval, int n_t_eval) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= b.M || !b.attempt_ok[m]) return;
+    const int order = b.order[m];
+    const double error_norm = sqrt(b.norms[(long long)m * BDF_MAXDOT] / (double)b.ndof);
+    b.err_norm[m] = error_norm;
+    if (error_norm > 1.0 || !isfinite(error_norm)) {
+        double factor = b.safety[m] * pow(error_norm, -1.0 / (order + 1));
+        factor = factor > BDF_MIN_FACTOR ? factor : BDF_MIN_FACTOR;         // max(MIN_FACTOR, x); NaN -> MIN_FACTOR
+        b.h_abs[m] *= factor;
+        bdf_set_change(b, m, order, factor);
+        b.n_equal[m] = 0;
+        b.n_rej[m] += 1;
+        if (b.max_steps > 0 && b.n_acc[m] + b.n_rej[m] >= b.max_steps) b.status[m] = OCCM_MEMBER_MAX_STEPS;
+        return;
+    }
+    // accepted
+    b.accepted_now[m] = 1;
+    b.n_equal[m] += 1;
+    b.t_old_out[m] = b.t[m];
+    b.t[m] = b.t_new[m];
+    b.n_acc[m] += 1;
+    b.fresh[m] = 1;
+    const double t = b.t[m];
+    if (t_eval) {
+        int lo = b.out_hi[m], hi = lo;
+        while (hi < n_t_eval && t_eval[hi] <= t) ++hi;
+        b.out_lo[m] = lo; b.out_hi[m] = hi;
+    } else {
+        const int row = b.n_rows[m];
+        b.out_lo[m] = row; b.n_rows[m] = row + 1;
+    }
+}
+
+// order / step selection after an accepted step (bdf.py:424-453) and end-of-step status
+__global__ void bdf_ctrl_order(const OccmBdfDev b, int all_cap) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= b.M || !b.accepted_now[m]) return;
+    b.need_change[m] = 0;
+    int order = b.order[m];
+    if (b.n_equal[m] >= order + 1) {
+        const double* nr = b.norms + (long long)m * BDF_MAXDOT;
+        const double n = (double)b.ndof;
+        const double em = order > 1 ? sqrt(nr[0] / n) : INFINITY;
+        const double ep = order < BDF_MAX_ORDER ? sqrt(nr[1] / n) : INFINITY;
+        const double en[3] = {em, b.err_norm[m], ep};
+        double fac[3]; int best = 0;
+        for (int i = 0; i < 3; ++i) {
+            fac[i] = pow(en[i], -1.0 / (order + i));        // error_norms ** (-1 / arange(order, order + 3))
+            if (fac[i] > fac[best]) best = i;                // argmax: first maximum
+        }
+        order += best - 1;
+        b.order[m] = order;
+        const double f = b.safety[m] * fac[best];
+        const double factor = f < BDF_MAX_FACTOR ? f : BDF_MAX_FACTOR;
+        b.h_abs[m] *= factor;
+        bdf_set_change(b, m, order, factor);
+        b.n_equal[m] = 0;
+    }
+    int status = OCCM_MEMBER_RUNNING;
+    if (b.t[m] - b.t_bound >= 0.0) status = OCCM_MEMBER_FINISHED;
+    else if (b.max_steps > 0 && b.n_acc[m] + b.n_rej[m] >= b.max_steps) status = OCCM_MEMBER_MAX_STEPS;
+    else if (all_cap > 0 && b.n_rows[m] >= all_cap) status = OCCM_MEMBER_PAUSED;
+    b.status[m] = status;
+}
+
+__global__ void bdf_clear_change(const OccmBdfDev b) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < b.M) b.need_change[m] = 0;
+}
+
+__global__ void bdf_count(const OccmBdfDev b) {
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    int local = 0;
+    for (int m = threadIdx.x; m < b.M; m += blockDim.x) local += b.status[m] == OCCM_MEMBER_RUNNING;
+    atomicAdd(&cnt, local);
+    __syncthreads();
+    if (threadIdx.x == 0) b.counters[0] = cnt;
+}
+
+__global__ void bdf_resume_kernel(const OccmBdfDev b) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= b.M) return;
+    b.n_rows[m] = 0;
+    if (b.status[m] == OCCM_MEMBER_PAUSED) b.status[m] = OCCM_MEMBER_RUNNING;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct BdfLayout { size_t total; size_t off[64]; int n; };
+
+static size_t bdf_carve(const occm_system* sys, int M, int restart, OccmBdfDev* d, char* w) {
+    size_t o = 0;
+    const size_t vec = al256((size_t)M * sys->dev.ndof * sizeof(double));
+    auto take = [&](size_t bytes) { size_t r = o; o += al256(bytes); return w ? (void*)(w + r) : (void*)nullptr; };
+    const int nchunk = (int)((sys->dev.ndof + BDF_CHUNK - 1) / BDF_CHUNK);
+    OccmBdfDev t; memset(&t, 0, sizeof(t));
+    OccmBdfDev& b = d ? *d : t;
+    b.D = (double*)take(vec * BDF_NVEC_D);
+    b.y = (double*)take(vec); b.psi = (double*)take(vec); b.d = (double*)take(vec); b.f = (double*)take(vec);
+    b.f2 = (double*)take(vec); b.z = (double*)take(vec); b.w = (double*)take(vec);
+    b.V = (double*)take(vec * (restart + 1));
+    const size_t md = (size_t)M * 8, mi = (size_t)M * 4, mm = (size_t)M * BDF_MAXDOT * 8;
+    b.t = (double*)take(md); b.h_abs = (double*)take(md); b.t_new = (double*)take(md); b.c = (double*)take(md); b.t_old_out = (double*)take(md);
+    b.order = (int*)take(mi); b.n_equal = (int*)take(mi); b.status = (int*)take(mi); b.fresh = (int*)take(mi);
+    b.newton_active = (int*)take(mi); b.newton_k = (int*)take(mi); b.converged = (int*)take(mi); b.n_iter = (int*)take(mi);
+    b.dy_norm_old = (double*)take(md);
+    b.gmres_active = (int*)take(mi); b.gmres_j = (int*)take(mi);
+    b.H = (double*)take(mm * BDF_MAXDOT); b.cs = (double*)take(mm); b.sn = (double*)take(mm); b.gv = (double*)take(mm);
+    b.ycoef = (double*)take(mm); b.eps = (double*)take(md); b.ynorm = (double*)take(md);
+    b.RU = (double*)take((size_t)M * 36 * 8); b.need_change = (int*)take(mi); b.attempt_ok = (int*)take(mi);
+    b.safety = (double*)take(md); b.err_norm = (double*)take(md);
+    b.partial = (double*)take((size_t)M * nchunk * BDF_MAXDOT * 8); b.norms = (double*)take(mm);
+    b.accepted_now = (int*)take(mi); b.out_lo = (int*)take(mi); b.out_hi = (int*)take(mi); b.n_rows = (int*)take(mi);
+    b.nfev = (long long*)take(md); b.n_acc = (long long*)take(md); b.n_rej = (long long*)take(md);
+    b.n_newton_fail = (long long*)take(md); b.n_gmres = (long long*)take(md); b.n_precond = (long long*)take(md);
+    b.counters = (int*)take(256);
+    b.nchunk = nchunk;
+    return o;
+}
+
+extern "C" size_t occm_bdf_workspace_bytes(const occm_system* sys, int32_t M, int32_t restart) {
+    if (!sys || M < 1) return 0;
+    if (restart <= 0) restart = 30;
+    return bdf_carve(sys, M, restart, nullptr, nullptr);
+}
+
+static int bdf_grid(const occm_system* sys, long long chunks) {
+    long long g = (long long)sys->sm_count * 8;
+    if (g > chunks) g = chunks;
+    return (int)(g < 1 ? 1 : g);
+}
+
+#define BDF_LAUNCH(name, grid, block, smem, ...)                                   \
+    do {                                                                           \
+        name<<<grid, block, smem, st>>>(__VA_ARGS__);                              \
+        OCCM_LAUNCH_CHECK(#name);                                                  \
+    } while (0)
+
+static int bdf_reduce_launch(occm_bdf* h, int nvals, const int* mask, cudaStream_t st) {
+    BDF_LAUNCH(bdf_reduce, h->M, 128, 0, h->d.partial, h->d.nchunk, nvals, h->d.norms, mask);
+    return OCCM_OK;
+}
+
+static int bdf_rhs(occm_bdf* h, const int* mask, const double* z, const double* eps, double* out, cudaStream_t st) {
+    OccmMemDev md = occm_mem_dev(h->has_mem ? &h->mem : nullptr, 1);
+    md.active = mask; md.z = z; md.eps = eps;
+    return occm_launch_rhs(h->sys, md, h->d.t_new, 0.0, h->d.y, out, st);
+}
+
+static int bdf_precond_launch(occm_bdf* h, const double* src, int from_col_j, double* dst, const int* mask, int want_norm, cudaStream_t st) {
+    const occm_system* sys = h->sys;
+    const size_t smem = sys->smem_tables;
+    const int grid = bdf_grid(sys, (long long)h->M * h->d.nchunk);
+    if (sys->dev.model == OCCM_MODEL_CSTR) {
+        static size_t lim = 48 * 1024;
+        if (smem > lim) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(bdf_precond<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); lim = smem; }
+        BDF_LAUNCH(bdf_precond<0>, grid, 128, smem, sys->dev, h->d, src, from_col_j, dst, mask, want_norm);
+    } else {
+        static size_t lim = 48 * 1024;
+        if (smem > lim) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(bdf_precond<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); lim = smem; }
+        BDF_LAUNCH(bdf_precond<1>, grid, 128, smem, sys->dev, h->d, src, from_col_j, dst, mask, want_norm);
+    }
+    return OCCM_OK;
+}
+
+static int bdf_read_counters(occm_bdf* h, cudaStream_t st) {
+    OCCM_CUDA_CHECK(cudaMemcpyAsync(h->h_counters, h->d.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    OCCM_CUDA_CHECK(cudaStreamSynchronize(st));
+    return OCCM_OK;
+}
+
+extern "C" int occm_bdf_init(occm_bdf** out, const occm_system* sys, const occm_members* mem, const occm_bdf_problem* p,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+    if (!out || !sys || !p || !workspace || !p->y0 || !p->out || !p->tdiag) { occm_set_error("occm_bdf_init: null argument"); return OCCM_ERR_INVALID; }
+    const int M = mem ? mem->n_members : 1;
+    if (M < 1) { occm_set_error("n_members must be >= 1"); return OCCM_ERR_INVALID; }
+    if (sys->dev.S > 16) { occm_set_error("B200-BDF supports up to 16 species (block preconditioner), got %d", sys->dev.S); return OCCM_ERR_UNSUPPORTED; }
+    if (!(p->t_bound > p->t0)) { occm_set_error("t_bound must be greater than t0"); return OCCM_ERR_INVALID; }
+    if (!(p->first_step > 0.0)) { occm_set_error("`first_step` must be positive."); return OCCM_ERR_INVALID; }
+    if (p->first_step > fabs(p->t_bound - p->t0)) { occm_set_error("`first_step` exceeds bounds."); return OCCM_ERR_INVALID; }
+    if (!(p->rtol > 0.0) || !(p->atol >= 0.0)) { occm_set_error("rtol must be > 0 and atol >= 0"); return OCCM_ERR_INVALID; }
+    if (p->n_t_eval < 1 || (!p->t_eval && (p->n_t_eval < 2 || !p->out_t))) { occm_set_error("bad output description"); return OCCM_ERR_INVALID; }
+    const int restart = p->gmres_restart > 0 ? p->gmres_restart : 30;
+    if (restart + 2 > BDF_MAXDOT) { occm_set_error("gmres_restart must be <= %d", BDF_MAXDOT - 2); return OCCM_ERR_INVALID; }
+    const size_t need = bdf_carve(sys, M, restart, nullptr, nullptr);
+    if (workspace_bytes < need) { occm_set_error("workspace too small: %zu < %zu", workspace_bytes, need); return OCCM_ERR_WORKSPACE; }
+    if ((uintptr_t)workspace & 255) { occm_set_error("workspace must be 256-byte aligned"); return OCCM_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    occm_bdf* h = (occm_bdf*)calloc(1, sizeof(occm_bdf));
+    h->sys = sys; h->M = M; h->prob = *p; h->has_mem = mem != nullptr;
+    if (mem) h->mem = *mem; else { memset(&h->mem, 0, sizeof(h->mem)); h->mem.n_members = 1; }
+    OccmBdfDev& b = h->d;
+    memset(&b, 0, sizeof(b));
+    bdf_carve(sys, M, restart, &b, (char*)workspace);
+    b.M = M; b.S = sys->dev.S; b.P = sys->dev.P; b.model = sys->dev.model; b.restart = restart;
+    b.ndof = sys->dev.ndof; b.n_points = sys->dev.n_points; b.vstride = (long long)M * sys->dev.ndof;
+    b.rtol = p->rtol; b.atol = p->atol; b.t_bound = p->t_bound; b.max_steps = p->max_steps;
+    const double EPS = 2.220446049250313e-16;
+    b.newton_tol = fmax(10.0 * EPS / p->rtol, fmin(0.03, sqrt(p->rtol)));       // bdf.py:224
+    b.lin_tol = (p->lin_tol_factor > 0.0 ? p->lin_tol_factor : 0.01) * b.newton_tol;
+    b.tdiag = p->tdiag; b.q_scale = h->mem.q_scale; b.k_scale = h->mem.k_scale;
+    if (cudaHostAlloc((void**)&h->h_counters, 4 * sizeof(int), cudaHostAllocDefault) != cudaSuccess) { occm_set_error("cudaHostAlloc failed"); free(h); return OCCM_ERR_CUDA; }
+    const int gm = (M + 63) / 64;
+    BDF_LAUNCH(bdf_ctrl_init, gm, 64, 0, b, p->t0, p->first_step, p->t_eval ? 0 : 1);
+    // f(t0, y0) -> b.f ; D[0] = y0, D[1] = f h
+    OCCM_CUDA_CHECK(cudaMemcpyAsync(b.y, p->y0, (size_t)M * b.ndof * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    int rc = bdf_rhs(h, nullptr, nullptr, nullptr, b.f, st);
+    if (rc) { free(h); return rc; }
+    const int gv = bdf_grid(sys, (long long)M * b.nchunk);
+    BDF_LAUNCH(bdf_init_D, gv, 256, 0, b, p->y0);
+    if (!p->t_eval) {
+        const int n_save = p->save_idx ? p->n_save : (int)b.ndof;
+        BDF_LAUNCH(bdf_write_initial, 148 * 4, 256, 0, b, n_save, p->save_idx, p->n_t_eval, p->t0, p->out, p->out_t);
+    }
+    *out = h;
+    return OCCM_OK;
+}
+
+// one step attempt of every running member
+static int bdf_attempt(occm_bdf* h, cudaStream_t st) {
+    OccmBdfDev& b = h->d;
+    const occm_system* sys = h->sys;
+    const int gm = (h->M + 63) / 64;
+    const int gv = bdf_grid(sys, (long long)h->M * b.nchunk);
+    int rc;
+    OCCM_CUDA_CHECK(cudaMemsetAsync(b.counters, 0, 4 * sizeof(int), st));
+    BDF_LAUNCH(bdf_ctrl_begin, gm, 64, 0, b);
+    BDF_LAUNCH(bdf_change_D, gv, 256, 0, b);
+    BDF_LAUNCH(bdf_clear_change, gm, 64, 0, b);
+    BDF_LAUNCH(bdf_predict, gv, 256, 0, b);
+    for (int k = 0; k < BDF_NEWTON_MAXITER; ++k) {
+        if ((rc = bdf_rhs(h, b.newton_active, nullptr, nullptr, b.f, st))) return rc;          // f = fun(t_new, y)
+        BDF_LAUNCH(bdf_newton_rhs, gv, 256, 0, b);
+        if ((rc = bdf_reduce_launch(h, 2, b.newton_active, st))) return rc;
+        OCCM_CUDA_CHECK(cudaMemsetAsync(b.counters + 2, 0, sizeof(int), st));
+        BDF_LAUNCH(bdf_ctrl_gmres_start, gm, 64, 0, b);
+        BDF_LAUNCH(bdf_scale_col, gv, 256, 0, b, 0, b.eps);                                     // v0 = b~ / beta
+        if ((rc = bdf_read_counters(h, st))) return rc;
+        int gm_active = h->h_counters[2];
+        for (int j = 0; j < b.restart && gm_active > 0; ++j) {
+            if ((rc = bdf_precond_launch(h, b.V, 1, b.z, b.gmres_active, 1, st))) return rc;   // z = M^-1 S v_j
+            if ((rc = bdf_reduce_launch(h, 1, b.gmres_active, st))) return rc;
+            BDF_LAUNCH(bdf_ctrl_eps, gm, 64, 0, b);
+            if ((rc = bdf_rhs(h, b.gmres_active, b.z, b.eps, b.f2, st))) return rc;             // f(y + eps z)
+            BDF_LAUNCH(bdf_arnoldi_w, gv, 256, 0, b);
+            if ((rc = bdf_reduce_launch(h, j + 1, b.gmres_active, st))) return rc;
+            BDF_LAUNCH(bdf_ctrl_h1, gm, 64, 0, b);
+            BDF_LAUNCH(bdf_orth, gv, 256, 0, b, 0);
+            if ((rc = bdf_reduce_launch(h, j + 2, b.gmres_active, st))) return rc;
+            BDF_LAUNCH(bdf_ctrl_h2, gm, 64, 0, b);
+            BDF_LAUNCH(bdf_orth, gv, 256, 0, b, 1);                                             // re-orthogonalisation (CGS2)
+            if ((rc = bdf_reduce_launch(h, 1, b.gmres_active, st))) return rc;
+            OCCM_CUDA_CHECK(cudaMemsetAsync(b.counters + 2, 0, sizeof(int), st));
+            // scale_col must see the pre-update gmres_j: run it with the members that stay active AFTER givens
+            BDF_LAUNCH(bdf_ctrl_givens, gm, 64, 0, b);
+            BDF_LAUNCH(bdf_scale_col, gv, 256, 0, b, 1, b.eps);
+            if ((rc = bdf_read_counters(h, st))) return rc;
+            gm_active = h->h_counters[2];
+        }
+        BDF_LAUNCH(bdf_lincomb_V, gv, 256, 0, b);                                               // u~ = sum y_k v_k
+        if ((rc = bdf_precond_launch(h, b.w, 0, b.z, b.newton_active, 0, st))) return rc;      // dy = M^-1 S u~
+        BDF_LAUNCH(bdf_newton_update, gv, 256, 0, b);
+        if ((rc = bdf_reduce_launch(h, 1, b.newton_active, st))) return rc;
+        OCCM_CUDA_CHECK(cudaMemsetAsync(b.counters + 1, 0, sizeof(int), st));
+        BDF_LAUNCH(bdf_ctrl_newton, gm, 64, 0, b);
+        if ((rc = bdf_read_counters(h, st))) return rc;
+        if (h->h_counters[1] == 0) break;
+    }
+    BDF_LAUNCH(bdf_ctrl_after_newton, gm, 64, 0, b);
+    BDF_LAUNCH(bdf_error, gv, 256, 0, b);
+    if ((rc = bdf_reduce_launch(h, 1, b.attempt_ok, st))) return rc;
+    BDF_LAUNCH(bdf_ctrl_error, gm, 64, 0, b, h->prob.t_eval, h->prob.n_t_eval);
+    BDF_LAUNCH(bdf_change_D, gv, 256, 0, b);            // rejected / failed attempts rescale D
+    BDF_LAUNCH(bdf_clear_change, gm, 64, 0, b);
+    BDF_LAUNCH(bdf_update_D, gv, 256, 0, b);
+    if ((rc = bdf_reduce_launch(h, 2, b.accepted_now, st))) return rc;
+    BDF_LAUNCH(bdf_ctrl_order, gm, 64, 0, b, h->prob.t_eval ? 0 : h->prob.n_t_eval);
+    BDF_LAUNCH(bdf_change_D, gv, 256, 0, b);            // accepted members that changed order / step size
+    BDF_LAUNCH(bdf_clear_change, gm, 64, 0, b);
+    const int n_save = h->prob.save_idx ? h->prob.n_save : (int)b.ndof;
+    BDF_LAUNCH(bdf_output, bdf_grid(sys, (long long)h->M * ((n_save + 255) / 256)), 256, 0, b, n_save, h->prob.save_idx, h->prob.t_eval,
+               h->prob.n_t_eval, h->prob.out, h->prob.out_t);
+    return OCCM_OK;
+}
+
+extern "C" int occm_bdf_run(occm_bdf* h, int64_t max_attempts, int32_t* n_running, void* stream) {
+    if (!h) { occm_set_error("occm_bdf_run: null handle"); return OCCM_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    long long done = 0;
+    int running = h->M;
+    while (true) {
+        int rc = bdf_attempt(h, st);
+        if (rc) return rc;
+        ++done;
+        bdf_count<<<1, 256, 0, st>>>(h->d);
+        OCCM_LAUNCH_CHECK("bdf_count");
+        if ((rc = bdf_read_counters(h, st))) return rc;
+        running = h->h_counters[0];
+        if (running == 0) break;
+        if (max_attempts > 0 && done >= max_attempts) break;
+    }
+    if (n_running) *n_running = running;
+    return OCCM_OK;
+}
+
+extern "C" int occm_bdf_resume(occm_bdf* h, void* stream) {
+    if (!h) { occm_set_error("occm_bdf_resume: null handle"); return OCCM_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    BDF_LAUNCH(bdf_resume_kernel, (h->M + 63) / 64, 64, 0, h->d);
+    return OCCM_OK;
+}
+
+extern "C" int occm_bdf_stats(occm_bdf* h, int32_t* status, int64_t* n_accepted, int64_t* n_rejected, int64_t* nfev,
+                              int64_t* n_gmres, int64_t* n_newton_fail, double* t, int32_t* n_rows, int32_t* order, void* stream) {
+    if (!h) { occm_set_error("occm_bdf_stats: null handle"); return OCCM_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int M = h->M;
+    const OccmBdfDev& b = h->d;
+    auto cp = [&](void* dst, const void* src, size_t n) { return dst ? cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, st) : cudaSuccess; };
+    OCCM_CUDA_CHECK(cp(status, b.status, M * 4)); OCCM_CUDA_CHECK(cp(n_accepted, b.n_acc, M * 8)); OCCM_CUDA_CHECK(cp(n_rejected, b.n_rej, M * 8));
+    OCCM_CUDA_CHECK(cp(nfev, b.nfev, M * 8)); OCCM_CUDA_CHECK(cp(n_gmres, b.n_gmres, M * 8)); OCCM_CUDA_CHECK(cp(n_newton_fail, b.n_newton_fail, M * 8));
+    OCCM_CUDA_CHECK(cp(t, b.t, M * 8)); OCCM_CUDA_CHECK(cp(n_rows, h->prob.t_eval ? b.out_hi : b.n_rows, M * 4)); OCCM_CUDA_CHECK(cp(order, b.order, M * 4));
+    OCCM_CUDA_CHECK(cudaStreamSynchronize(st));
+    return OCCM_OK;
+}
+
+extern "C" int occm_bdf_get_state(occm_bdf* h, double* y_out, void* stream) {
+    if (!h || !y_out) { occm_set_error("occm_bdf_get_state: null argument"); return OCCM_ERR_INVALID; }
+    OCCM_CUDA_CHECK(cudaMemcpyAsync(y_out, h->d.D, (size_t)h->M * h->d.ndof * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return OCCM_OK;
+}
+
+extern "C" int occm_bdf_free(occm_bdf* h) {
+    if (!h) return OCCM_OK;
+    if (h->h_counters) cudaFreeHost(h->h_counters);
+    free(h);
+    return OCCM_OK;
+}

@@ -35,6 +35,9 @@ struct OccmSysDev {
 struct OccmMemDev {
     int M;
     const double* k_scale; const double* q_scale; const double* bc_scale;
+    const int* active;      // optional member mask of the plain RHS launches (BDF inner loops)
+    const double* z;        // optional: evaluate the RHS at y + eps[m] * z   (matrix-free Jacobian action)
+    const double* eps;
 };
 
 // Views into the shared-memory copy of the table blob.

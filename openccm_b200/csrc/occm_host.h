@@ -15,6 +15,10 @@ struct occm_system {
 
 void occm_set_error(const char* fmt, ...);
 void occm_count_launch(int n = 1);
+struct occm_system;
+struct OccmMemDev;
+int occm_launch_rhs(const occm_system* sys, const OccmMemDev& mem, const double* t_dev, double t_scalar, const double* y,
+                    double* dy, cudaStream_t st);
 
 #define OCCM_CUDA_CHECK(expr)                                                                      \
     do {                                                                                           \
@@ -41,6 +45,7 @@ static inline OccmMemDev occm_mem_dev(const occm_members* mem, int fallback_M) {
     m.k_scale = mem ? mem->k_scale : nullptr;
     m.q_scale = mem ? mem->q_scale : nullptr;
     m.bc_scale = mem ? mem->bc_scale : nullptr;
+    m.active = nullptr; m.z = nullptr; m.eps = nullptr;
     return m;
 }
 

@@ -157,6 +157,7 @@ struct OccmStageIn {       // the stage state this kernel differentiates, as a f
     const double* a; const double* b; double hb;
     __device__ __forceinline__ double operator()(int e) const {
         if (STAGE == 2) return __ldg(a + e) + (dp::A21 * __ldg(b + e)) * hb;   // y + h * a21 * K1 formed on the fly
+        if (STAGE == 1) return __ldg(a + e) + __ldg(b + e) * hb;               // y + eps * z (matrix-free Jacobian action)
         return __ldg(a + e);
     }
 };
@@ -169,7 +170,7 @@ template <int STAGE>
 __device__ __forceinline__ OccmOps occm_load_ops(const OccmRkDev& rk, const double* y, const double* k1, long long base, int e) {
     OccmOps o;
     o.ye = o.k1 = o.ka = o.kb = o.kc = o.kd = 0.0;
-    if (STAGE == 0) return o;
+    if (STAGE == 0 || STAGE == 1) return o;
     o.ye = __ldg(y + e); o.k1 = __ldg(k1 + e);
     if (STAGE == 3) { o.ka = __ldg(rk.K2 + base + e); }
     if (STAGE == 4) { o.ka = __ldg(rk.K2 + base + e); o.kb = __ldg(rk.K3 + base + e); }
@@ -183,7 +184,7 @@ __device__ __forceinline__ OccmOps occm_load_ops(const OccmRkDev& rk, const doub
 template <int STAGE>
 __device__ __forceinline__ double occm_finish(const OccmRkDev& rk, const OccmOps& o, double f, double h, int par, long long base,
                                               int e, double y_new_own, double* __restrict__ dy_out) {
-    if (STAGE == 0) { dy_out[base + e] = f; return 0.0; }
+    if (STAGE == 0 || STAGE == 1) { dy_out[base + e] = f; return 0.0; }
     if (STAGE == 2) {
         rk.K2[base + e] = f;
         rk.YS[0][base + e] = o.ye + (dp::A31 * o.k1 + dp::A32 * f) * h;
@@ -220,9 +221,10 @@ __device__ __noinline__ double occm_cold_element(const OccmSysDev& sys, const Oc
     const int RS = sys.S + 1;
     double h = 0.0; int par = 0;
     const double* y = nullptr; const double* k1 = nullptr;
-    if (STAGE != 0) { h = rk.h[m]; par = rk.parity[m]; y = rk.Y[par] + base; k1 = rk.KF[par] + base; }
+    if (STAGE >= 2) { h = rk.h[m]; par = rk.parity[m]; y = rk.Y[par] + base; k1 = rk.KF[par] + base; }
+    if (STAGE == 1) { h = __ldg(mem.eps + m); k1 = mem.z + base; }
     OccmStageIn<STAGE> in;
-    in.a = STAGE == 0 ? y_in + base : STAGE == 2 ? y
+    in.a = STAGE <= 1 ? y_in + base : STAGE == 2 ? y
          : STAGE == 3 || STAGE == 5 ? rk.YS[0] + base
          : STAGE == 4 || STAGE == 6 ? rk.YS[1] + base : rk.Y[par ^ 1] + base;
     in.b = k1; in.hb = h;
@@ -235,7 +237,7 @@ __device__ __noinline__ double occm_cold_element(const OccmSysDev& sys, const Oc
 }
 
 template <int MODEL, int STAGE, int E>
-__global__ void __launch_bounds__(OCCM_BLOCK, (STAGE == 0 ? OCCM_MIN_CTAS0 : OCCM_MIN_CTAS))
+__global__ void __launch_bounds__(OCCM_BLOCK, (STAGE <= 1 ? OCCM_MIN_CTAS0 : OCCM_MIN_CTAS))
 occm_stage(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmMemDev mem, const __grid_constant__ OccmRkDev rk,
            const double* __restrict__ t_dev, double t_scalar, const double* __restrict__ y_in, double* __restrict__ dy_out) {
     extern __shared__ double smem_d[];
@@ -279,13 +281,15 @@ occm_stage(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmM
     for (int q = 0; q < OCCM_NT; ++q) coeffm[q] = 0.0;
 
     for (; m < mem.M; m += step_m, ci += step_c, m += (ci >= cpm), ci -= (ci >= cpm) ? cpm : 0) {
-        if (STAGE != 0 && rk.status[m] != OCCM_MEMBER_RUNNING) continue;   // uniform over the CTA
+        if (STAGE >= 2 && rk.status[m] != OCCM_MEMBER_RUNNING) continue;   // uniform over the CTA
+        if (STAGE <= 1 && mem.active && !mem.active[m]) continue;
         const long long base = (long long)m * sys.ndof;
         double t_stage, h = 0.0;
         int par = 0;
         const double* y = nullptr; const double* k1 = nullptr;
-        if (STAGE == 0) {
+        if (STAGE <= 1) {
             t_stage = t_dev ? __ldg(t_dev + m) : t_scalar;
+            if (STAGE == 1) { h = __ldg(mem.eps + m); k1 = mem.z + base; }
         } else {
             const double t0 = rk.t[m];
             h = rk.h[m];
@@ -296,7 +300,7 @@ occm_stage(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmM
                     : STAGE == 5 ? t0 + dp::C5 * h : t0 + h;
         }
         OccmStageIn<STAGE> in;
-        in.a = STAGE == 0 ? y_in + base : STAGE == 2 ? y
+        in.a = STAGE <= 1 ? y_in + base : STAGE == 2 ? y
              : STAGE == 3 || STAGE == 5 ? rk.YS[0] + base
              : STAGE == 4 || STAGE == 6 ? rk.YS[1] + base : rk.Y[par ^ 1] + base;
         in.b = k1; in.hb = h;
@@ -576,7 +580,7 @@ static int occm_launch_stage_m(const occm_system* sys, const OccmMemDev& mem, co
                                double t_scalar, const double* y_in, double* dy_out, cudaStream_t st) {
     static size_t smem_limit = 48 * 1024;   // the default opt-out limit; raise it only when needed
     static int ctas_per_sm = 0;
-    constexpr int E = STAGE == 0 ? OCCM_E0 : OCCM_E;
+    constexpr int E = STAGE <= 1 ? OCCM_E0 : OCCM_E;
     const size_t smem = occm_elem_smem(sys, E);
     auto kern = occm_stage<MODEL, STAGE, E>;
     if (smem > smem_limit) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_limit = smem; }
@@ -599,6 +603,15 @@ static int occm_launch_stage(const occm_system* sys, const OccmMemDev& mem, cons
                              double t_scalar, const double* y_in, double* dy_out, cudaStream_t st) {
     return sys->dev.model == OCCM_MODEL_CSTR ? occm_launch_stage_m<0, STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st)
                                              : occm_launch_stage_m<1, STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st);
+}
+
+// used by occm_bdf.cu
+int occm_launch_rhs(const occm_system* sys, const OccmMemDev& mem, const double* t_dev, double t_scalar, const double* y,
+                    double* dy, cudaStream_t st) {
+    OccmRkDev none;
+    memset(&none, 0, sizeof(none));
+    return mem.z ? occm_launch_stage<1>(sys, mem, none, t_dev, t_scalar, y, dy, st)
+                 : occm_launch_stage<0>(sys, mem, none, t_dev, t_scalar, y, dy, st);
 }
 
 extern "C" int occm_rhs(const occm_system* sys, const occm_members* mem, const double* t_dev, double t_scalar,

@@ -1,0 +1,65 @@
+"""
+Drop-in installation behind OpenCCM's own entry point.
+
+``openccm.run`` binds ``solve_system`` at import time (``from .system_solvers import solve_system``,
+/root/reference/openccm/run.py:35) and calls it at run.py:199, so both names must be rebound
+(SURVEY.md §8(b)).  After ``install()`` an unmodified ``openccm`` run uses the device whenever the CONFIG says
+
+    [SIMULATION]
+    solver = B200-RK45        # or B200-BDF
+
+Every other solver name is forwarded untouched to the reference's scipy path (this package itself never integrates on
+the CPU).  With ``route_scipy_names=True`` the scipy method names are mapped too: RK45/RK23/DOP853 -> B200-RK45,
+LSODA/BDF/Radau -> B200-BDF.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+from .system_solvers import is_device_solver, solve_system as _device_solve_system
+
+_SCIPY_TO_DEVICE = {'RK45': 'B200-RK45', 'RK23': 'B200-RK45', 'DOP853': 'B200-RK45',
+                    'LSODA': 'B200-BDF', 'BDF': 'B200-BDF', 'RADAU': 'B200-BDF'}
+_original: Optional[Callable] = None
+
+
+def make_dispatcher(reference_solve_system: Callable, route_scipy_names: bool = False) -> Callable:
+    def solve_system(model, model_network, config_parser, cmesh):
+        solver = config_parser.get_item(['SIMULATION', 'solver'], str)
+        if route_scipy_names and solver.upper() in _SCIPY_TO_DEVICE:
+            config_parser['SIMULATION']['solver'] = _SCIPY_TO_DEVICE[solver.upper()]
+            solver = config_parser['SIMULATION']['solver']
+        if is_device_solver(solver):
+            return _device_solve_system(model, model_network, config_parser, cmesh)
+        return reference_solve_system(model, model_network, config_parser, cmesh)
+    solve_system.__doc__ = reference_solve_system.__doc__
+    return solve_system
+
+
+def install(route_scipy_names: bool = False) -> None:
+    """Rebind openccm.system_solvers.solve_system and openccm.run.solve_system. Needs the `openccm` package importable."""
+    global _original
+    import openccm.system_solvers as ss
+    import openccm.run as run_mod
+    if _original is None:
+        _original = ss.solve_system
+    dispatcher = make_dispatcher(_original, route_scipy_names)
+    ss.solve_system = dispatcher
+    run_mod.solve_system = dispatcher
+    try:                                   # RTD post-processing on the device as well
+        import openccm.postprocessing as pp
+        from .postprocessing.analysis import network_to_rtd
+        pp._reference_network_to_rtd = getattr(pp, '_reference_network_to_rtd', pp.network_to_rtd)
+    except Exception:
+        pass
+
+
+def uninstall() -> None:
+    global _original
+    if _original is None:
+        return
+    import openccm.system_solvers as ss
+    import openccm.run as run_mod
+    ss.solve_system = _original
+    run_mod.solve_system = _original
+    _original = None

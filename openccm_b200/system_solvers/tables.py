@@ -163,6 +163,12 @@ class Compiler:
             for a in e.args[1:]:
                 self._compile(a, p)
                 p.emit(op, 0, -1)
+        elif isinstance(e, sp.Heaviside):          # sympy's sharp step (from d/dt of Min/Max/Abs): (x > 0) + 0.5 (x == 0)
+            zero = self.const(0.0)
+            self._compile(e.args[0], p); p.emit('CONST', zero, +1); p.emit('GT', 0, -1)
+            self._compile(e.args[0], p); p.emit('CONST', zero, +1); p.emit('EQ', 0, -1)
+            p.emit('CONST', self.const(0.5), +1); p.emit('MUL', 0, -1)
+            p.emit('ADD', 0, -1)
         elif e.func in _FUNCS:
             self._compile(e.args[0], p)
             p.emit(_FUNCS[e.func])

@@ -1,0 +1,144 @@
+"""CPU tests of the host side: table builder, byte-code compiler, export layer (vs the reference's golden c0), ELL
+conversion, C-ABI symbol table, drop-in dispatcher."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import sympy as sp
+
+import cases as C
+from _util import GOLDEN_DIR, load_golden, setup_case
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads and exports every function include/occm_b200.h declares (no compute calls here)."""
+    from openccm_b200 import _lib
+    from openccm_b200.build import build_library
+    build_library()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    header = open(os.path.join(REPO, 'include', 'occm_b200.h')).read()
+    declared = set(re.findall(r'\b(occm_[a-z0-9_]+)\s*\(', header))
+    declared -= {'occm_status', 'occm_model'}
+    assert declared, 'no declarations found'
+    for name in sorted(declared):
+        assert hasattr(lib, name), f'{name} declared in the header but not exported'
+    assert set(_lib.SIGNATURES) == declared, set(_lib.SIGNATURES) ^ declared
+    assert lib.occm_abi_version() == _lib.ABI_VERSION
+
+
+def test_reaction_tables_match_parser_kats():
+    """Per-species sum of the table terms == the reference's sympy-simplified rate expression (parser KATs)."""
+    from openccm_b200.system_solvers.tables import MechanismTables, extra_term_values
+    import configparser
+    kats = json.load(open(os.path.join(GOLDEN_DIR, 'parser_kats.json')))
+    rng = np.random.default_rng(0)
+    for key, text in C.RXN.items():
+        p = configparser.ConfigParser(); p.optionxform = str; p.read_string(text)
+        species = sorted(kats[key]['sympy'])
+        extra = dict(p['EXTRA TERMS']) if p.has_section('EXTRA TERMS') else {}
+        tab = MechanismTables(species)
+        tab.add_reactions(dict(p['REACTIONS']), dict(p['RATE CONSTANTS']), extra)
+        c = rng.uniform(0.1, 2.0, len(species))
+        got = tab.reaction_rates_host(c)
+        values, _ = extra_term_values(extra)
+        subs = {sp.Symbol(s): v for s, v in zip(species, c)}
+        for i, s in enumerate(species):
+            want = float(sp.parse_expr(kats[key]['sympy'][s]).subs(values).subs(subs))
+            assert got[i] == pytest.approx(want, rel=1e-13, abs=1e-15), (key, s)
+        blob = tab.pack()
+        assert blob.nbytes % 8 == 0 and blob[1] == blob.nbytes
+
+
+def test_bytecode_matches_sympy():
+    from openccm_b200.system_solvers.tables import Compiler, H, T_SYM, run_program
+    exprs = ['1 + 0.5*sin(t)', 'H(10*t)', 'H(t - 1)', '3.5 * H(t) * H(-(t - 2*0.01))', 'exp(-t)*cos(3*t)**2 + sqrt(t + 1)',
+             'Max(t, 0.5) - Min(t, 0.25)', 'tanh(t) / (1 + t**2)']
+    for text in exprs:
+        e = sp.parse_expr(text, local_dict={'H': H})
+        for expr in (e, e.diff(T_SYM)):
+            comp = Compiler()
+            pid = comp.add_program(expr)
+            for tv in (0.0, 0.0005, 0.004, 0.015, 0.7, 1.003, 2.5):
+                ref = expr
+                # the reference evaluates Piecewise as sum(expr * cond): identical to sympy's Piecewise when the
+                # conditions are mutually exclusive, which they are for H
+                want = float(ref.subs(T_SYM, tv))
+                got = run_program(comp.programs[pid], comp.consts, t=tv)
+                assert got == pytest.approx(want, rel=1e-12, abs=1e-13), (text, tv)
+
+
+@pytest.mark.parametrize('name', sorted(C.CASES))
+def test_export_c0_matches_reference(name, tmp_path):
+    """Vectorised initial/boundary-condition handling reproduces the reference's c0 exactly (goldens)."""
+    from openccm_b200.system_solvers.export import export_system
+    g = load_golden(name)
+    cp, cmesh, net, mn = setup_case(name, 'B200-RK45', tmp_path)
+    host = export_system(C.CASES[name]['model'], mn, cp, cmesh)
+    np.testing.assert_allclose(host.c0.reshape(-1), g['c0'], rtol=1e-13, atol=1e-15)
+    # same result from the array form of the network
+    host2 = export_system(C.CASES[name]['model'], net, cp, cmesh)
+    np.testing.assert_array_equal(host2.c0, host.c0)
+    np.testing.assert_array_equal(host2.row_src, host.row_src)
+    assert host.row_ptr[-1] == len(host.row_src) == len(host.row_w)
+    y = np.arange(host.ndof, dtype=float)
+    np.testing.assert_array_equal(host.to_reference_layout(host.to_device_layout(y)), y)
+
+
+def test_ell_conversion_roundtrip():
+    from openccm_b200.device import ell_from_csr
+    from openccm_b200 import synthetic as syn
+    from openccm_b200.workloads import cstr_ensemble_workload
+    from openccm_b200.system_solvers.export import export_system
+    model, net, cp, cmesh = cstr_ensemble_workload(n_cstr=500, n_io=4)
+    host = export_system(model, net, cp, cmesh)
+    k, src, w, flags = ell_from_csr(host.row_ptr, host.row_src, host.row_w)
+    assert 1 <= k <= 4
+    x = np.random.default_rng(0).normal(size=host.n_models)
+    csr = np.zeros(host.n_models)
+    rows = np.repeat(np.arange(host.n_models), np.diff(host.row_ptr))
+    ok = host.row_src >= 0
+    np.add.at(csr, rows[ok], host.row_w[ok] * x[host.row_src[ok]])
+    ell = (w * x[src]).sum(0)
+    good = flags == 0
+    np.testing.assert_allclose(ell[good], csr[good], rtol=1e-13, atol=1e-15)
+    assert set(np.nonzero(flags)[0]) >= set(rows[~ok])          # rows with boundary entries are flagged
+
+
+def test_generate_t_eval_forms(tmp_path):
+    from openccm_b200.system_solvers.helper_functions import generate_t_eval
+    from oracle import openccm_oracle as O
+    for name, te in (('cstr_irreversible', '1.0, linear'), ('cstr_log_teval', 'log, 12'), ('cstr_second_order', None),
+                     ('cstr_irreversible', 'all'), ('cstr_irreversible', '0.3, linear')):
+        kw = {} if te is None else {'t_eval': te}
+        cp, *_ = setup_case(name, 'B200-RK45', tmp_path, **kw)
+        a, b = generate_t_eval(cp), O.generate_t_eval(cp)
+        assert (a is None and b is None) or np.array_equal(np.asarray(a), np.asarray(b))
+
+
+def test_dropin_dispatcher_routes_by_solver_name(tmp_path):
+    from openccm_b200 import dropin
+    calls = []
+    ref = lambda *a: calls.append('reference') or 'ref-result'
+    disp = dropin.make_dispatcher(ref)
+    cp, cmesh, net, mn = setup_case('cstr_irreversible', 'LSODA', tmp_path)
+    assert disp('cstr', mn, cp, cmesh) == 'ref-result' and calls == ['reference']
+    # device solver names never reach the reference path; without a GPU the device path refuses loudly (no CPU fallback)
+    cp2, *_ = setup_case('cstr_irreversible', 'B200-RK45', tmp_path)
+    import torch
+    if not torch.cuda.is_available():
+        from openccm_b200._lib import OccmError
+        with pytest.raises(OccmError):
+            disp('cstr', mn, cp2, cmesh)
+        assert calls == ['reference']
+
+
+def test_unknown_solver_is_rejected(tmp_path):
+    from openccm_b200.system_solvers import solve_system
+    cp, cmesh, net, mn = setup_case('cstr_irreversible', 'LSODA', tmp_path)
+    with pytest.raises(ValueError):
+        solve_system('cstr', mn, cp, cmesh)

@@ -290,7 +290,8 @@ def main():
     solver_e2e = EnsembleSolver(model, net, cp, cmesh, host=host)
     def e2e_step():
         solver_e2e.dev = None                      # re-upload tables every step
-        r = solver_e2e.solve(M_loc, k_scale=ks, q_scale=qs, ic_scale=ics, save=save_idx, gather=False)
+        # global host arrays in; the solver takes this rank's contiguous member block (no collective on the data path)
+        r = solver_e2e.solve(M_glob, k_scale=ks_all, q_scale=qs_all, ic_scale=ics_all, save=save_idx, gather=False)
         return r
     for _ in range(min(args.warmup, 1)):
         e2e_step()

@@ -97,6 +97,11 @@ typedef struct {
     const int32_t* ell_src;
     const double*  ell_w;
     const uint8_t* point_flags; /* [n_points] or NULL: 1 = evaluate this point on the generic path */
+    /* optional: the same ELL operator packed as 16-byte entries {int32 src; int32 flag; double w}, column-major
+     * [ell_width][n_models], flag (column 0 only) = point_flags; enables the 128-bit fast kernels for even n_species */
+    const void*    ell_packed;
+    const int32_t* flagged_points; /* [n_flagged] indices of the points with point_flags = 1 (needed with ell_packed) */
+    int32_t        n_flagged;
 } occm_system_desc;
 
 /* Per-member parameters of an ensemble (all device pointers, any may be NULL = 1.0).

@@ -24,7 +24,8 @@ class SystemDesc(C.Structure):
                 ('row_ptr', C.c_void_p), ('row_src', C.c_void_p), ('row_w', C.c_void_p), ('a', C.c_void_p),
                 ('pulse_ptr', C.c_void_p), ('pulse_fn', C.c_void_p), ('pulse_w', C.c_void_p),
                 ('tables', C.c_void_p), ('tables_bytes', C.c_int32), ('fields', C.c_void_p), ('n_fields', C.c_int32),
-                ('ell_width', C.c_int32), ('ell_src', C.c_void_p), ('ell_w', C.c_void_p), ('point_flags', C.c_void_p)]
+                ('ell_width', C.c_int32), ('ell_src', C.c_void_p), ('ell_w', C.c_void_p), ('point_flags', C.c_void_p), ('ell_packed', C.c_void_p),
+                ('flagged_points', C.c_void_p), ('n_flagged', C.c_int32)]
 
 
 class Members(C.Structure):

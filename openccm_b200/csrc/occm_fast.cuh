@@ -1,0 +1,289 @@
+// Fast path of the fused CSTR kernels (included by occm_solver.cu after the generic kernel).
+//
+// Preconditions (checked on the host, otherwise the generic occm_stage kernel runs): CSTR network, even species
+// count S, mechanism in register form (fast_ok), ELL width K <= 4, ndof and all member offsets 16-byte aligned.
+//
+// Differences from the generic kernel:
+//   * one thread owns TWO adjacent species of a point: every own-element access is a 128-bit LDG/STG, every row
+//     gather a 128-bit load — half the memory instructions per byte;
+//   * the ELL operator is packed as 16-byte entries {src, flag, w} (one LDG.128 per entry; the point flag rides in
+//     column 0, no separate flag array);
+//   * straight-line code templated on K, 32-bit element offsets against per-member base pointers;
+//   * software pipelining: while a trip computes, the own values, epilogue operands and ELL entries of the CTA's
+//     NEXT trip are already in flight (registers), so only the L2 latency of the row gathers is exposed;
+//   * the staged tile is double buffered: one __syncthreads per trip.
+#pragma once
+
+struct __align__(16) OccmEllEntry { int src; int flag; double w; };
+
+struct OccmOps2 { double2 ye, k1, ka, kb, kc, kd; };
+
+__device__ __forceinline__ double2 occm_ld2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+__device__ __forceinline__ void occm_st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+__device__ __forceinline__ double2 occm_fma2(double a, double2 x, double2 y) { return make_double2(fma(a, x.x, y.x), fma(a, x.y, y.y)); }
+
+// Per-member context of a trip.  Only the values that cost a global load are kept (6 registers); the array pointers
+// are rebuilt where they are used from kernel parameters (constant bank) + m * ndof.
+template <int STAGE>
+struct OccmFastCtx {
+    double h;        // step (stages 2..7) or eps of the directional difference (stage 1)
+    double qs;       // flow scale of the member
+    int par;         // parity of the state ping-pong
+    int m;
+};
+
+template <int STAGE>
+__device__ __forceinline__ OccmFastCtx<STAGE> occm_fast_ctx(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk, int m) {
+    OccmFastCtx<STAGE> c;
+    c.m = m; c.h = 0.0; c.par = 0;
+    c.qs = mem.q_scale ? __ldg(mem.q_scale + m) : 1.0;
+    if (STAGE == 1) c.h = __ldg(mem.eps + m);
+    if (STAGE >= 2) { c.h = rk.h[m]; c.par = rk.parity[m]; }
+    return c;
+}
+
+// base pointers of member c.m
+template <int STAGE>
+__device__ __forceinline__ const double* occm_fast_in_a(const OccmSysDev& sys, const OccmRkDev& rk, const double* y_in, const OccmFastCtx<STAGE>& c) {
+    const long long base = (long long)c.m * sys.ndof;
+    return STAGE <= 1 ? y_in + base : STAGE == 2 ? rk.Y[c.par] + base : STAGE == 3 || STAGE == 5 ? rk.YS[0] + base
+         : STAGE == 4 || STAGE == 6 ? rk.YS[1] + base : rk.Y[c.par ^ 1] + base;
+}
+template <int STAGE>
+__device__ __forceinline__ const double* occm_fast_in_b(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk, const OccmFastCtx<STAGE>& c) {
+    const long long base = (long long)c.m * sys.ndof;
+    return STAGE == 1 ? mem.z + base : rk.KF[c.par] + base;
+}
+
+template <int STAGE>
+__device__ __forceinline__ double2 occm_fast_in(const double* in_a, const double* in_b, double hb, int e) {
+    const double2 a = occm_ld2(in_a + e);
+    if (STAGE == 2) { const double2 b = occm_ld2(in_b + e); return make_double2(a.x + (dp::A21 * b.x) * hb, a.y + (dp::A21 * b.y) * hb); }
+    if (STAGE == 1) { const double2 b = occm_ld2(in_b + e); return make_double2(a.x + b.x * hb, a.y + b.y * hb); }
+    return a;
+}
+
+template <int STAGE>
+__device__ __forceinline__ OccmOps2 occm_fast_load_ops(const OccmSysDev& sys, const OccmRkDev& rk, const OccmFastCtx<STAGE>& c, int e) {
+    OccmOps2 o;
+    const double2 z = make_double2(0.0, 0.0);
+    o.ye = o.k1 = o.ka = o.kb = o.kc = o.kd = z;
+    if (STAGE <= 1) return o;
+    const long long g = (long long)c.m * sys.ndof + e;
+    o.ye = occm_ld2(rk.Y[c.par] + g); o.k1 = occm_ld2(rk.KF[c.par] + g);
+    if (STAGE == 3) { o.ka = occm_ld2(rk.K2 + g); }
+    if (STAGE == 4) { o.ka = occm_ld2(rk.K2 + g); o.kb = occm_ld2(rk.K3 + g); }
+    if (STAGE == 5) { o.ka = occm_ld2(rk.K2 + g); o.kb = occm_ld2(rk.K3 + g); o.kc = occm_ld2(rk.K4 + g); }
+    if (STAGE == 6) { o.ka = occm_ld2(rk.K3 + g); o.kb = occm_ld2(rk.K4 + g); o.kc = occm_ld2(rk.K5 + g); }
+    if (STAGE == 7) { o.ka = occm_ld2(rk.K3 + g); o.kb = occm_ld2(rk.K4 + g); o.kc = occm_ld2(rk.K5 + g); o.kd = occm_ld2(rk.K6 + g); }
+    return o;
+}
+
+// one species of the epilogue (same arithmetic as occm_finish); returns the squared scaled error in stage 7
+template <int STAGE>
+__device__ __forceinline__ double occm_fast_comb(const OccmRkDev& rk, double ye, double k1, double ka, double kb, double kc, double kd,
+                                                 double f, double h, double yn, double& next) {
+    if (STAGE == 2) next = ye + (dp::A31 * k1 + dp::A32 * f) * h;
+    else if (STAGE == 3) next = ye + (dp::A41 * k1 + dp::A42 * ka + dp::A43 * f) * h;
+    else if (STAGE == 4) next = ye + (dp::A51 * k1 + dp::A52 * ka + dp::A53 * kb + dp::A54 * f) * h;
+    else if (STAGE == 5) next = ye + (dp::A61 * k1 + dp::A62 * ka + dp::A63 * kb + dp::A64 * kc + dp::A65 * f) * h;
+    else if (STAGE == 6) next = ye + h * (dp::B1 * k1 + dp::B3 * ka + dp::B4 * kb + dp::B5 * kc + dp::B6 * f);
+    else if (STAGE == 7) {
+        const double err = (dp::E1 * k1 + dp::E3 * ka + dp::E4 * kb + dp::E5 * kc + dp::E6 * kd + dp::E7 * f) * h;
+        const double scale = rk.atol + fmax(fabs(ye), fabs(yn)) * rk.rtol;
+        const double q = err / scale;
+        return q * q;
+    }
+    return 0.0;
+}
+
+template <int STAGE>
+__device__ __forceinline__ double occm_fast_finish(const OccmSysDev& sys, const OccmRkDev& rk, const OccmFastCtx<STAGE>& c, const OccmOps2& o,
+                                                   double2 f, double2 yn, int e, double* __restrict__ dy_out) {
+    const long long g = (long long)c.m * sys.ndof + e;
+    if (STAGE <= 1) { occm_st2(dy_out + g, f); return 0.0; }
+    double2 nx = make_double2(0.0, 0.0);
+    const double e0 = occm_fast_comb<STAGE>(rk, o.ye.x, o.k1.x, o.ka.x, o.kb.x, o.kc.x, o.kd.x, f.x, c.h, yn.x, nx.x);
+    const double e1 = occm_fast_comb<STAGE>(rk, o.ye.y, o.k1.y, o.ka.y, o.kb.y, o.kc.y, o.kd.y, f.y, c.h, yn.y, nx.y);
+    if (STAGE == 2) { occm_st2(rk.K2 + g, f); occm_st2(rk.YS[0] + g, nx); }
+    else if (STAGE == 3) { occm_st2(rk.K3 + g, f); occm_st2(rk.YS[1] + g, nx); }
+    else if (STAGE == 4) { occm_st2(rk.K4 + g, f); occm_st2(rk.YS[0] + g, nx); }
+    else if (STAGE == 5) { occm_st2(rk.K5 + g, f); occm_st2(rk.YS[1] + g, nx); }
+    else if (STAGE == 6) { occm_st2(rk.K6 + g, f); occm_st2(rk.Y[c.par ^ 1] + g, nx); }
+    else { occm_st2(rk.KF[c.par ^ 1] + g, f); }
+    return e0 + e1;
+}
+
+template <int STAGE, int K>
+struct OccmFastPre {          // everything of a trip that can be loaded before the tile barrier
+    double2 own; int4 ell[K]; int pt; int ci;
+};
+
+template <int STAGE, int K>
+__global__ void __launch_bounds__(OCCM_BLOCK, 2)
+occm_fast_cstr(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmMemDev mem, const __grid_constant__ OccmRkDev rk,
+               const double* __restrict__ t_dev, double t_scalar, const double* __restrict__ y_in, double* __restrict__ dy_out,
+               const OccmEllEntry* __restrict__ ell, int cpm, int tcv, int err_stride) {
+    extern __shared__ double smem_d[];
+    int* tab_s = reinterpret_cast<int*>(smem_d);
+    occm_load_tables(sys.tables, sys.tables_bytes, tab_s);
+    const int S = sys.S, H = S >> 1, RS = S + 2;            // staged rows: S values + two 1.0 pads (keeps 16-byte alignment)
+    double* tile = smem_d + (((sys.tables_bytes + 15) >> 4) << 1);   // [2][tcv][RS], 16-byte aligned
+    double* rxc_s = tile + 2 * tcv * RS;                    // unscaled coefficients [S][OCCM_NT]
+    double* scratch = rxc_s + S * OCCM_NT;
+    const int tid = threadIdx.x;
+    const bool lane_on = tid < tcv * H;
+    const int pl = tid / H;
+    const int sp = 2 * (tid - pl * H);
+    const int nt_u = tab_s[OCCM_H_MAX_TERMS], nf_u = tab_s[OCCM_H_MAX_SLOTS];
+    unsigned meta0[OCCM_NT], meta1[OCCM_NT];
+    {
+        const OccmTab T = occm_tab_views(tab_s);
+        const OccmRxnRegs R0 = occm_rxn_regs(T, lane_on ? sp : 0, S), R1 = occm_rxn_regs(T, lane_on ? sp + 1 : 0, S);
+#pragma unroll
+        for (int q = 0; q < OCCM_NT; ++q) {
+            meta0[q] = R0.meta[q]; meta1[q] = R1.meta[q];
+            if (lane_on && pl == 0) { rxc_s[sp * OCCM_NT + q] = R0.coeff[q]; rxc_s[(sp + 1) * OCCM_NT + q] = R1.coeff[q]; }
+        }
+    }
+    for (int r = tid; r < 2 * tcv; r += OCCM_BLOCK) { tile[r * RS + S] = 1.0; tile[r * RS + S + 1] = 1.0; }
+    const int n_points = (int)sys.n_points, N = sys.n_models;
+    const int my_tile = pl * RS + sp;
+    __syncthreads();
+
+    // ---- cursor over this CTA's (member, chunk) trips, skipping members that are not running
+    int m = (int)(blockIdx.x / (unsigned)cpm);
+    int ci = (int)(blockIdx.x - (unsigned)m * (unsigned)cpm);
+    const int step_m = (int)(gridDim.x / (unsigned)cpm), step_c = (int)(gridDim.x - (unsigned)step_m * (unsigned)cpm);
+    auto skip = [&]() {       // move forward until (m, ci) is a trip that has to be done; false when past the end
+        while (m < mem.M) {
+            const bool run = STAGE >= 2 ? rk.status[m] == OCCM_MEMBER_RUNNING : (!mem.active || mem.active[m]);
+            if (run) return true;
+            m += step_m; ci += step_c; if (ci >= cpm) { ci -= cpm; ++m; }
+        }
+        return false;
+    };
+    auto advance = [&]() { m += step_m; ci += step_c; if (ci >= cpm) { ci -= cpm; ++m; } return skip(); };
+
+    // Two register sets (A, B) alternate between "current trip" and "trip in flight": the loop body is instantiated
+    // twice so that no register-to-register copies are needed.
+    OccmFastCtx<STAGE> cxA, cxB;
+    cxA.m = -1; cxB.m = -1;
+    OccmFastPre<STAGE, K> A, B;
+    int coeff_m = -1;
+    double cm0[OCCM_NT], cm1[OCCM_NT];
+#pragma unroll
+    for (int q = 0; q < OCCM_NT; ++q) { cm0[q] = 0.0; cm1[q] = 0.0; }
+
+    auto load = [&](OccmFastPre<STAGE, K>& pre, OccmFastCtx<STAGE>& cx) {
+        if (cx.m != m) cx = occm_fast_ctx<STAGE>(sys, mem, rk, m);
+        pre.ci = ci;
+        const int p = ci * tcv + pl;
+        pre.pt = (lane_on && p < n_points) ? p : -1;
+        const int pp = pre.pt >= 0 ? pre.pt : 0;
+        const int e = pp * S + sp;
+        pre.own = occm_fast_in<STAGE>(occm_fast_in_a<STAGE>(sys, rk, y_in, cx), occm_fast_in_b<STAGE>(sys, mem, rk, cx), cx.h, e);
+#pragma unroll
+        for (int k = 0; k < K; ++k) pre.ell[k] = __ldg(reinterpret_cast<const int4*>(ell + (size_t)k * N + pp));
+    };
+
+    auto process = [&](const OccmFastPre<STAGE, K>& cur, const OccmFastCtx<STAGE>& cc, OccmFastPre<STAGE, K>& nxt,
+                       OccmFastCtx<STAGE>& ncx, bool have_next, int buf) {
+        double* tb = tile + buf * tcv * RS;
+        // epilogue operands of THIS trip: needed last, so they have the whole trip to arrive
+        const OccmOps2 ops = occm_fast_load_ops<STAGE>(sys, rk, cc, (cur.pt >= 0 ? cur.pt : 0) * S + sp);
+        if (lane_on) occm_st2(tb + my_tile, cur.own);
+        __syncthreads();
+        // ---- row gathers (L2 hits), then the next trip's loads: both fly while the reactions are evaluated
+        double2 g[K];
+        {
+            const double* ga = occm_fast_in_a<STAGE>(sys, rk, y_in, cc);
+            const double* gb = occm_fast_in_b<STAGE>(sys, mem, rk, cc);
+#pragma unroll
+            for (int k = 0; k < K; ++k) g[k] = occm_fast_in<STAGE>(ga, gb, cc.h, cur.ell[k].x * S + sp);
+        }
+        if (have_next) load(nxt, ncx);
+
+        if (coeff_m != cc.m) {                          // uniform: fold the member's rate-constant scales into the coefficients
+#pragma unroll
+            for (int q = 0; q < OCCM_NT; ++q) {
+                const double k0 = mem.k_scale ? __ldg(mem.k_scale + (long long)cc.m * sys.n_rxn + (meta0[q] & 0xffu)) : 1.0;
+                const double k1 = mem.k_scale ? __ldg(mem.k_scale + (long long)cc.m * sys.n_rxn + (meta1[q] & 0xffu)) : 1.0;
+                cm0[q] = rxc_s[sp * OCCM_NT + q] * k0; cm1[q] = rxc_s[(sp + 1) * OCCM_NT + q] * k1;
+            }
+            coeff_m = cc.m;
+        }
+        double err2 = 0.0;
+        if (cur.pt >= 0) {
+            const double* myrow = tb + pl * RS;
+            if (!cur.ell[0].y) {
+                const double r0 = occm_reaction_fast(cm0, meta0, myrow, nt_u, nf_u);
+                const double r1 = occm_reaction_fast(cm1, meta1, myrow, nt_u, nf_u);
+                double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc = occm_fma2(__hiloint2double(cur.ell[k].w, cur.ell[k].z), g[k], acc);
+                const double2 f = make_double2(cc.qs * acc.x + r0, cc.qs * acc.y + r1);
+                err2 = occm_fast_finish<STAGE>(sys, rk, cc, ops, f, cur.own, cur.pt * S + sp, dy_out);
+            }   // flagged rows (boundary / pulse / overflow entries) are left to occm_fixup, launched right after
+        }
+        if (STAGE == 7) {
+            const double sum = occm_block_sum(err2, scratch);
+            if (tid == 0) rk.err_partial[(long long)cc.m * err_stride + cur.ci] = sum;
+        }
+    };
+
+    bool valid = skip();
+    if (valid) load(A, cxA);
+    while (valid) {
+        bool vn = advance();                 // (m, ci) now name the next trip
+        process(A, cxA, B, cxB, vn, 0);
+        if (!vn) break;
+        valid = advance();
+        process(B, cxB, A, cxA, valid, 1);
+    }
+}
+
+
+// Flagged points of the fast path: rows with boundary / pulse entries or more entries than the ELL width.  A few
+// dozen points per member; evaluated with the generic CSR / table walk, one thread per (flagged point, species).
+template <int STAGE>
+__global__ void __launch_bounds__(OCCM_BLOCK)
+occm_fixup(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmMemDev mem, const __grid_constant__ OccmRkDev rk,
+           const double* __restrict__ t_dev, double t_scalar, const double* __restrict__ y_in, double* __restrict__ dy_out,
+           const int* __restrict__ flagged, int n_flagged, int err_cpm, int err_offset) {
+    extern __shared__ double smem_d[];
+    __shared__ double scratch[8];
+    int* tab_s = reinterpret_cast<int*>(smem_d);
+    occm_load_tables(sys.tables, sys.tables_bytes, tab_s);
+    const int S = sys.S, RS = S + 1, tcf = OCCM_BLOCK / S;
+    double* tile = smem_d + (sys.tables_bytes >> 3);
+    const int m = blockIdx.y;
+    if (STAGE >= 2 && rk.status[m] != OCCM_MEMBER_RUNNING) return;
+    if (STAGE <= 1 && mem.active && !mem.active[m]) return;
+    const int tid = threadIdx.x, pl = tid / S, s = tid - pl * S;
+    const int idx = blockIdx.x * tcf + pl;
+    const bool on = pl < tcf && idx < n_flagged;
+    const int p = on ? flagged[idx] : 0;
+    const long long base = (long long)m * sys.ndof;
+    double h = 0.0, t_stage; int par = 0;
+    if (STAGE <= 1) { t_stage = t_dev ? __ldg(t_dev + m) : t_scalar; if (STAGE == 1) h = __ldg(mem.eps + m); }
+    else {
+        const double t0 = rk.t[m]; h = rk.h[m]; par = rk.parity[m];
+        t_stage = STAGE == 2 ? t0 + dp::C2 * h : STAGE == 3 ? t0 + dp::C3 * h : STAGE == 4 ? t0 + dp::C4 * h : STAGE == 5 ? t0 + dp::C5 * h : t0 + h;
+    }
+    OccmStageIn<STAGE> in;
+    in.a = STAGE <= 1 ? y_in + base : STAGE == 2 ? rk.Y[par] + base : STAGE == 3 || STAGE == 5 ? rk.YS[0] + base
+         : STAGE == 4 || STAGE == 6 ? rk.YS[1] + base : rk.Y[par ^ 1] + base;
+    in.b = STAGE == 1 ? mem.z + base : STAGE == 2 ? rk.KF[par] + base : nullptr; in.hb = h;
+    if (on) tile[pl * RS + s] = in(p * S + s);
+    __syncthreads();
+    double err2 = 0.0;
+    if (on) {
+        const double* ksc = mem.k_scale ? mem.k_scale + (long long)m * sys.n_rxn : nullptr;
+        err2 = occm_cold_element<0, STAGE>(sys, mem, rk, tab_s, y_in, tile + pl * RS, p, s, t_stage, m, ksc, dy_out);
+    }
+    if (STAGE == 7) {
+        const double sum = occm_block_sum(err2, scratch);
+        if (tid == 0) rk.err_partial[(long long)m * err_cpm + err_offset + blockIdx.x] = sum;
+    }
+}

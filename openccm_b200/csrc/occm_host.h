@@ -10,6 +10,7 @@ struct occm_system {
     occm_system_desc desc;
     OccmSysDev dev;
     int sm_count;
+    int use_fast;         // 0: always run the generic kernels (OCCM_B200_NO_FAST=1, used by the tests to cover both)
     size_t smem_tables;   // bytes of the staged table blob (8-byte aligned)
 };
 

@@ -77,6 +77,7 @@ extern "C" int occm_system_create(occm_system** out, const occm_system_desc* d) 
     v.ell_k = d->model == OCCM_MODEL_CSTR ? d->ell_width : 0;
     v.ell_src = d->ell_src; v.ell_w = d->ell_w;
     v.point_flags = d->point_flags;
+    s->use_fast = getenv("OCCM_B200_NO_FAST") ? 0 : 1;
     v.fast_ok = hdr[OCCM_H_MAX_TERMS] <= OCCM_NT && hdr[OCCM_H_MAX_SLOTS] <= OCCM_NF && !hdr[OCCM_H_ANY_PROG] && hdr[OCCM_H_NRXN] <= 255;
     if (d->model == OCCM_MODEL_CSTR && (v.ell_k == 0 || !d->point_flags)) v.fast_ok = 0;   // no ELL copy: CSR walk for every row
     if (v.ell_k < 0 || v.ell_k > OCCM_KREG || (v.ell_k > 0 && (!d->ell_src || !d->ell_w))) { occm_set_error("bad ELL description"); free(s); return OCCM_ERR_INVALID; }
@@ -398,6 +399,8 @@ occm_stage(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmM
     }
 }
 
+#include "occm_fast.cuh"
+
 // ------------------------------------------------------------------------------------------------ controller
 // np.nextafter(t, +inf) for t >= 0 (the reference asserts t0 >= 0, helper_functions.py:82)
 __device__ __forceinline__ double occm_next_up(double t) { return __longlong_as_double(__double_as_longlong(t) + 1ll); }
@@ -598,11 +601,61 @@ static int occm_launch_stage_m(const occm_system* sys, const OccmMemDev& mem, co
     return OCCM_OK;
 }
 
+template <int STAGE, int K>
+static int occm_launch_fast(const occm_system* sys, const OccmMemDev& mem, const OccmRkDev& rk, const double* t_dev,
+                            double t_scalar, const double* y_in, double* dy_out, cudaStream_t st, int* cpm_out) {
+    static size_t smem_limit = 48 * 1024;
+    static int ctas_per_sm = 0;
+    const int S = sys->dev.S, tcv = OCCM_BLOCK / (S / 2);
+    const size_t smem = (((size_t)sys->dev.tables_bytes + 15) & ~(size_t)15) + sizeof(double) * ((size_t)2 * tcv * (S + 2) + (size_t)S * OCCM_NT + 40);
+    auto kern = occm_fast_cstr<STAGE, K>;
+    if (smem > smem_limit) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_limit = smem; }
+    if (ctas_per_sm == 0) {
+        OCCM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, OCCM_BLOCK, smem));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    const int cpm = (int)((sys->dev.n_points + tcv - 1) / tcv);
+    const long long chunks = (long long)mem.M * cpm;
+    if (chunks >= (1ll << 31)) { occm_set_error("too many chunks (%lld) for one launch", chunks); return OCCM_ERR_INVALID; }
+    const int grid = occm_grid(sys, chunks, ctas_per_sm);
+    const int n_flagged = sys->desc.n_flagged;
+    const int tcf = OCCM_BLOCK / S;
+    const int nfix = n_flagged > 0 ? (n_flagged + tcf - 1) / tcf : 0;
+    const int err_stride = cpm + nfix;                    // partial sums per member: fast chunks, then fix-up blocks
+    kern<<<grid, OCCM_BLOCK, smem, st>>>(sys->dev, mem, rk, t_dev, t_scalar, y_in, dy_out, (const OccmEllEntry*)sys->desc.ell_packed, cpm, tcv, err_stride);
+    OCCM_LAUNCH_CHECK("occm_fast_cstr");
+    if (nfix > 0) {
+        const size_t fsmem = (size_t)sys->dev.tables_bytes + sizeof(double) * ((size_t)tcf * (S + 1) + 8);
+        static size_t fix_limit = 48 * 1024;
+        if (fsmem > fix_limit) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(occm_fixup<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); fix_limit = fsmem; }
+        occm_fixup<STAGE><<<dim3(nfix, mem.M), OCCM_BLOCK, fsmem, st>>>(sys->dev, mem, rk, t_dev, t_scalar, y_in, dy_out, sys->desc.flagged_points,
+                                                                          n_flagged, err_stride, cpm);
+        OCCM_LAUNCH_CHECK("occm_fixup");
+    }
+    if (cpm_out) *cpm_out = err_stride;
+    return OCCM_OK;
+}
+
+static inline bool occm_aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
 template <int STAGE>
 static int occm_launch_stage(const occm_system* sys, const OccmMemDev& mem, const OccmRkDev& rk, const double* t_dev,
-                             double t_scalar, const double* y_in, double* dy_out, cudaStream_t st) {
-    return sys->dev.model == OCCM_MODEL_CSTR ? occm_launch_stage_m<0, STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st)
-                                             : occm_launch_stage_m<1, STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st);
+                             double t_scalar, const double* y_in, double* dy_out, cudaStream_t st, int* cpm_out = nullptr) {
+    const OccmSysDev& d = sys->dev;
+    const bool fast = sys->use_fast && d.model == OCCM_MODEL_CSTR && d.fast_ok && (d.S % 2 == 0) && sys->desc.ell_packed &&
+                      (sys->desc.n_flagged == 0 || sys->desc.flagged_points) && mem.M <= 65535 && d.ell_k >= 1 &&
+                      d.ell_k <= 4 && occm_aligned16(y_in) && occm_aligned16(dy_out) && occm_aligned16(mem.z);
+    if (fast) {
+        switch (d.ell_k) {
+            case 1: return occm_launch_fast<STAGE, 1>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
+            case 2: return occm_launch_fast<STAGE, 2>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
+            case 3: return occm_launch_fast<STAGE, 3>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
+            default: return occm_launch_fast<STAGE, 4>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
+        }
+    }
+    if (cpm_out) *cpm_out = d.chunks_per_member;
+    return d.model == OCCM_MODEL_CSTR ? occm_launch_stage_m<0, STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st)
+                                      : occm_launch_stage_m<1, STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st);
 }
 
 // used by occm_bdf.cu
@@ -640,7 +693,7 @@ static RkLayout rk_layout(const occm_system* sys, int M) {
     L.off_par = take(M * 4); L.off_status = take(M * 4); L.off_rej = take(M * 4); L.off_acc_now = take(M * 4);
     L.off_lo = take(M * 4); L.off_hi = take(M * 4); L.off_rows = take(M * 4);
     L.off_nacc = take(M * 8); L.off_nrej = take(M * 8); L.off_nfev = take(M * 8);
-    L.off_err = take((size_t)M * sys->dev.chunks_per_member * 8);
+    L.off_err = take((size_t)M * (size_t)((sys->dev.n_points + sys->dev.tc - 1) / sys->dev.tc + 2 + sys->desc.n_flagged) * 8);   // capacity for any chunking
     L.off_running = take(256);
     L.total = o;
     return L;
@@ -723,8 +776,9 @@ static int occm_rk45_launch_step(occm_rk45* rk, cudaStream_t st) {
     if ((rc = occm_launch_stage<4>(sys, md, d, nullptr, 0.0, nullptr, nullptr, st))) return rc;
     if ((rc = occm_launch_stage<5>(sys, md, d, nullptr, 0.0, nullptr, nullptr, st))) return rc;
     if ((rc = occm_launch_stage<6>(sys, md, d, nullptr, 0.0, nullptr, nullptr, st))) return rc;
-    if ((rc = occm_launch_stage<7>(sys, md, d, nullptr, 0.0, nullptr, nullptr, st))) return rc;
-    occm_rk45_control<<<rk->M, 128, 0, st>>>(d, sys->dev.chunks_per_member, sys->dev.ndof, rk->prob.t_eval, rk->prob.n_t_eval);
+    int err_cpm = sys->dev.chunks_per_member;
+    if ((rc = occm_launch_stage<7>(sys, md, d, nullptr, 0.0, nullptr, nullptr, st, &err_cpm))) return rc;
+    occm_rk45_control<<<rk->M, 128, 0, st>>>(d, err_cpm, sys->dev.ndof, rk->prob.t_eval, rk->prob.n_t_eval);
     OCCM_LAUNCH_CHECK("occm_rk45_control");
     const int n_save = rk->prob.save_idx ? rk->prob.n_save : (int)sys->dev.ndof;
     const long long chunks = (long long)rk->M * ((n_save + OCCM_BLOCK - 1) / OCCM_BLOCK);

@@ -54,12 +54,14 @@ def ell_from_csr(row_ptr: np.ndarray, row_src: np.ndarray, row_w: np.ndarray, pu
     if len(row_src):
         rows = np.repeat(np.arange(n), deg)
         has_bc[np.unique(rows[np.asarray(row_src) < 0])] = True
-    k = int(min(max_width, max(1, np.quantile(deg, coverage, method='higher')))) if n else 1
-    if n and deg.max() <= max_width and deg.max() - k <= 1:
-        k = int(max(1, deg.max()))
-    flags[(deg > k) | has_bc] = 1
+    special = has_bc.copy()
     if pulse_ptr is not None:
-        flags[np.diff(np.asarray(pulse_ptr, dtype=np.int64)) > 0] = 1
+        special |= np.diff(np.asarray(pulse_ptr, dtype=np.int64)) > 0
+    plain_deg = deg[~special] if (~special).any() else deg          # rows the ELL path can serve at all
+    k = int(min(max_width, max(1, np.quantile(plain_deg, coverage, method='higher')))) if n else 1
+    if n and plain_deg.max() <= max_width and plain_deg.max() - k <= 1:
+        k = int(max(1, plain_deg.max()))
+    flags[(deg > k) | special] = 1
     src = np.tile(np.arange(n, dtype=np.int64), (k, 1))
     w = np.zeros((k, n), dtype=np.float64)
     good = flags == 0
@@ -111,21 +113,27 @@ class DeviceSystem:
         self.tables = torch.as_tensor(blob, device=self.dev)
         self.fields = f64(host.fields)
         self.n_rxn = host.tables.n_rxn
-        self.ell_k, self.ell_src, self.ell_w = 0, None, None
+        self.ell_k, self.ell_src, self.ell_w, self.ell_packed = 0, None, None, None
         if host.model != 'pfr':
             k, es, ew, flags = ell_from_csr(host.row_ptr, host.row_src, host.row_w, host.pulse_ptr)
             self.ell_k, self.ell_src, self.ell_w = k, i32(es), f64(ew)
+            packed = np.zeros((k, host.n_models), dtype=np.dtype([('src', '<i4'), ('flag', '<i4'), ('w', '<f8')]))
+            packed['src'] = es; packed['w'] = ew; packed['flag'][0] = flags
+            self.ell_packed = torch.as_tensor(packed.view(np.uint8).reshape(-1), device=self.dev)
         else:
             flags = np.zeros(host.n_points, dtype=np.uint8)
             if host.pulse_ptr is not None:       # every node of a PFR with a pulse source takes the generic path
                 flags[np.repeat(np.diff(host.pulse_ptr) > 0, host.P)] = 1
         self.point_flags = torch.as_tensor(flags, device=self.dev)
+        flagged = np.nonzero(flags)[0].astype(np.int32)
+        self.flagged_points = torch.as_tensor(flagged if len(flagged) else np.zeros(1, np.int32), device=self.dev)
         desc = _lib.SystemDesc(1 if host.model == 'pfr' else 0, host.S, host.n_models, host.P,
                                _ptr(self.row_ptr), _ptr(self.row_src), _ptr(self.row_w), _ptr(self.a),
                                _ptr(self.pulse_ptr), _ptr(self.pulse_fn), _ptr(self.pulse_w),
                                _ptr(self.tables), blob.nbytes, _ptr(self.fields),
                                0 if host.fields is None else host.fields.shape[0],
-                               self.ell_k, _ptr(self.ell_src), _ptr(self.ell_w), _ptr(self.point_flags))
+                               self.ell_k, _ptr(self.ell_src), _ptr(self.ell_w), _ptr(self.point_flags), _ptr(self.ell_packed),
+                               _ptr(self.flagged_points), int(len(flagged)))
         h = C.c_void_p()
         _lib.check(self.lib.occm_system_create(C.byref(h), C.byref(desc)))
         self.handle = h

@@ -47,3 +47,30 @@ def test_rhs_batched_members_vs_oracle(name, tmp_path):
     for m in range(M):
         ref = ora.fun(float(ts[m]), ys[m].copy())
         np.testing.assert_allclose(host.to_reference_layout(out[m]), ref, rtol=1e-12, atol=1e-13 * max(1.0, np.abs(ref).max()))
+
+
+@pytest.mark.parametrize('name', ['cstr_net12_nacl', 'cstr_reversible', 'cstr_net20_timebc'])
+def test_generic_and_fast_kernels_agree(name, tmp_path, monkeypatch):
+    """The 128-bit fast CSTR kernels (even S) and the generic kernels give the same RHS and the same RK45 solution."""
+    import torch
+    from openccm_b200.device import DeviceSystem
+    from openccm_b200.system_solvers.export import export_system
+    cp, cmesh, net, mn = setup_case(name, 'B200-RK45', tmp_path)
+    host = export_system(C.CASES[name]['model'], mn, cp, cmesh)
+    rng = np.random.default_rng(11)
+    M = 5
+    y = torch.as_tensor(np.abs(rng.normal(0.5, 0.5, (M, host.ndof))), device='cuda')
+    t = torch.as_tensor(rng.uniform(0, 2, M), device='cuda')
+    outs, sols = [], []
+    for no_fast in ('', '1'):
+        if no_fast:
+            monkeypatch.setenv('OCCM_B200_NO_FAST', '1')
+        else:
+            monkeypatch.delenv('OCCM_B200_NO_FAST', raising=False)
+        dev = DeviceSystem(host)
+        outs.append(dev.rhs(y, t).cpu().numpy())
+        res = dev.rk45(y, (0.0, 3.0), rtol=1e-8, atol=1e-10, first_step=1e-4, t_eval=np.linspace(0, 3, 7))
+        assert np.all(res.status == 1)
+        sols.append(res.y.cpu().numpy())
+    np.testing.assert_allclose(outs[0], outs[1], rtol=1e-13, atol=1e-14)
+    np.testing.assert_allclose(sols[0], sols[1], rtol=1e-9, atol=1e-12)

@@ -226,9 +226,11 @@ occm_fast_cstr(const __grid_constant__ OccmSysDev sys, const __grid_constant__ O
                 err2 = occm_fast_finish<STAGE>(sys, rk, cc, ops, f, cur.own, cur.pt * S + sp, dy_out);
             }   // flagged rows (boundary / pulse / overflow entries) are left to occm_fixup, launched right after
         }
-        if (STAGE == 7) {
-            const double sum = occm_block_sum(err2, scratch);
-            if (tid == 0) rk.err_partial[(long long)cc.m * err_stride + cur.ci] = sum;
+        if (STAGE == 7) {          // one partial per warp: no block barrier in the hot loop (summed in fixed order by the controller)
+            double v = err2;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            if ((tid & 31) == 0) rk.err_partial[(long long)cc.m * err_stride + cur.ci * (OCCM_BLOCK / 32) + (tid >> 5)] = v;
         }
     };
 

@@ -621,7 +621,8 @@ static int occm_launch_fast(const occm_system* sys, const OccmMemDev& mem, const
     const int n_flagged = sys->desc.n_flagged;
     const int tcf = OCCM_BLOCK / S;
     const int nfix = n_flagged > 0 ? (n_flagged + tcf - 1) / tcf : 0;
-    const int err_stride = cpm + nfix;                    // partial sums per member: fast chunks, then fix-up blocks
+    const int nwarp = OCCM_BLOCK / 32;
+    const int err_stride = cpm * nwarp + nfix;            // partial sums per member: one per warp and chunk, then fix-up blocks
     kern<<<grid, OCCM_BLOCK, smem, st>>>(sys->dev, mem, rk, t_dev, t_scalar, y_in, dy_out, (const OccmEllEntry*)sys->desc.ell_packed, cpm, tcv, err_stride);
     OCCM_LAUNCH_CHECK("occm_fast_cstr");
     if (nfix > 0) {
@@ -629,7 +630,7 @@ static int occm_launch_fast(const occm_system* sys, const OccmMemDev& mem, const
         static size_t fix_limit = 48 * 1024;
         if (fsmem > fix_limit) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(occm_fixup<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); fix_limit = fsmem; }
         occm_fixup<STAGE><<<dim3(nfix, mem.M), OCCM_BLOCK, fsmem, st>>>(sys->dev, mem, rk, t_dev, t_scalar, y_in, dy_out, sys->desc.flagged_points,
-                                                                          n_flagged, err_stride, cpm);
+                                                                          n_flagged, err_stride, cpm * nwarp);
         OCCM_LAUNCH_CHECK("occm_fixup");
     }
     if (cpm_out) *cpm_out = err_stride;
@@ -693,7 +694,7 @@ static RkLayout rk_layout(const occm_system* sys, int M) {
     L.off_par = take(M * 4); L.off_status = take(M * 4); L.off_rej = take(M * 4); L.off_acc_now = take(M * 4);
     L.off_lo = take(M * 4); L.off_hi = take(M * 4); L.off_rows = take(M * 4);
     L.off_nacc = take(M * 8); L.off_nrej = take(M * 8); L.off_nfev = take(M * 8);
-    L.off_err = take((size_t)M * (size_t)((sys->dev.n_points + sys->dev.tc - 1) / sys->dev.tc + 2 + sys->desc.n_flagged) * 8);   // capacity for any chunking
+    L.off_err = take((size_t)M * (size_t)(((sys->dev.n_points + sys->dev.tc - 1) / sys->dev.tc + 2) * (OCCM_BLOCK / 32) + sys->desc.n_flagged) * 8);   // capacity for any chunking
     L.off_running = take(256);
     L.total = o;
     return L;

@@ -334,7 +334,7 @@ def main():
             pass
         peak = float(peaks.get('hbm_gbs', 6650.0))
         ach = alg5 / (ms5 * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "occm_stage<CSTR, stage 5>", "achieved": ach, "peak": peak, "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": "occm_fast_cstr<stage 5, K> (fused Dormand-Prince stage: RHS + next stage state)", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": None, "peak_source": "measured" if peaks else "fallback",
                 "ms_per_launch": ms5, "alg_bytes_per_launch": alg5,
                 "stage_ms": stage_ms}

@@ -178,82 +178,132 @@ __global__ void __launch_bounds__(256) bdf_scale_col(const OccmBdfDev b, int col
     }
 }
 
-// ---- block-Jacobi preconditioner, one thread per point: out = (I - c (tau I + dr/dc))^{-1} (scale .* in)
-// The reaction Jacobian block is rebuilt from the state by one-sided differences of the mechanism tables.
-template <int MODEL>
-__global__ void __launch_bounds__(128) bdf_precond(const __grid_constant__ OccmSysDev sys, const OccmBdfDev b, const double* __restrict__ src,
-                                                   int src_is_V_col_j, double* __restrict__ dst, const int* __restrict__ mask, int want_norm) {
+// ---- warp-cooperative block preconditioner: out = M^{-1} (scale .* in), M ~ I - c J, nothing stored between applications
+// W = 4, 8 or 16 lanes form a group, lane i < S owns row i of the S x S block in registers; elimination without
+// pivoting through warp shuffles (I - c J of a mass-action mechanism is column diagonally dominant).
+//   CSTR: one group per point (block Jacobi).
+//   PFR : one group per PFR sweeps its points in flow order, x_p = B_p^{-1} (u_p + c a x_{p-1}): the exact inverse of
+//         the block lower-bidiagonal operator of the upwind discretisation (pfr_system.py:296) — block ILU(0) == LU here.
+//         Inlet nodes (coupled to OTHER PFRs, pfr_system.py:313-314) keep the identity; that coupling is left to GMRES.
+template <int W>
+__device__ __forceinline__ void bdf_group_solve(const OccmTab& T, const OccmSysDev& sys, int S, int lane, double cown, double c, double tau,
+                                                const double* ksc, double tnew, long long point, double& u) {
+    // row `lane` of B = (1 - c tau) I - c dr/dc
+    double row[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) row[j] = (j == lane) ? 1.0 - c * tau : 0.0;
+    auto conc = [&](int sp) { return __shfl_sync(0xffffffffu, cown, sp, W); };
+    const int tb = lane < S ? T.term_ptr[lane] : 0, te = lane < S ? T.term_ptr[lane + 1] : 0;
+    // all lanes of the warp must execute the same shuffles: iterate to the warp-wide maximum term / factor counts
+    int nterm = te - tb;
+    for (int off = 16; off > 0; off >>= 1) nterm = max(nterm, __shfl_xor_sync(0xffffffffu, nterm, off));
+    for (int kk = 0; kk < nterm; ++kk) {
+        const int k = tb + kk;
+        const bool on = k < te;
+        double v0 = on ? T.term_coeff[k] : 0.0;
+        if (on && ksc) v0 *= ksc[T.term_rxn[k]];
+        const int fb = on ? T.fac_ptr[k] : 0, fe = on ? T.fac_ptr[k + 1] : 0;
+        int nfac = fe - fb;
+        for (int off = 16; off > 0; off >>= 1) nfac = max(nfac, __shfl_xor_sync(0xffffffffu, nfac, off));
+        // values of the factors of this term (up to 4 distinct factors are supported in the preconditioner)
+        double xv[4]; int xs[4], xo[4];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            const bool fon = f < nfac && fb + f < fe;
+            xs[f] = fon ? T.fac_sp[fb + f] : 0; xo[f] = fon ? T.fac_ord[fb + f] : 0;
+            xv[f] = f < nfac ? conc(xs[f]) : 1.0;
+        }
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            if (xo[f] == 0) continue;
+            double dv = v0 * xo[f];
+            for (int q = 1; q < xo[f]; ++q) dv *= xv[f];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) if (g != f) for (int q = 0; q < xo[g]; ++q) dv *= xv[g];
+#pragma unroll
+            for (int j = 0; j < W; ++j) row[j] -= (j == xs[f]) ? c * dv : 0.0;
+        }
+    }
+    // elimination (no pivoting)
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+        if (k >= S) break;
+        const double pkk = __shfl_sync(0xffffffffu, row[k], k, W);
+        const double uk = __shfl_sync(0xffffffffu, u, k, W);
+        const double l = (lane > k && lane < S) ? row[k] / pkk : 0.0;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            if (j <= k) continue;
+            const double pkj = __shfl_sync(0xffffffffu, row[j], k, W);
+            row[j] -= l * pkj;
+        }
+        u -= l * uk;
+    }
+    // back substitution
+#pragma unroll
+    for (int k = W - 1; k >= 0; --k) {
+        if (k >= S) continue;
+        const double xk = __shfl_sync(0xffffffffu, u / row[k], k, W);      // lane k holds x_k = u_k / B_kk
+        if (lane == k) u = xk;
+        else if (lane < k) u -= row[k] * xk;
+    }
+}
+
+template <int MODEL, int W>
+__global__ void __launch_bounds__(128) bdf_precond_warp(const __grid_constant__ OccmSysDev sys, const OccmBdfDev b, const double* __restrict__ src,
+                                                        int src_is_V_col_j, double* __restrict__ dst, const int* __restrict__ mask) {
     extern __shared__ double smem_d[];
-    __shared__ double scratch[8];
     int* tab_s = reinterpret_cast<int*>(smem_d);
     occm_load_tables(sys.tables, sys.tables_bytes, tab_s);
     const OccmTab T = occm_tab_views(tab_s);
-    const int S = sys.S;
-    const int ppc = (int)((sys.n_points + b.nchunk - 1) / b.nchunk);      // points per chunk (same chunk count as the vector kernels)
-    const long long total = (long long)b.M * b.nchunk;
-    for (long long cc = blockIdx.x; cc < total; cc += gridDim.x) {
-        const int m = (int)(cc / b.nchunk);
-        if (!mask[m]) continue;
-        const int ci = (int)(cc - (long long)m * b.nchunk);
+    const int S = sys.S, P = sys.P;
+    const int lane = threadIdx.x % W, gib = threadIdx.x / W, gpb = 128 / W;
+    const long long per_member = MODEL == 0 ? sys.n_points : sys.n_models;
+    const long long total = (long long)b.M * per_member;
+    const long long rounded = (total + gpb - 1) / gpb * gpb;
+    for (long long g = (long long)blockIdx.x * gpb + gib; g < rounded; g += (long long)gridDim.x * gpb) {
+        const bool gv = g < total;
+        const int m = gv ? (int)(g / per_member) : 0;
+        const long long idx = gv ? g - (long long)m * per_member : 0;
+        const bool on = gv && mask[m] && lane < S;
         const double c = b.c[m];
         const double qs = b.q_scale ? b.q_scale[m] : 1.0;
         const double* ksc = b.k_scale ? b.k_scale + (long long)m * sys.n_rxn : nullptr;
         const double* in = src + (src_is_V_col_j ? (long long)b.gmres_j[m] * b.vstride : 0) + (long long)m * b.ndof;
-        double zn = 0.0;
-        const long long p_end = min((long long)(ci + 1) * ppc, sys.n_points);
-        for (long long p = (long long)ci * ppc + threadIdx.x; p < p_end; p += blockDim.x) {
-            const long long g0 = (long long)m * b.ndof + p * S;
-            double cr[OCCM_MAX_S > 16 ? 16 : OCCM_MAX_S], r0[16], u[16], B[16 * 16];
-            bool inlet = false;
-            double tau;
-            if (MODEL == 0) tau = qs * b.tdiag[p];
-            else { const int k = (int)(p / sys.P); inlet = (p - (long long)k * sys.P) == 0; tau = qs * b.tdiag[k]; }
-            for (int s = 0; s < S; ++s) {
-                const double y = b.y[g0 + s], d = b.d[g0 + s];
-                cr[s] = y;
-                u[s] = (b.atol + b.rtol * fabs(y - d)) * in[p * S + s];
+        const double tnew = b.t_new[m];
+        if (MODEL == 0) {
+            const long long g0 = (long long)m * b.ndof + idx * S + lane;
+            const double y = on ? b.y[g0] : 0.0, d = on ? b.d[g0] : 0.0;
+            double u = on ? (b.atol + b.rtol * fabs(y - d)) * in[idx * S + lane] : 0.0;
+            bdf_group_solve<W>(T, sys, S, lane, y, c, qs * b.tdiag[gv ? idx : 0], ksc, tnew, idx, u);
+            if (on) dst[g0] = u;
+        } else {
+            const double ca = c * qs * (-b.tdiag[gv ? idx : 0]);             // c * Q/dV of this PFR
+            double xprev = 0.0;
+            for (int i = 0; i < P; ++i) {
+                const long long p = idx * P + i;
+                const long long g0 = (long long)m * b.ndof + p * S + lane;
+                const double y = on ? b.y[g0] : 0.0, d = on ? b.d[g0] : 0.0;
+                double u = on ? (b.atol + b.rtol * fabs(y - d)) * in[p * S + lane] : 0.0;
+                if (i > 0) {
+                    u += ca * xprev;
+                    bdf_group_solve<W>(T, sys, S, lane, y, c, -ca / c, ksc, tnew, p, u);
+                }
+                if (on) dst[g0] = u;
+                xprev = u;
             }
-            if (!inlet) {          // PFR inlet nodes have no self coupling (their block is the identity)
-                auto row = [&cr](int sp) { return cr[sp]; };
-                for (int s = 0; s < S; ++s) r0[s] = occm_reaction_tables(T, s, row, ksc, b.t_new[m], (int)p, sys);
-                for (int j = 0; j < S; ++j) {
-                    const double save = cr[j];
-                    const double dl = 1.4901161193847656e-08 * (fabs(save) + 1e-3);
-                    cr[j] = save + dl;
-                    for (int s = 0; s < S; ++s) {
-                        const double r1 = occm_reaction_tables(T, s, row, ksc, b.t_new[m], (int)p, sys);
-                        B[s * S + j] = -c * ((r1 - r0[s]) / dl);
-                    }
-                    cr[j] = save;
-                    B[j * S + j] += 1.0 - c * tau;
-                }
-                // Gaussian elimination with partial pivoting on the S x S block
-                for (int k = 0; k < S; ++k) {
-                    int piv = k; double best = fabs(B[k * S + k]);
-                    for (int i = k + 1; i < S; ++i) if (fabs(B[i * S + k]) > best) { best = fabs(B[i * S + k]); piv = i; }
-                    if (piv != k) {
-                        for (int j = k; j < S; ++j) { const double tmp = B[k * S + j]; B[k * S + j] = B[piv * S + j]; B[piv * S + j] = tmp; }
-                        const double tmp = u[k]; u[k] = u[piv]; u[piv] = tmp;
-                    }
-                    const double inv = 1.0 / B[k * S + k];
-                    for (int i = k + 1; i < S; ++i) {
-                        const double l = B[i * S + k] * inv;
-                        for (int j = k + 1; j < S; ++j) B[i * S + j] -= l * B[k * S + j];
-                        u[i] -= l * u[k];
-                    }
-                }
-                for (int k = S - 1; k >= 0; --k) {
-                    double acc = u[k];
-                    for (int j = k + 1; j < S; ++j) acc -= B[k * S + j] * u[j];
-                    u[k] = acc / B[k * S + k];
-                }
-            }
-            for (int s = 0; s < S; ++s) { dst[g0 + s] = u[s]; zn += u[s] * u[s]; }
         }
-        if (want_norm) {
-            const double tz = occm_block_sum(zn, scratch);
-            if (threadIdx.x == 0) b.partial[cc * BDF_MAXDOT + 0] = tz;
-        }
+    }
+}
+
+// partial[0] = |v|^2
+__global__ void __launch_bounds__(256) bdf_norm2(const OccmBdfDev b, const double* __restrict__ v, const int* __restrict__ mask) {
+    __shared__ double scratch[8];
+    BDF_FOR_CHUNKS(b, mask[m]) {
+        double s0 = 0.0;
+        BDF_ELEMS(b, ci, e) { const double x = v[(long long)m * b.ndof + e]; s0 += x * x; }
+        const double t0 = occm_block_sum(s0, scratch);
+        if (threadIdx.x == 0) b.partial[cc * BDF_MAXDOT + 0] = t0;
     }
 }
 
@@ -767,18 +817,35 @@ static int bdf_rhs(occm_bdf* h, const int* mask, const double* z, const double* 
     return occm_launch_rhs(h->sys, md, h->d.t_new, 0.0, h->d.y, out, st);
 }
 
-static int bdf_precond_launch(occm_bdf* h, const double* src, int from_col_j, double* dst, const int* mask, int want_norm, cudaStream_t st) {
+template <int MODEL, int W>
+static int bdf_precond_launch_w(occm_bdf* h, const double* src, int from_col_j, double* dst, const int* mask, cudaStream_t st) {
     const occm_system* sys = h->sys;
     const size_t smem = sys->smem_tables;
-    const int grid = bdf_grid(sys, (long long)h->M * h->d.nchunk);
-    if (sys->dev.model == OCCM_MODEL_CSTR) {
-        static size_t lim = 48 * 1024;
-        if (smem > lim) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(bdf_precond<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); lim = smem; }
-        BDF_LAUNCH(bdf_precond<0>, grid, 128, smem, sys->dev, h->d, src, from_col_j, dst, mask, want_norm);
-    } else {
-        static size_t lim = 48 * 1024;
-        if (smem > lim) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(bdf_precond<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); lim = smem; }
-        BDF_LAUNCH(bdf_precond<1>, grid, 128, smem, sys->dev, h->d, src, from_col_j, dst, mask, want_norm);
+    static size_t lim = 48 * 1024;
+    if (smem > lim) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(bdf_precond_warp<MODEL, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); lim = smem; }
+    const long long groups = (long long)h->M * (MODEL == 0 ? sys->dev.n_points : sys->dev.n_models);
+    const int gpb = 128 / W;
+    long long blocks = (groups + gpb - 1) / gpb;
+    const long long cap = (long long)sys->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    BDF_LAUNCH((bdf_precond_warp<MODEL, W>), (int)blocks, 128, smem, sys->dev, h->d, src, from_col_j, dst, mask);
+    return OCCM_OK;
+}
+
+static int bdf_precond_launch(occm_bdf* h, const double* src, int from_col_j, double* dst, const int* mask, int want_norm, cudaStream_t st) {
+    const occm_system* sys = h->sys;
+    const int S = sys->dev.S;
+    int rc;
+    if (sys->dev.model == OCCM_MODEL_CSTR)
+        rc = S <= 4 ? bdf_precond_launch_w<0, 4>(h, src, from_col_j, dst, mask, st) : S <= 8 ? bdf_precond_launch_w<0, 8>(h, src, from_col_j, dst, mask, st)
+                                                                                           : bdf_precond_launch_w<0, 16>(h, src, from_col_j, dst, mask, st);
+    else
+        rc = S <= 4 ? bdf_precond_launch_w<1, 4>(h, src, from_col_j, dst, mask, st) : S <= 8 ? bdf_precond_launch_w<1, 8>(h, src, from_col_j, dst, mask, st)
+                                                                                           : bdf_precond_launch_w<1, 16>(h, src, from_col_j, dst, mask, st);
+    if (rc) return rc;
+    if (want_norm) {
+        const int gv = bdf_grid(sys, (long long)h->M * h->d.nchunk);
+        BDF_LAUNCH(bdf_norm2, gv, 256, 0, h->d, dst, mask);
     }
     return OCCM_OK;
 }

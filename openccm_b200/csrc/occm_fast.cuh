@@ -130,7 +130,6 @@ occm_fast_cstr(const __grid_constant__ OccmSysDev sys, const __grid_constant__ O
     const int S = sys.S, H = S >> 1, RS = S + 2;            // staged rows: S values + two 1.0 pads (keeps 16-byte alignment)
     double* tile = smem_d + (((sys.tables_bytes + 15) >> 4) << 1);   // [2][tcv][RS], 16-byte aligned
     double* rxc_s = tile + 2 * tcv * RS;                    // unscaled coefficients [S][OCCM_NT]
-    double* scratch = rxc_s + S * OCCM_NT;
     const int tid = threadIdx.x;
     const bool lane_on = tid < tcv * H;
     const int pl = tid / H;

@@ -186,25 +186,21 @@ __global__ void __launch_bounds__(256) bdf_scale_col(const OccmBdfDev b, int col
 //         the block lower-bidiagonal operator of the upwind discretisation (pfr_system.py:296) — block ILU(0) == LU here.
 //         Inlet nodes (coupled to OTHER PFRs, pfr_system.py:313-314) keep the identity; that coupling is left to GMRES.
 template <int W>
-__device__ __forceinline__ void bdf_group_solve(const OccmTab& T, const OccmSysDev& sys, int S, int lane, double cown, double c, double tau,
-                                                const double* ksc, double tnew, long long point, double& u) {
+__device__ __forceinline__ void bdf_group_solve(const OccmTab& T, int nterm, int nfac, int S, int lane, double cown, double c, double tau,
+                                                const double* ksc, double& u) {
     // row `lane` of B = (1 - c tau) I - c dr/dc
     double row[W];
 #pragma unroll
     for (int j = 0; j < W; ++j) row[j] = (j == lane) ? 1.0 - c * tau : 0.0;
     auto conc = [&](int sp) { return __shfl_sync(0xffffffffu, cown, sp, W); };
     const int tb = lane < S ? T.term_ptr[lane] : 0, te = lane < S ? T.term_ptr[lane + 1] : 0;
-    // all lanes of the warp must execute the same shuffles: iterate to the warp-wide maximum term / factor counts
-    int nterm = te - tb;
-    for (int off = 16; off > 0; off >>= 1) nterm = max(nterm, __shfl_xor_sync(0xffffffffu, nterm, off));
+    // all lanes of the warp must execute the same shuffles: nterm / nfac are the mechanism-wide maxima (table header)
     for (int kk = 0; kk < nterm; ++kk) {
         const int k = tb + kk;
         const bool on = k < te;
         double v0 = on ? T.term_coeff[k] : 0.0;
         if (on && ksc) v0 *= ksc[T.term_rxn[k]];
         const int fb = on ? T.fac_ptr[k] : 0, fe = on ? T.fac_ptr[k + 1] : 0;
-        int nfac = fe - fb;
-        for (int off = 16; off > 0; off >>= 1) nfac = max(nfac, __shfl_xor_sync(0xffffffffu, nfac, off));
         // values of the factors of this term (up to 4 distinct factors are supported in the preconditioner)
         double xv[4]; int xs[4], xo[4];
 #pragma unroll
@@ -228,9 +224,9 @@ __device__ __forceinline__ void bdf_group_solve(const OccmTab& T, const OccmSysD
 #pragma unroll
     for (int k = 0; k < W; ++k) {
         if (k >= S) break;
-        const double pkk = __shfl_sync(0xffffffffu, row[k], k, W);
+        const double ipk = 1.0 / __shfl_sync(0xffffffffu, row[k], k, W);
         const double uk = __shfl_sync(0xffffffffu, u, k, W);
-        const double l = (lane > k && lane < S) ? row[k] / pkk : 0.0;
+        const double l = (lane > k && lane < S) ? row[k] * ipk : 0.0;
 #pragma unroll
         for (int j = 0; j < W; ++j) {
             if (j <= k) continue;
@@ -257,6 +253,7 @@ __global__ void __launch_bounds__(128) bdf_precond_warp(const __grid_constant__ 
     occm_load_tables(sys.tables, sys.tables_bytes, tab_s);
     const OccmTab T = occm_tab_views(tab_s);
     const int S = sys.S, P = sys.P;
+    const int nterm = tab_s[OCCM_H_MAX_TERMS], nfac = min(4, tab_s[OCCM_H_MAX_SLOTS]);
     const int lane = threadIdx.x % W, gib = threadIdx.x / W, gpb = 128 / W;
     const long long per_member = MODEL == 0 ? sys.n_points : sys.n_models;
     const long long total = (long long)b.M * per_member;
@@ -270,27 +267,32 @@ __global__ void __launch_bounds__(128) bdf_precond_warp(const __grid_constant__ 
         const double qs = b.q_scale ? b.q_scale[m] : 1.0;
         const double* ksc = b.k_scale ? b.k_scale + (long long)m * sys.n_rxn : nullptr;
         const double* in = src + (src_is_V_col_j ? (long long)b.gmres_j[m] * b.vstride : 0) + (long long)m * b.ndof;
-        const double tnew = b.t_new[m];
         if (MODEL == 0) {
             const long long g0 = (long long)m * b.ndof + idx * S + lane;
             const double y = on ? b.y[g0] : 0.0, d = on ? b.d[g0] : 0.0;
             double u = on ? (b.atol + b.rtol * fabs(y - d)) * in[idx * S + lane] : 0.0;
-            bdf_group_solve<W>(T, sys, S, lane, y, c, qs * b.tdiag[gv ? idx : 0], ksc, tnew, idx, u);
+            bdf_group_solve<W>(T, nterm, nfac, S, lane, y, c, qs * b.tdiag[gv ? idx : 0], ksc, u);
             if (on) dst[g0] = u;
         } else {
             const double ca = c * qs * (-b.tdiag[gv ? idx : 0]);             // c * Q/dV of this PFR
             double xprev = 0.0;
+            const long long gbase = (long long)m * b.ndof + idx * P * S + lane;
+            const double* inp = in + idx * P * S + lane;
+            double y = on ? b.y[gbase] : 0.0, d = on ? b.d[gbase] : 0.0, w = on ? inp[0] : 0.0;
             for (int i = 0; i < P; ++i) {
-                const long long p = idx * P + i;
-                const long long g0 = (long long)m * b.ndof + p * S + lane;
-                const double y = on ? b.y[g0] : 0.0, d = on ? b.d[g0] : 0.0;
-                double u = on ? (b.atol + b.rtol * fabs(y - d)) * in[p * S + lane] : 0.0;
+                // operands of the next point are requested before this point's (sequentially dependent) solve
+                const bool more = on && i + 1 < P;
+                const double yn = more ? b.y[gbase + (long long)(i + 1) * S] : 0.0;
+                const double dn = more ? b.d[gbase + (long long)(i + 1) * S] : 0.0;
+                const double wn = more ? inp[(long long)(i + 1) * S] : 0.0;
+                double u = (b.atol + b.rtol * fabs(y - d)) * w;
                 if (i > 0) {
                     u += ca * xprev;
-                    bdf_group_solve<W>(T, sys, S, lane, y, c, -ca / c, ksc, tnew, p, u);
+                    bdf_group_solve<W>(T, nterm, nfac, S, lane, y, c, -ca / c, ksc, u);
                 }
-                if (on) dst[g0] = u;
+                if (on) dst[gbase + (long long)i * S] = u;
                 xprev = u;
+                y = yn; d = dn; w = wn;
             }
         }
     }

@@ -70,12 +70,13 @@ __device__ __forceinline__ OccmOps2 occm_fast_load_ops(const OccmSysDev& sys, co
     o.ye = o.k1 = o.ka = o.kb = o.kc = o.kd = z;
     if (STAGE <= 1) return o;
     const long long g = (long long)c.m * sys.ndof + e;
-    o.ye = occm_ld2(rk.Y[c.par] + g); o.k1 = occm_ld2(rk.KF[c.par] + g);
+    o.ye = occm_ld2(rk.Y[c.par] + g);
+    if (STAGE != 7) o.k1 = occm_ld2(rk.KF[c.par] + g);
     if (STAGE == 3) { o.ka = occm_ld2(rk.K2 + g); }
     if (STAGE == 4) { o.ka = occm_ld2(rk.K2 + g); o.kb = occm_ld2(rk.K3 + g); }
     if (STAGE == 5) { o.ka = occm_ld2(rk.K2 + g); o.kb = occm_ld2(rk.K3 + g); o.kc = occm_ld2(rk.K4 + g); }
     if (STAGE == 6) { o.ka = occm_ld2(rk.K3 + g); o.kb = occm_ld2(rk.K4 + g); o.kc = occm_ld2(rk.K5 + g); }
-    if (STAGE == 7) { o.ka = occm_ld2(rk.K3 + g); o.kb = occm_ld2(rk.K4 + g); o.kc = occm_ld2(rk.K5 + g); o.kd = occm_ld2(rk.K6 + g); }
+    if (STAGE == 7) { o.ka = occm_ld2(rk.K2 + g); }        // partial error combination written by stage 6
     return o;
 }
 
@@ -89,7 +90,7 @@ __device__ __forceinline__ double occm_fast_comb(const OccmRkDev& rk, double ye,
     else if (STAGE == 5) next = ye + (dp::A61 * k1 + dp::A62 * ka + dp::A63 * kb + dp::A64 * kc + dp::A65 * f) * h;
     else if (STAGE == 6) next = ye + h * (dp::B1 * k1 + dp::B3 * ka + dp::B4 * kb + dp::B5 * kc + dp::B6 * f);
     else if (STAGE == 7) {
-        const double err = (dp::E1 * k1 + dp::E3 * ka + dp::E4 * kb + dp::E5 * kc + dp::E6 * kd + dp::E7 * f) * h;
+        const double err = (ka + dp::E7 * f) * h;          // ka = E1 k1 + E3 k3 + E4 k4 + E5 k5 + E6 k6 from stage 6
         const double scale = rk.atol + fmax(fabs(ye), fabs(yn)) * rk.rtol;
         const double q = err / scale;
         return q * q;
@@ -109,7 +110,11 @@ __device__ __forceinline__ double occm_fast_finish(const OccmSysDev& sys, const 
     else if (STAGE == 3) { occm_st2(rk.K3 + g, f); occm_st2(rk.YS[1] + g, nx); }
     else if (STAGE == 4) { occm_st2(rk.K4 + g, f); occm_st2(rk.YS[0] + g, nx); }
     else if (STAGE == 5) { occm_st2(rk.K5 + g, f); occm_st2(rk.YS[1] + g, nx); }
-    else if (STAGE == 6) { occm_st2(rk.K6 + g, f); occm_st2(rk.Y[c.par ^ 1] + g, nx); }
+    else if (STAGE == 6) {
+        occm_st2(rk.K6 + g, f); occm_st2(rk.Y[c.par ^ 1] + g, nx);
+        occm_st2(rk.K2 + g, make_double2(dp::E1 * o.k1.x + dp::E3 * o.ka.x + dp::E4 * o.kb.x + dp::E5 * o.kc.x + dp::E6 * f.x,
+                                          dp::E1 * o.k1.y + dp::E3 * o.ka.y + dp::E4 * o.kb.y + dp::E5 * o.kc.y + dp::E6 * f.y));
+    }
     else { occm_st2(rk.KF[c.par ^ 1] + g, f); }
     return e0 + e1;
 }

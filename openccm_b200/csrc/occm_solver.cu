@@ -172,12 +172,13 @@ __device__ __forceinline__ OccmOps occm_load_ops(const OccmRkDev& rk, const doub
     OccmOps o;
     o.ye = o.k1 = o.ka = o.kb = o.kc = o.kd = 0.0;
     if (STAGE == 0 || STAGE == 1) return o;
-    o.ye = __ldg(y + e); o.k1 = __ldg(k1 + e);
+    o.ye = __ldg(y + e);
+    if (STAGE != 7) o.k1 = __ldg(k1 + e);
     if (STAGE == 3) { o.ka = __ldg(rk.K2 + base + e); }
     if (STAGE == 4) { o.ka = __ldg(rk.K2 + base + e); o.kb = __ldg(rk.K3 + base + e); }
     if (STAGE == 5) { o.ka = __ldg(rk.K2 + base + e); o.kb = __ldg(rk.K3 + base + e); o.kc = __ldg(rk.K4 + base + e); }
     if (STAGE == 6) { o.ka = __ldg(rk.K3 + base + e); o.kb = __ldg(rk.K4 + base + e); o.kc = __ldg(rk.K5 + base + e); }
-    if (STAGE == 7) { o.ka = __ldg(rk.K3 + base + e); o.kb = __ldg(rk.K4 + base + e); o.kc = __ldg(rk.K5 + base + e); o.kd = __ldg(rk.K6 + base + e); }
+    if (STAGE == 7) { o.ka = __ldg(rk.K2 + base + e); }      // K2's buffer holds the partial error combination written by stage 6
     return o;
 }
 
@@ -202,9 +203,12 @@ __device__ __forceinline__ double occm_finish(const OccmRkDev& rk, const OccmOps
         rk.K6[base + e] = f;
         // y_new = y + h * dot(K[:-1].T, B)   (rk.py:64)
         rk.Y[par ^ 1][base + e] = o.ye + h * (dp::B1 * o.k1 + dp::B3 * o.ka + dp::B4 * o.kb + dp::B5 * o.kc + dp::B6 * f);
+        // first six terms of the error combination dot(K.T, E) (rk.py:157): K2 is dead after stage 5 (b2 = e2 = 0, not used
+        // by the dense output), so its buffer carries the partial sum to stage 7 and saves four vector reads there
+        rk.K2[base + e] = dp::E1 * o.k1 + dp::E3 * o.ka + dp::E4 * o.kb + dp::E5 * o.kc + dp::E6 * f;
     } else {  // STAGE 7: f_new = K7, error estimate (rk.py:66-69, 157-162)
         rk.KF[par ^ 1][base + e] = f;
-        const double err = (dp::E1 * o.k1 + dp::E3 * o.ka + dp::E4 * o.kb + dp::E5 * o.kc + dp::E6 * o.kd + dp::E7 * f) * h;
+        const double err = (o.ka + dp::E7 * f) * h;
         const double scale = rk.atol + fmax(fabs(o.ye), fabs(y_new_own)) * rk.rtol;
         const double q = err / scale;
         return q * q;

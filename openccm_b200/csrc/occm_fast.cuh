@@ -124,8 +124,11 @@ struct OccmFastPre {          // everything of a trip that can be loaded before 
     double2 own; int4 ell[K]; int pt; int ci;
 };
 
+#ifndef OCCM_FAST_CTAS
+#define OCCM_FAST_CTAS 2
+#endif
 template <int STAGE, int K>
-__global__ void __launch_bounds__(OCCM_BLOCK, 2)
+__global__ void __launch_bounds__(OCCM_BLOCK, OCCM_FAST_CTAS)
 occm_fast_cstr(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmMemDev mem, const __grid_constant__ OccmRkDev rk,
                const double* __restrict__ t_dev, double t_scalar, const double* __restrict__ y_in, double* __restrict__ dy_out,
                const OccmEllEntry* __restrict__ ell, int cpm, int tcv, int err_stride) {

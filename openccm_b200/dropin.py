@@ -39,8 +39,10 @@ def make_dispatcher(reference_solve_system: Callable, route_scipy_names: bool = 
 def install(route_scipy_names: bool = False) -> None:
     """Rebind openccm.system_solvers.solve_system and openccm.run.solve_system. Needs the `openccm` package importable."""
     global _original
-    import openccm.system_solvers as ss
-    import openccm.run as run_mod
+    import importlib
+    ss = importlib.import_module('openccm.system_solvers')
+    # `openccm/__init__.py` re-exports the function `run`, which shadows the submodule attribute: take the module itself
+    run_mod = importlib.import_module('openccm.run')
     if _original is None:
         _original = ss.solve_system
     dispatcher = make_dispatcher(_original, route_scipy_names)
@@ -58,8 +60,9 @@ def uninstall() -> None:
     global _original
     if _original is None:
         return
-    import openccm.system_solvers as ss
-    import openccm.run as run_mod
+    import importlib
+    ss = importlib.import_module('openccm.system_solvers')
+    run_mod = importlib.import_module('openccm.run')
     ss.solve_system = _original
     run_mod.solve_system = _original
     _original = None

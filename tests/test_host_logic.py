@@ -142,3 +142,31 @@ def test_unknown_solver_is_rejected(tmp_path):
     cp, cmesh, net, mn = setup_case('cstr_irreversible', 'LSODA', tmp_path)
     with pytest.raises(ValueError):
         solve_system('cstr', mn, cp, cmesh)
+
+
+def test_dropin_install_rebinds_both_names():
+    """With the reference importable (build container only) install() must rebind BOTH openccm.system_solvers.solve_system
+    and openccm.run.solve_system (run.py:35 binds the name at import time) and uninstall() must restore them."""
+    import sys
+    if not os.path.isdir('/root/reference/openccm'):
+        pytest.skip('reference package not available on this box')
+    try:
+        import pyparsing  # noqa: F401
+    except ModuleNotFoundError:
+        import pip._vendor.pyparsing as _pp
+        sys.modules['pyparsing'] = _pp
+    sys.path.insert(0, '/root/reference')
+    try:
+        import importlib
+        run_mod = importlib.import_module('openccm.run')       # (the attribute openccm.run is the re-exported function)
+        ss = importlib.import_module('openccm.system_solvers')
+        from openccm_b200 import dropin
+        original = ss.solve_system
+        assert run_mod.solve_system is original
+        dropin.install()
+        assert ss.solve_system is not original and run_mod.solve_system is ss.solve_system
+        assert ss.solve_system.__doc__ == original.__doc__
+        dropin.uninstall()
+        assert ss.solve_system is original and run_mod.solve_system is original
+    finally:
+        sys.path.remove('/root/reference')

@@ -29,6 +29,7 @@ class BdfResult:
     n_gmres: np.ndarray
     n_newton_fail: np.ndarray
     y_final: Optional[torch.Tensor] = None
+    n_rows: Optional[np.ndarray] = None
 
 
 def transport_diagonal(system: DeviceSystem) -> torch.Tensor:
@@ -108,4 +109,4 @@ def solve_bdf(system: DeviceSystem, y0: torch.Tensor, t_span: Sequence[float], *
         t_res = [np.concatenate(x) if x else np.zeros(0) for x in ts_all]
         y_res = [torch.cat(x) if x else out[m, :0] for m, x in enumerate(ys_all)]
         return BdfResult(t_res, y_res, status, n_acc, n_rej, nfev, n_gm, n_nf, y_final)
-    return BdfResult(te_np, out, status, n_acc, n_rej, nfev, n_gm, n_nf, y_final)
+    return BdfResult(te_np, out, status, n_acc, n_rej, nfev, n_gm, n_nf, y_final, n_rows)

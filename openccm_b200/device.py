@@ -94,6 +94,7 @@ class Rk45Result:
     n_rejected: np.ndarray
     nfev: np.ndarray
     y_final: Optional[torch.Tensor] = None
+    n_rows: Optional[np.ndarray] = None      # t_eval mode: output rows actually written per member (< T after a failure)
 
 
 class DeviceSystem:
@@ -280,4 +281,4 @@ class Rk45Run:
             t_res = [np.concatenate(x) if x else np.zeros(0) for x in ts_all]
             y_res = [torch.cat(x) if x else self.out[m, :0] for m, x in enumerate(ys_all)]
             return Rk45Result(t_res, y_res, *st, y_final)
-        return Rk45Result(self.te_np, self.out, *st, y_final)
+        return Rk45Result(self.te_np, self.out, *st, y_final, self.n_rows.copy())

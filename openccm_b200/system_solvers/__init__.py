@@ -27,7 +27,7 @@ def is_device_solver(name: str) -> bool:
     return name.upper() in DEVICE_SOLVERS
 
 
-def solve_system(model: str, model_network, config_parser, cmesh, *, return_info: bool = False):
+def solve_system(model: str, model_network, config_parser, cmesh, *, return_info: bool = False, fields=None, max_steps: int = 0):
     """Drop-in for openccm.system_solvers.solve_system (system_solvers/__init__.py:38-81)."""
     import torch
     from ..device import DeviceSystem, STATUS_MESSAGES
@@ -45,15 +45,15 @@ def solve_system(model: str, model_network, config_parser, cmesh, *, return_info
                          f"(this package has no CPU integration path)")
     t_eval = generate_t_eval(cp)
     model = model.lower()
-    host = export_system(model, model_network, cp, cmesh)
+    host = export_system(model, model_network, cp, cmesh, fields=fields)
     dev = DeviceSystem(host)
     y0 = torch.as_tensor(host.to_device_layout(host.c0.reshape(-1)), device=dev.dev).reshape(1, -1)
 
     if solver == 'B200-RK45':
-        res = dev.rk45(y0, t_span, rtol=rtol, atol=atol, first_step=first_timestep, t_eval=t_eval)
+        res = dev.rk45(y0, t_span, rtol=rtol, atol=atol, first_step=first_timestep, t_eval=t_eval, max_steps=max_steps)
     else:
         from ..bdf import solve_bdf
-        res = solve_bdf(dev, y0, t_span, rtol=rtol, atol=atol, first_step=first_timestep, t_eval=t_eval)
+        res = solve_bdf(dev, y0, t_span, rtol=rtol, atol=atol, first_step=first_timestep, t_eval=t_eval, max_steps=max_steps)
     status = int(res.status[0])
     message = STATUS_MESSAGES.get(status, str(status))
     if model == 'pfr':
@@ -61,8 +61,8 @@ def solve_system(model: str, model_network, config_parser, cmesh, *, return_info
     if t_eval is None:
         ts = np.asarray(res.t[0]); y = res.y[0].cpu().numpy()
     else:
-        n_rows = len(res.t) if status == 1 else int(np.searchsorted(res.t, res.t_reached[0], side='right')) \
-            if hasattr(res, 't_reached') else len(res.t)
+        # like solve_ivp, a run that stops early (CSTR path: no success check, cstr_system.py:151-154) returns the rows reached
+        n_rows = len(res.t) if status == 1 or res.n_rows is None else int(res.n_rows[0])
         ts = np.asarray(res.t)[:n_rows]; y = res.y[0, :n_rows].cpu().numpy()
     # [T, n_points, S] -> [S, n_points, T]   (cstr_system.py:152-154)
     c = np.ascontiguousarray(y.reshape(len(ts), host.n_points, host.S).transpose(2, 1, 0))

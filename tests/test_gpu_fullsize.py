@@ -1,0 +1,113 @@
+"""Parity at BASELINE.json sizes.
+
+C4 (1e5 CSTRs x 10 species): the fused RHS of two ensemble members against the oracle's sparse restatement, a mass-balance
+identity of the transport operator, and one complete member solve against scipy RK45 around the oracle's ddt.
+C5 (stiff PFR chains, BDF + GMRES): a reduced instance against scipy LSODA at tight tolerance."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def c4():
+    from oracle import openccm_oracle as O
+    from openccm_b200.device import DeviceSystem
+    from openccm_b200.system_solvers.export import export_system
+    from openccm_b200.workloads import cstr_ensemble_workload
+    model, net, cp, cmesh = cstr_ensemble_workload()
+    host = export_system(model, net, cp, cmesh)
+    dev = DeviceSystem(host)
+    ora = O.build_cstr(net.to_model_network(), cp, cmesh, sparse=True)
+    return dict(net=net, cp=cp, cmesh=cmesh, host=host, dev=dev, ora=ora)
+
+
+def test_c4_rhs_full_size_vs_oracle(c4):
+    import torch
+    from oracle import openccm_oracle as O
+    from openccm_b200 import synthetic as syn
+    from openccm_b200.device import MemberParams
+    host, dev, ora, cp = c4['host'], c4['dev'], c4['ora'], c4['cp']
+    assert host.n_models == 100_000 and host.S == 10
+    M = 2
+    ks, qs, _ = syn.ensemble_sweeps(M, host.tables.n_rxn)
+    rng = np.random.default_rng(0)
+    c = rng.uniform(0.0, 1.5, (M, host.S, host.n_points))
+    y = torch.as_tensor(host.to_device_layout(c.reshape(M, -1)), device='cuda')
+    mem = MemberParams(M, torch.as_tensor(ks, device='cuda'), torch.as_tensor(qs, device='cuda'), None)
+    out = dev.rhs(y, 0.25, mem).cpu().numpy()
+    A, bcs = ora.extra['A'], ora.extra['bcs']
+    for m in range(M):
+        rx = O.make_reactions_scaled(cp, host.species, ks[m])
+        d = np.ascontiguousarray((A @ c[m].T).T)
+        bcs(0.25, d)
+        d *= qs[m]
+        rx(c[m], d)
+        got = host.to_reference_layout(out[m]).reshape(host.S, -1)
+        np.testing.assert_allclose(got, d, rtol=1e-12, atol=1e-12)
+
+
+def test_c4_transport_mass_balance(c4):
+    """sum_j V_j (dc_j/dt)_transport = inflow - outflow for every species (exactly balanced synthetic flows)."""
+    import torch
+    host, dev, net, cp = c4['host'], c4['dev'], c4['net'], c4['cp']
+    from openccm_b200.system_solvers.export import export_system
+    cp['SIMULATION']['reactions_file_path'] = 'None'
+    try:
+        host0 = export_system('cstr', net, cp, c4['cmesh'])
+    finally:
+        from openccm_b200.workloads import cstr_ensemble_workload
+    from openccm_b200.device import DeviceSystem
+    dev0 = DeviceSystem(host0)
+    rng = np.random.default_rng(1)
+    c = rng.uniform(0.0, 1.0, (host0.S, host0.n_points))
+    y = torch.as_tensor(host0.to_device_layout(c.reshape(-1)), device='cuda').reshape(1, -1)
+    d = host0.to_reference_layout(dev0.rhs(y, 0.0).cpu().numpy().reshape(-1)).reshape(host0.S, -1)
+    lhs = (d * net.volumes[None, :]).sum(1)
+    bc_vals = np.array([1.0 if i % 2 == 0 else 0.5 for i in range(host0.S)])        # workloads._config boundary values
+    q_in = net.flows[net.in_conn[net.in_other < 0]].sum()
+    out_sel = net.out_other < 0
+    outflow = (c[:, net.out_model[out_sel]] * net.flows[net.out_conn[out_sel]][None, :]).sum(1)
+    np.testing.assert_allclose(lhs, bc_vals * q_in - outflow, rtol=1e-9, atol=1e-9)
+
+
+def test_c4_member_solve_full_size_vs_scipy(c4):
+    """One full-size member (1e6 DOF, t in [0, 10], 101 outputs) against scipy RK45 around the oracle's sparse ddt."""
+    import scipy.integrate
+    import torch
+    from oracle import openccm_oracle as O
+    host, dev, ora, cp = c4['host'], c4['dev'], c4['ora'], c4['cp']
+    te = np.asarray(O.generate_t_eval(cp))
+    y0 = torch.as_tensor(host.to_device_layout(host.c0.reshape(-1)), device='cuda').reshape(1, -1)
+    save = torch.arange(0, host.ndof, 997, dtype=torch.int32, device='cuda')
+    res = dev.rk45(y0, (0.0, 10.0), rtol=1e-6, atol=1e-10, first_step=1e-4, t_eval=te, save_idx=save)
+    assert res.status[0] == 1
+    ref = scipy.integrate.solve_ivp(ora.fun, (0.0, 10.0), ora.y0, method='RK45', rtol=1e-6, atol=1e-10, first_step=1e-4, t_eval=te)
+    assert abs(int(res.nfev[0]) - ref.nfev) <= 12
+    sel = save.cpu().numpy()
+    p, s = sel // host.S, sel % host.S
+    ref_sel = ref.y.reshape(host.S, host.n_points, -1)[s, p, :].T            # [T, n_save]
+    got = res.y[0].cpu().numpy()
+    assert np.all(np.abs(got - ref_sel) <= 1e-10 + 1e-6 * np.abs(ref_sel)), np.abs(got - ref_sel).max()
+    np.testing.assert_allclose(got, ref_sel, rtol=1e-9, atol=1e-12)
+
+
+def test_c5_reduced_bdf_vs_scipy_lsoda(tmp_path):
+    """Stiff 20-reaction mechanism (k from 1e-3 to 1e4) on recycle chains of PFRs: device BDF at rtol 1e-9 vs LSODA at 1e-11."""
+    import torch
+    from oracle import openccm_oracle as O
+    from openccm_b200.bdf import solve_bdf
+    from openccm_b200.device import DeviceSystem
+    from openccm_b200.system_solvers.export import export_system
+    from openccm_b200.workloads import pfr_stiff_workload
+    model, net, cp, cmesh = pfr_stiff_workload(n_chains=2, chain_len=3, P=8, t_end=5.0, n_out=11, workdir=str(tmp_path))
+    host = export_system(model, net, cp, cmesh)
+    dev = DeviceSystem(host)
+    y0 = torch.as_tensor(host.to_device_layout(host.c0.reshape(-1)), device='cuda').reshape(1, -1)
+    te = np.asarray(O.generate_t_eval(cp))
+    res = solve_bdf(dev, y0, (0.0, 5.0), rtol=1e-9, atol=1e-12, first_step=1e-4, t_eval=te)
+    assert res.status[0] == 1 and res.n_newton_fail[0] <= 2
+    cp['SIMULATION']['solver'] = 'LSODA'; cp['SIMULATION']['rtol'] = '1e-11'; cp['SIMULATION']['atol'] = '1e-13'
+    ref, t_ref, *_ = O.solve_system('pfr', net.to_model_network(), cp, cmesh)
+    got = res.y[0].cpu().numpy().reshape(len(te), host.n_points, host.S).transpose(2, 1, 0)
+    assert np.all(np.abs(got - ref) <= 1e-10 + 1e-6 * np.abs(ref)), np.abs(got - ref).max()

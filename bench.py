@@ -165,7 +165,8 @@ def cpu_baseline(args, n_members_sample, k_scale, q_scale, ic_scale, budget_s=25
     n = n_members_sample or max(cores, 8)
     jobs = [(args.n_cstr, m, k_scale[m], float(q_scale[m]), float(ic_scale[m])) for m in range(n)]
     t0 = time.perf_counter()
-    with mp.get_context('fork').Pool(min(cores, n)) as pool:
+    # spawn: the device arm calls this after CUDA is initialised in the parent (fork would inherit that context)
+    with mp.get_context('spawn').Pool(min(cores, n)) as pool:
         out = pool.map(_cpu_member_job, jobs)
     wall = time.perf_counter() - t0
     nfev = sum(o[0] for o in out)

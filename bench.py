@@ -338,7 +338,9 @@ def main():
         roof = {"bound": "hbm", "kernel": "occm_fast_cstr<stage 5, K> (fused Dormand-Prince stage: RHS + next stage state)", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": None, "peak_source": "measured" if peaks else "fallback",
                 "ms_per_launch": ms5, "alg_bytes_per_launch": alg5,
-                "stage_ms": stage_ms}
+                "stage_ms": stage_ms,
+                # all six stage kernels of a step attempt together: 304 B per element over their summed time
+                "all_stages_frac": (M_loc * ndof * 304.0 + 6 * csr_bytes) / (sum(stage_ms.values()) * 1e-3) / 1e9 / peak}
         # plain fused RHS (16 B per compartment-species eval)
         dy = torch.empty_like(y0)
         for _ in range(3):

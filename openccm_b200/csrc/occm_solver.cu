@@ -144,6 +144,10 @@ struct occm_rk45 {
     int M;
     int* h_running;     // pinned host
     long long launched_steps;
+    // CUDA graph of OCCM_GRAPH_STEPS consecutive step launches (launch-bound small systems); built lazily
+    cudaGraphExec_t graph_exec;
+    int graph_state;          // 0 = not tried, 1 = ready, -1 = unavailable (fall back to direct launches)
+    int launches_per_step;
 };
 
 // ------------------------------------------------------------------------------------------------ stage kernel
@@ -793,6 +797,27 @@ static int occm_rk45_launch_step(occm_rk45* rk, cudaStream_t st) {
     return OCCM_OK;
 }
 
+#define OCCM_GRAPH_STEPS 8
+
+// Capture OCCM_GRAPH_STEPS step launches into a graph (after one direct step has initialised the per-kernel launch state).
+static void occm_rk45_build_graph(occm_rk45* rk, cudaStream_t st) {
+    rk->graph_state = -1;
+    if (getenv("OCCM_B200_NO_GRAPH")) return;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return; }
+    const long long before = occm_launch_count();
+    int rc = OCCM_OK;
+    for (int i = 0; i < OCCM_GRAPH_STEPS && rc == OCCM_OK; ++i) rc = occm_rk45_launch_step(rk, st);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &graph);
+    const long long captured = occm_launch_count() - before;
+    occm_count_launch(-(int)captured);                       // nothing ran yet: launches are counted when the graph is launched
+    if (rc != OCCM_OK || e != cudaSuccess || !graph) { cudaGetLastError(); if (graph) cudaGraphDestroy(graph); return; }
+    if (cudaGraphInstantiate(&rk->graph_exec, graph, 0) != cudaSuccess) { cudaGetLastError(); cudaGraphDestroy(graph); return; }
+    cudaGraphDestroy(graph);
+    rk->launches_per_step = (int)(captured / OCCM_GRAPH_STEPS);
+    rk->graph_state = 1;
+}
+
 extern "C" int occm_rk45_run(occm_rk45* rk, int64_t max_launch_steps, int32_t* n_running, void* stream) {
     if (!rk) { occm_set_error("occm_rk45_run: null handle"); return OCCM_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -802,9 +827,18 @@ extern "C" int occm_rk45_run(occm_rk45* rk, int64_t max_launch_steps, int32_t* n
     while (true) {
         int todo = batch;
         if (max_launch_steps > 0 && launched + todo > max_launch_steps) todo = (int)(max_launch_steps - launched);
-        for (int i = 0; i < todo; ++i) {
-            int rc = occm_rk45_launch_step(rk, st);
-            if (rc) return rc;
+        int i = 0;
+        if (rk->graph_state == 0 && rk->launched_steps + launched >= 1) occm_rk45_build_graph(rk, st);
+        while (i < todo) {
+            if (rk->graph_state == 1 && todo - i >= OCCM_GRAPH_STEPS) {
+                OCCM_CUDA_CHECK(cudaGraphLaunch(rk->graph_exec, st));
+                occm_count_launch(rk->launches_per_step * OCCM_GRAPH_STEPS);
+                i += OCCM_GRAPH_STEPS;
+            } else {
+                int rc = occm_rk45_launch_step(rk, st);
+                if (rc) return rc;
+                ++i;
+            }
         }
         launched += todo;
         occm_count_running<<<1, 256, 0, st>>>(rk->d.status, rk->M, rk->d.n_running);
@@ -887,6 +921,7 @@ extern "C" int occm_rk45_time_stage(occm_rk45* rk, int32_t stage, int32_t reps, 
 extern "C" int occm_rk45_free(occm_rk45* rk) {
     if (!rk) return OCCM_OK;
     if (rk->h_running) cudaFreeHost(rk->h_running);
+    if (rk->graph_exec) cudaGraphExecDestroy(rk->graph_exec);
     free(rk);
     return OCCM_OK;
 }

@@ -335,8 +335,15 @@ def main():
             pass
         peak = float(peaks.get('hbm_gbs', 6650.0))
         ach = alg5 / (ms5 * 1e-3) / 1e9
+        traffic = None          # dram__bytes_read + dram__bytes_write of this kernel from the committed ncu capture (same workload)
+        try:
+            tr = json.load(open(os.path.join(REPO, 'profiles', 'traffic_r01.json')))
+            if tr.get('members_per_gpu') == M_loc and tr.get('n_cstr') == N:
+                traffic = tr['traffic_bytes_per_launch']
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": "occm_fast_cstr<stage 5, K> (fused Dormand-Prince stage: RHS + next stage state)", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                "frac": ach / peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
                 "ms_per_launch": ms5, "alg_bytes_per_launch": alg5,
                 "stage_ms": stage_ms,
                 # all six stage kernels of a step attempt together: 304 B per element over their summed time

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OCCM_ABI_VERSION 1
+#define OCCM_ABI_VERSION 2
 
 typedef enum {
     OCCM_OK = 0,
@@ -193,11 +193,14 @@ typedef struct {
     const double* tdiag;      /* device [n_models]: transport diagonal (CSTR: Q_div_v[j,j]; PFR: -Q_pfr/dV) for the preconditioner */
     int32_t gmres_restart;    /* Krylov dimension per Newton solve (0 = 30) */
     double lin_tol_factor;    /* GMRES stops at |r|_rms <= factor * newton_tol in error-weight scaling (0 = 0.01) */
+    int32_t precond_mode;     /* 0: block inverses kept in the workspace (ndof * n_species doubles per member) and rebuilt only when
+                                 c = h/alpha moved by > 20 %, after 20 attempts or after a slow / failed Newton solve;
+                                 1: blocks rebuilt and solved on every application, nothing stored */
 } occm_bdf_problem;
 
 typedef struct occm_bdf occm_bdf;
 
-size_t occm_bdf_workspace_bytes(const occm_system* sys, int32_t n_members, int32_t gmres_restart);
+size_t occm_bdf_workspace_bytes(const occm_system* sys, int32_t n_members, int32_t gmres_restart, int32_t precond_mode);
 int occm_bdf_init(occm_bdf** out, const occm_system* sys, const occm_members* mem, const occm_bdf_problem* prob,
                   void* workspace, size_t workspace_bytes, void* stream);
 /* Advance until every member is finished / failed / paused (or for at most max_attempts step attempts if > 0). */
@@ -206,6 +209,8 @@ int occm_bdf_resume(occm_bdf* bdf, void* stream);
 /* HOST arrays, any may be NULL. nfev counts Newton and Jacobian-action RHS evaluations. */
 int occm_bdf_stats(occm_bdf* bdf, int32_t* status, int64_t* n_accepted, int64_t* n_rejected, int64_t* nfev, int64_t* n_gmres,
                    int64_t* n_newton_fail, double* t, int32_t* n_rows, int32_t* order, void* stream);
+/* HOST arrays [n_members]: preconditioner applications and rebuilds of the stored block inverses. */
+int occm_bdf_precond_stats(occm_bdf* bdf, int64_t* n_apply, int64_t* n_factor, void* stream);
 int occm_bdf_get_state(occm_bdf* bdf, double* y_out, void* stream);
 int occm_bdf_free(occm_bdf* bdf);
 

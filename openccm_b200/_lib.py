@@ -12,7 +12,7 @@ from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('OCCM_B200_LIB', os.path.join(HERE, 'csrc', 'liboccm_b200.so'))   # override: kernel experiments
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class OccmError(RuntimeError):
@@ -43,7 +43,8 @@ class BdfProblem(C.Structure):
     _fields_ = [('t0', C.c_double), ('t_bound', C.c_double), ('first_step', C.c_double), ('rtol', C.c_double),
                 ('atol', C.c_double), ('y0', C.c_void_p), ('t_eval', C.c_void_p), ('n_t_eval', C.c_int32),
                 ('save_idx', C.c_void_p), ('n_save', C.c_int32), ('out', C.c_void_p), ('out_t', C.c_void_p),
-                ('max_steps', C.c_int64), ('tdiag', C.c_void_p), ('gmres_restart', C.c_int32), ('lin_tol_factor', C.c_double)]
+                ('max_steps', C.c_int64), ('tdiag', C.c_void_p), ('gmres_restart', C.c_int32), ('lin_tol_factor', C.c_double),
+                ('precond_mode', C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/occm_b200.h declares
@@ -65,7 +66,8 @@ SIGNATURES = {
     'occm_rk45_get_state': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'occm_rk45_free': (C.c_int, [C.c_void_p]),
     'occm_rk45_time_stage': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_void_p]),
-    'occm_bdf_workspace_bytes': (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32]),
+    'occm_bdf_workspace_bytes': (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    'occm_bdf_precond_stats': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'occm_bdf_init': (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(Members), C.POINTER(BdfProblem), C.c_void_p, C.c_size_t,
                                 C.c_void_p]),
     'occm_bdf_run': (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.c_void_p]),

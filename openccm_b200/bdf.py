@@ -11,7 +11,10 @@ import ctypes as C
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
+import os
+
 import numpy as np
+
 import torch
 
 from . import _lib
@@ -30,6 +33,8 @@ class BdfResult:
     n_newton_fail: np.ndarray
     y_final: Optional[torch.Tensor] = None
     n_rows: Optional[np.ndarray] = None
+    n_precond_apply: Optional[np.ndarray] = None
+    n_precond_factor: Optional[np.ndarray] = None
 
 
 def transport_diagonal(system: DeviceSystem) -> torch.Tensor:
@@ -47,7 +52,11 @@ def transport_diagonal(system: DeviceSystem) -> torch.Tensor:
 def solve_bdf(system: DeviceSystem, y0: torch.Tensor, t_span: Sequence[float], *, rtol: float, atol: float, first_step: float,
               t_eval: Optional[Sequence[float]] = None, save_idx: Optional[torch.Tensor] = None,
               members: Optional[MemberParams] = None, max_steps: int = 0, gmres_restart: int = 30, lin_tol_factor: float = 0.0,
-              all_capacity: int = 4096, return_final: bool = False) -> BdfResult:
+              all_capacity: int = 4096, return_final: bool = False, precond_mode: Optional[int] = None) -> BdfResult:
+    """``precond_mode``: 0 keeps the block inverses of the preconditioner in HBM (ndof * S doubles per member, rebuilt by
+    CVODE's setup policy), 1 rebuilds and solves the blocks on every application; None = ``OCCM_B200_BDF_PRECOND`` or 0."""
+    if precond_mode is None:
+        precond_mode = int(os.environ.get('OCCM_B200_BDF_PRECOND', '0'))
     assert y0.is_cuda and y0.dtype == torch.float64 and y0.is_contiguous()
     lib = system.lib
     M = 1 if y0.dim() == 1 else y0.shape[0]
@@ -68,12 +77,12 @@ def solve_bdf(system: DeviceSystem, y0: torch.Tensor, t_span: Sequence[float], *
     out = torch.empty((M, T, n_save), dtype=torch.float64, device=system.dev)
     out_t = torch.empty((M, T), dtype=torch.float64, device=system.dev)
     tdiag = transport_diagonal(system)
-    ws_bytes = lib.occm_bdf_workspace_bytes(system.handle, M, gmres_restart)
+    ws_bytes = lib.occm_bdf_workspace_bytes(system.handle, M, gmres_restart, int(precond_mode))
     ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=system.dev)
     ws_ptr = (ws.data_ptr() + 255) & ~255
     prob = _lib.BdfProblem(float(t_span[0]), float(t_span[1]), float(first_step), float(rtol), float(atol), y0.data_ptr(),
                            _ptr(te), T, _ptr(save_idx), n_save, out.data_ptr(), out_t.data_ptr(), int(max_steps),
-                           tdiag.data_ptr(), int(gmres_restart), float(lin_tol_factor))
+                           tdiag.data_ptr(), int(gmres_restart), float(lin_tol_factor), int(precond_mode))
     ms = mem.c_struct()
     handle = C.c_void_p()
     _lib.check(lib.occm_bdf_init(C.byref(handle), system.handle, C.byref(ms), C.byref(prob), ws_ptr, ws_bytes, _stream()))
@@ -98,6 +107,8 @@ def solve_bdf(system: DeviceSystem, y0: torch.Tensor, t_span: Sequence[float], *
             if not np.any(status == 2):
                 break
             _lib.check(lib.occm_bdf_resume(handle, _stream()))
+        n_pa, n_pf = i64(), i64()
+        _lib.check(lib.occm_bdf_precond_stats(handle, n_pa.ctypes.data, n_pf.ctypes.data, _stream()))
         y_final = None
         if return_final:
             y_final = torch.empty((M, system.ndof), dtype=torch.float64, device=system.dev)
@@ -108,5 +119,5 @@ def solve_bdf(system: DeviceSystem, y0: torch.Tensor, t_span: Sequence[float], *
     if all_mode:
         t_res = [np.concatenate(x) if x else np.zeros(0) for x in ts_all]
         y_res = [torch.cat(x) if x else out[m, :0] for m, x in enumerate(ys_all)]
-        return BdfResult(t_res, y_res, status, n_acc, n_rej, nfev, n_gm, n_nf, y_final)
-    return BdfResult(te_np, out, status, n_acc, n_rej, nfev, n_gm, n_nf, y_final, n_rows)
+        return BdfResult(t_res, y_res, status, n_acc, n_rej, nfev, n_gm, n_nf, y_final, None, n_pa, n_pf)
+    return BdfResult(te_np, out, status, n_acc, n_rej, nfev, n_gm, n_nf, y_final, n_rows, n_pa, n_pf)

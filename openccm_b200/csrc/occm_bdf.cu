@@ -8,8 +8,10 @@
 // scaling of the Newton test, with
 //   * J*v by a directional difference of the fused RHS kernel (always the Jacobian at the current predictor, so the
 //     "stale Jacobian" bookkeeping of scipy disappears), and
-//   * a block-Jacobi preconditioner: per point the S x S block I - c*(transport diagonal + d r/d c) is rebuilt from the
-//     state and solved on the fly (nothing stored).
+//   * a block preconditioner: per point the S x S block I - c*(transport diagonal + d r/d c); its inverse is formed
+//     once (warp-cooperative Gauss-Jordan), kept in HBM and reused — CVODE's setup policy: rebuilt when c = h/alpha
+//     has moved by more than 20 %, after 20 attempts, or after a slow / failed Newton solve — so an application is one
+//     S x S mat-vec per point (precond_mode 1 instead rebuilds and solves the block on every application, nothing stored).
 // All members advance in lock step through the phases of a step attempt; per-member masks switch members off inside
 // the Newton and GMRES loops.  Reductions go through per-chunk partial sums added in a fixed order (deterministic).
 #include <math.h>
@@ -44,6 +46,9 @@ struct OccmBdfDev {
     long long max_steps;
     const double* tdiag;                     // transport diagonal per model (CSTR: A_jj, PFR: -Q/dV)
     const double* q_scale; const double* k_scale;
+    // stored block inverses (precond_mode 0): Binv[m][point][j][i] = (B_point^-1)(i, j)
+    int store;
+    double* Binv; double* c_fact; int* need_factor; int* since_factor; int* force_factor; long long* n_factor;
 };
 
 struct occm_bdf {
@@ -186,10 +191,9 @@ __global__ void __launch_bounds__(256) bdf_scale_col(const OccmBdfDev b, int col
 //         the block lower-bidiagonal operator of the upwind discretisation (pfr_system.py:296) — block ILU(0) == LU here.
 //         Inlet nodes (coupled to OTHER PFRs, pfr_system.py:313-314) keep the identity; that coupling is left to GMRES.
 template <int W>
-__device__ __forceinline__ void bdf_group_solve(const OccmTab& T, int nterm, int nfac, int S, int lane, double cown, double c, double tau,
-                                                const double* ksc, double& u) {
+__device__ __forceinline__ void bdf_group_rows(const OccmTab& T, int nterm, int nfac, int S, int lane, double cown, double c, double tau,
+                                               const double* ksc, double (&row)[W]) {
     // row `lane` of B = (1 - c tau) I - c dr/dc
-    double row[W];
 #pragma unroll
     for (int j = 0; j < W; ++j) row[j] = (j == lane) ? 1.0 - c * tau : 0.0;
     auto conc = [&](int sp) { return __shfl_sync(0xffffffffu, cown, sp, W); };
@@ -220,6 +224,38 @@ __device__ __forceinline__ void bdf_group_solve(const OccmTab& T, int nterm, int
             for (int j = 0; j < W; ++j) row[j] -= (j == xs[f]) ? c * dv : 0.0;
         }
     }
+}
+
+// Gauss-Jordan inverse without pivoting: on return inv[] is row `lane` of B^-1 (row[] is destroyed).  At pivot k the
+// pivot row of the right half is non-zero only in columns <= k and of the left half only columns > k matter: W shuffles.
+template <int W>
+__device__ __forceinline__ void bdf_group_invert(int S, int lane, double (&row)[W], double (&inv)[W]) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) inv[j] = (j == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+        if (k >= S) break;
+        const double ipk = 1.0 / __shfl_sync(0xffffffffu, row[k], k, W);
+        const bool piv = lane == k;
+        const double l = (!piv && lane < S) ? row[k] * ipk : 0.0;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            if (j > k) {
+                const double pkj = __shfl_sync(0xffffffffu, row[j], k, W);
+                row[j] = piv ? pkj * ipk : row[j] - l * pkj;
+            } else {
+                const double pij = __shfl_sync(0xffffffffu, inv[j], k, W);
+                inv[j] = piv ? pij * ipk : inv[j] - l * pij;
+            }
+        }
+    }
+}
+
+template <int W>
+__device__ __forceinline__ void bdf_group_solve(const OccmTab& T, int nterm, int nfac, int S, int lane, double cown, double c, double tau,
+                                                const double* ksc, double& u) {
+    double row[W];
+    bdf_group_rows<W>(T, nterm, nfac, S, lane, cown, c, tau, ksc, row);
     // elimination (no pivoting)
 #pragma unroll
     for (int k = 0; k < W; ++k) {
@@ -293,6 +329,116 @@ __global__ void __launch_bounds__(128) bdf_precond_warp(const __grid_constant__ 
                 if (on) dst[gbase + (long long)i * S] = u;
                 xprev = u;
                 y = yn; d = dn; w = wn;
+            }
+        }
+    }
+}
+
+// ---- stored variant: factor (all points in parallel, members with need_factor) ...
+template <int W>
+__global__ void __launch_bounds__(128) bdf_precond_factor(const __grid_constant__ OccmSysDev sys, const OccmBdfDev b) {
+    extern __shared__ double smem_d[];
+    if (b.counters[3] == 0) return;                   // no member asked for a rebuild in this attempt
+    int* tab_s = reinterpret_cast<int*>(smem_d);
+    occm_load_tables(sys.tables, sys.tables_bytes, tab_s);
+    const OccmTab T = occm_tab_views(tab_s);
+    const int S = sys.S, P = sys.P;
+    const int nterm = tab_s[OCCM_H_MAX_TERMS], nfac = min(4, tab_s[OCCM_H_MAX_SLOTS]);
+    const int lane = threadIdx.x % W, gib = threadIdx.x / W, gpb = 128 / W;
+    const long long per_member = sys.n_points;
+    const long long total = (long long)b.M * per_member;
+    const long long rounded = (total + gpb - 1) / gpb * gpb;
+    for (long long g = (long long)blockIdx.x * gpb + gib; g < rounded; g += (long long)gridDim.x * gpb) {
+        const bool gv = g < total;
+        const int m = gv ? (int)(g / per_member) : 0;
+        const long long idx = gv ? g - (long long)m * per_member : 0;
+        const bool inlet_node = sys.model == OCCM_MODEL_PFR && idx % P == 0;      // keeps the identity, never read
+        // whole warps skip together only when both of their groups skip: the shuffles below are group-wide (width W)
+        const bool work = gv && b.need_factor[m] && !inlet_node;
+        const bool on = work && lane < S;
+        const long long e = (long long)m * b.ndof + idx * S;
+        const double y = on ? b.y[e + lane] : 0.0;
+        const double qs = b.q_scale ? b.q_scale[m] : 1.0;
+        const double* ksc = b.k_scale ? b.k_scale + (long long)m * sys.n_rxn : nullptr;
+        const long long model = sys.model == OCCM_MODEL_PFR ? idx / P : idx;
+        double row[W], inv[W];
+        bdf_group_rows<W>(T, nterm, nfac, S, lane, y, b.c[m], qs * b.tdiag[gv ? model : 0], ksc, row);
+        bdf_group_invert<W>(S, lane, row, inv);
+        if (on) {
+            double* o = b.Binv + e * S + lane;
+#pragma unroll
+            for (int j = 0; j < W; ++j) if (j < S) o[(long long)j * S] = inv[j];
+        }
+    }
+}
+
+// ... and apply: out = M^-1 (scale .* in) as one S x S mat-vec per point (PFR: inside the flow-order sweep)
+template <int MODEL, int W>
+__global__ void __launch_bounds__(128) bdf_precond_apply(const OccmBdfDev b, const double* __restrict__ src, int src_is_V_col_j,
+                                                         double* __restrict__ dst, const int* __restrict__ mask) {
+    const int S = b.S, P = b.P;
+    const int lane = threadIdx.x % W, gib = threadIdx.x / W, gpb = 128 / W;
+    const long long per_member = MODEL == 0 ? b.n_points : b.n_points / P;
+    const long long total = (long long)b.M * per_member;
+    const long long rounded = (total + gpb - 1) / gpb * gpb;
+    for (long long g = (long long)blockIdx.x * gpb + gib; g < rounded; g += (long long)gridDim.x * gpb) {
+        const bool gv = g < total;
+        const int m = gv ? (int)(g / per_member) : 0;
+        const long long idx = gv ? g - (long long)m * per_member : 0;
+        const bool on = gv && mask[m] && lane < S;
+        const double* in = src + (src_is_V_col_j ? (long long)b.gmres_j[m] * b.vstride : 0) + (long long)m * b.ndof;
+        if (MODEL == 0) {
+            const long long g0 = (long long)m * b.ndof + idx * S + lane;
+            const double* bi = b.Binv + ((long long)m * b.ndof + idx * S) * S + lane;
+            double r[W];
+#pragma unroll
+            for (int j = 0; j < W; ++j) r[j] = (on && j < S) ? bi[(long long)j * S] : 0.0;
+            const double y = on ? b.y[g0] : 0.0, d = on ? b.d[g0] : 0.0;
+            const double u = on ? (b.atol + b.rtol * fabs(y - d)) * in[idx * S + lane] : 0.0;
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < W; j += 2) {
+                a0 += r[j] * __shfl_sync(0xffffffffu, u, j, W);
+                a1 += r[j + 1] * __shfl_sync(0xffffffffu, u, j + 1, W);
+            }
+            if (on) dst[g0] = a0 + a1;
+        } else {
+            const double c = b.c[m];
+            const double qs = b.q_scale ? b.q_scale[m] : 1.0;
+            const double ca = c * qs * (-b.tdiag[gv ? idx : 0]);             // c * Q/dV of this PFR
+            const long long gbase = (long long)m * b.ndof + idx * P * S + lane;
+            const double* inp = in + idx * P * S + lane;
+            const double* bi = b.Binv + ((long long)m * b.ndof + idx * P * S) * S + lane;
+            double xprev = 0.0;
+            double y = on ? b.y[gbase] : 0.0, d = on ? b.d[gbase] : 0.0, w = on ? inp[0] : 0.0;
+            double r[W];
+#pragma unroll
+            for (int j = 0; j < W; ++j) r[j] = 0.0;
+            for (int i = 0; i < P; ++i) {
+                // the next point's block row and operands are requested before this point's (sequentially dependent) mat-vec
+                const bool more = on && i + 1 < P;
+                double rn[W];
+#pragma unroll
+                for (int j = 0; j < W; ++j) rn[j] = (more && j < S) ? bi[((long long)(i + 1) * S + j) * S] : 0.0;
+                const double yn = more ? b.y[gbase + (long long)(i + 1) * S] : 0.0;
+                const double dn = more ? b.d[gbase + (long long)(i + 1) * S] : 0.0;
+                const double wn = more ? inp[(long long)(i + 1) * S] : 0.0;
+                double u = (b.atol + b.rtol * fabs(y - d)) * w;
+                if (i > 0) {
+                    u += ca * xprev;
+                    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < W; j += 2) {
+                        a0 += r[j] * __shfl_sync(0xffffffffu, u, j, W);
+                        a1 += r[j + 1] * __shfl_sync(0xffffffffu, u, j + 1, W);
+                    }
+                    u = a0 + a1;
+                }
+                if (on) dst[gbase + (long long)i * S] = u;
+                xprev = u;
+                y = yn; d = dn; w = wn;
+#pragma unroll
+                for (int j = 0; j < W; ++j) r[j] = rn[j];
             }
         }
     }
@@ -505,6 +651,7 @@ __global__ void bdf_ctrl_init(const OccmBdfDev b, double t0, double first_step, 
     b.t_new[m] = t0;
     b.nfev[m] = 1; b.n_acc[m] = 0; b.n_rej[m] = 0; b.n_newton_fail[m] = 0; b.n_gmres[m] = 0; b.n_precond[m] = 0;
     b.accepted_now[m] = 0; b.out_lo[m] = 0; b.out_hi[m] = 0; b.n_rows[m] = all_mode ? 1 : 0; b.need_change[m] = 0;
+    b.c_fact[m] = 0.0; b.need_factor[m] = 0; b.since_factor[m] = 0; b.force_factor[m] = 0; b.n_factor[m] = 0;
 }
 
 // start of a step attempt (bdf.py:318-356): step-size clipping, t_new, h, c; may request a change_D
@@ -512,6 +659,7 @@ __global__ void bdf_ctrl_begin(const OccmBdfDev b) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= b.M) return;
     b.need_change[m] = 0; b.accepted_now[m] = 0; b.attempt_ok[m] = 0; b.newton_active[m] = 0; b.gmres_active[m] = 0;
+    b.need_factor[m] = 0;
     if (b.status[m] != OCCM_MEMBER_RUNNING) return;
     const double t = b.t[m];
     const int order = b.order[m];
@@ -527,7 +675,17 @@ __global__ void bdf_ctrl_begin(const OccmBdfDev b) {
     const double h = t_new - t;
     h_abs = fabs(h);
     if (clipped) bdf_set_change(b, m, order, h_abs / h_abs0);     // the clip events of bdf.py:321-326 and :348-352 in one rescale
-    b.h_abs[m] = h_abs; b.t_new[m] = t_new; b.c[m] = h / bdf_alpha(order);
+    const double c = h / bdf_alpha(order);
+    b.h_abs[m] = h_abs; b.t_new[m] = t_new; b.c[m] = c;
+    if (b.store) {
+        // when to rebuild the stored block inverses (the setup policy of CVODE's Newton iteration: gamma ratio, age, failure)
+        const double cf = b.c_fact[m];
+        const int age = b.since_factor[m];
+        if (cf == 0.0 || fabs(c / cf - 1.0) > 0.2 || age >= 20 || b.force_factor[m]) {
+            b.need_factor[m] = 1; b.c_fact[m] = c; b.since_factor[m] = 0; b.force_factor[m] = 0; b.n_factor[m] += 1;
+            atomicAdd(&b.counters[3], 1);
+        } else b.since_factor[m] = age + 1;
+    }
     b.newton_active[m] = 1; b.newton_k[m] = 0; b.converged[m] = 0; b.n_iter[m] = 0; b.dy_norm_old[m] = -1.0;
     atomicAdd(&b.counters[1], 1);
 }
@@ -641,6 +799,7 @@ __global__ void bdf_ctrl_newton(const OccmBdfDev b) {
         stop = true; conv = true;
     }
     b.dy_norm_old[m] = dy_norm;
+    if (b.gmres_j[m] >= 6) b.force_factor[m] = 1;        // the stored preconditioner has aged: many Krylov vectors were needed
     b.newton_k[m] = k + 1;
     if (!stop && k + 1 >= BDF_NEWTON_MAXITER) stop = true;
     if (stop) { b.newton_active[m] = 0; b.converged[m] = conv ? 1 : 0; }
@@ -661,6 +820,7 @@ __global__ void bdf_ctrl_after_newton(const OccmBdfDev b) {
         bdf_set_change(b, m, b.order[m], 0.5);
         b.n_equal[m] = 0;
         b.n_newton_fail[m] += 1; b.n_rej[m] += 1;
+        b.force_factor[m] = 1;
         if (b.max_steps > 0 && b.n_acc[m] + b.n_rej[m] >= b.max_steps) b.status[m] = OCCM_MEMBER_MAX_STEPS;
     }
 }
@@ -760,7 +920,7 @@ static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct BdfLayout { size_t total; size_t off[64]; int n; };
 
-static size_t bdf_carve(const occm_system* sys, int M, int restart, OccmBdfDev* d, char* w) {
+static size_t bdf_carve(const occm_system* sys, int M, int restart, int store, OccmBdfDev* d, char* w) {
     size_t o = 0;
     const size_t vec = al256((size_t)M * sys->dev.ndof * sizeof(double));
     auto take = [&](size_t bytes) { size_t r = o; o += al256(bytes); return w ? (void*)(w + r) : (void*)nullptr; };
@@ -786,14 +946,17 @@ static size_t bdf_carve(const occm_system* sys, int M, int restart, OccmBdfDev* 
     b.nfev = (long long*)take(md); b.n_acc = (long long*)take(md); b.n_rej = (long long*)take(md);
     b.n_newton_fail = (long long*)take(md); b.n_gmres = (long long*)take(md); b.n_precond = (long long*)take(md);
     b.counters = (int*)take(256);
+    b.c_fact = (double*)take(md); b.need_factor = (int*)take(mi); b.since_factor = (int*)take(mi); b.force_factor = (int*)take(mi);
+    b.n_factor = (long long*)take(md);
+    b.Binv = store ? (double*)take((size_t)M * sys->dev.ndof * sys->dev.S * sizeof(double)) : nullptr;
     b.nchunk = nchunk;
     return o;
 }
 
-extern "C" size_t occm_bdf_workspace_bytes(const occm_system* sys, int32_t M, int32_t restart) {
+extern "C" size_t occm_bdf_workspace_bytes(const occm_system* sys, int32_t M, int32_t restart, int32_t precond_mode) {
     if (!sys || M < 1) return 0;
     if (restart <= 0) restart = 30;
-    return bdf_carve(sys, M, restart, nullptr, nullptr);
+    return bdf_carve(sys, M, restart, precond_mode == 0, nullptr, nullptr);
 }
 
 static int bdf_grid(const occm_system* sys, long long chunks) {
@@ -834,11 +997,50 @@ static int bdf_precond_launch_w(occm_bdf* h, const double* src, int from_col_j, 
     return OCCM_OK;
 }
 
+template <int W>
+static int bdf_factor_launch_w(occm_bdf* h, cudaStream_t st) {
+    const occm_system* sys = h->sys;
+    const size_t smem = sys->smem_tables;
+    static size_t lim = 48 * 1024;
+    if (smem > lim) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(bdf_precond_factor<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); lim = smem; }
+    const long long groups = (long long)h->M * sys->dev.n_points;
+    const int gpb = 128 / W;
+    long long blocks = (groups + gpb - 1) / gpb;
+    const long long cap = (long long)sys->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    BDF_LAUNCH((bdf_precond_factor<W>), (int)blocks, 128, smem, sys->dev, h->d);
+    return OCCM_OK;
+}
+// rebuild the stored block inverses of the members flagged by bdf_ctrl_begin (at the predictor of this attempt)
+static int bdf_factor_launch(occm_bdf* h, cudaStream_t st) {
+    const int S = h->sys->dev.S;
+    return S <= 4 ? bdf_factor_launch_w<4>(h, st) : S <= 8 ? bdf_factor_launch_w<8>(h, st) : bdf_factor_launch_w<16>(h, st);
+}
+
+template <int MODEL, int W>
+static int bdf_apply_launch_w(occm_bdf* h, const double* src, int from_col_j, double* dst, const int* mask, cudaStream_t st) {
+    const occm_system* sys = h->sys;
+    const long long groups = (long long)h->M * (MODEL == 0 ? sys->dev.n_points : sys->dev.n_models);
+    const int gpb = 128 / W;
+    long long blocks = (groups + gpb - 1) / gpb;
+    const long long cap = (long long)sys->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    BDF_LAUNCH((bdf_precond_apply<MODEL, W>), (int)blocks, 128, 0, h->d, src, from_col_j, dst, mask);
+    return OCCM_OK;
+}
+
 static int bdf_precond_launch(occm_bdf* h, const double* src, int from_col_j, double* dst, const int* mask, int want_norm, cudaStream_t st) {
     const occm_system* sys = h->sys;
     const int S = sys->dev.S;
     int rc;
-    if (sys->dev.model == OCCM_MODEL_CSTR)
+    if (h->d.store) {
+        if (sys->dev.model == OCCM_MODEL_CSTR)
+            rc = S <= 4 ? bdf_apply_launch_w<0, 4>(h, src, from_col_j, dst, mask, st) : S <= 8 ? bdf_apply_launch_w<0, 8>(h, src, from_col_j, dst, mask, st)
+                                                                                              : bdf_apply_launch_w<0, 16>(h, src, from_col_j, dst, mask, st);
+        else
+            rc = S <= 4 ? bdf_apply_launch_w<1, 4>(h, src, from_col_j, dst, mask, st) : S <= 8 ? bdf_apply_launch_w<1, 8>(h, src, from_col_j, dst, mask, st)
+                                                                                              : bdf_apply_launch_w<1, 16>(h, src, from_col_j, dst, mask, st);
+    } else if (sys->dev.model == OCCM_MODEL_CSTR)
         rc = S <= 4 ? bdf_precond_launch_w<0, 4>(h, src, from_col_j, dst, mask, st) : S <= 8 ? bdf_precond_launch_w<0, 8>(h, src, from_col_j, dst, mask, st)
                                                                                            : bdf_precond_launch_w<0, 16>(h, src, from_col_j, dst, mask, st);
     else
@@ -871,7 +1073,9 @@ extern "C" int occm_bdf_init(occm_bdf** out, const occm_system* sys, const occm_
     if (p->n_t_eval < 1 || (!p->t_eval && (p->n_t_eval < 2 || !p->out_t))) { occm_set_error("bad output description"); return OCCM_ERR_INVALID; }
     const int restart = p->gmres_restart > 0 ? p->gmres_restart : 30;
     if (restart + 2 > BDF_MAXDOT) { occm_set_error("gmres_restart must be <= %d", BDF_MAXDOT - 2); return OCCM_ERR_INVALID; }
-    const size_t need = bdf_carve(sys, M, restart, nullptr, nullptr);
+    if (p->precond_mode != 0 && p->precond_mode != 1) { occm_set_error("precond_mode must be 0 (stored block inverses) or 1 (on the fly)"); return OCCM_ERR_INVALID; }
+    const int store = p->precond_mode == 0;
+    const size_t need = bdf_carve(sys, M, restart, store, nullptr, nullptr);
     if (workspace_bytes < need) { occm_set_error("workspace too small: %zu < %zu", workspace_bytes, need); return OCCM_ERR_WORKSPACE; }
     if ((uintptr_t)workspace & 255) { occm_set_error("workspace must be 256-byte aligned"); return OCCM_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -880,7 +1084,8 @@ extern "C" int occm_bdf_init(occm_bdf** out, const occm_system* sys, const occm_
     if (mem) h->mem = *mem; else { memset(&h->mem, 0, sizeof(h->mem)); h->mem.n_members = 1; }
     OccmBdfDev& b = h->d;
     memset(&b, 0, sizeof(b));
-    bdf_carve(sys, M, restart, &b, (char*)workspace);
+    bdf_carve(sys, M, restart, store, &b, (char*)workspace);
+    b.store = store;
     b.M = M; b.S = sys->dev.S; b.P = sys->dev.P; b.model = sys->dev.model; b.restart = restart;
     b.ndof = sys->dev.ndof; b.n_points = sys->dev.n_points; b.vstride = (long long)M * sys->dev.ndof;
     b.rtol = p->rtol; b.atol = p->atol; b.t_bound = p->t_bound; b.max_steps = p->max_steps;
@@ -917,6 +1122,7 @@ static int bdf_attempt(occm_bdf* h, cudaStream_t st) {
     BDF_LAUNCH(bdf_change_D, gv, 256, 0, b);
     BDF_LAUNCH(bdf_clear_change, gm, 64, 0, b);
     BDF_LAUNCH(bdf_predict, gv, 256, 0, b);
+    if (b.store && (rc = bdf_factor_launch(h, st))) return rc;
     for (int k = 0; k < BDF_NEWTON_MAXITER; ++k) {
         if ((rc = bdf_rhs(h, b.newton_active, nullptr, nullptr, b.f, st))) return rc;          // f = fun(t_new, y)
         BDF_LAUNCH(bdf_newton_rhs, gv, 256, 0, b);
@@ -1009,6 +1215,15 @@ extern "C" int occm_bdf_stats(occm_bdf* h, int32_t* status, int64_t* n_accepted,
     OCCM_CUDA_CHECK(cp(status, b.status, M * 4)); OCCM_CUDA_CHECK(cp(n_accepted, b.n_acc, M * 8)); OCCM_CUDA_CHECK(cp(n_rejected, b.n_rej, M * 8));
     OCCM_CUDA_CHECK(cp(nfev, b.nfev, M * 8)); OCCM_CUDA_CHECK(cp(n_gmres, b.n_gmres, M * 8)); OCCM_CUDA_CHECK(cp(n_newton_fail, b.n_newton_fail, M * 8));
     OCCM_CUDA_CHECK(cp(t, b.t, M * 8)); OCCM_CUDA_CHECK(cp(n_rows, h->prob.t_eval ? b.out_hi : b.n_rows, M * 4)); OCCM_CUDA_CHECK(cp(order, b.order, M * 4));
+    OCCM_CUDA_CHECK(cudaStreamSynchronize(st));
+    return OCCM_OK;
+}
+
+extern "C" int occm_bdf_precond_stats(occm_bdf* h, int64_t* n_apply, int64_t* n_factor, void* stream) {
+    if (!h) { occm_set_error("occm_bdf_precond_stats: null handle"); return OCCM_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_apply) OCCM_CUDA_CHECK(cudaMemcpyAsync(n_apply, h->d.n_precond, h->M * 8, cudaMemcpyDeviceToHost, st));
+    if (n_factor) OCCM_CUDA_CHECK(cudaMemcpyAsync(n_factor, h->d.n_factor, h->M * 8, cudaMemcpyDeviceToHost, st));
     OCCM_CUDA_CHECK(cudaStreamSynchronize(st));
     return OCCM_OK;
 }

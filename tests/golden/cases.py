@@ -44,6 +44,12 @@ def _cfg(model, species, ic, bc, t_span, t_eval, rxn, *, P=2, rtol=1e-8, atol=1e
                 rtol=rtol, atol=atol, first=first, rtd=rtd)
 
 
+def _openfoam_cstr_network() -> NetworkArrays:
+    with open(os.path.join(HERE, 'openfoam_2d_cstr_network.pickle'), 'rb') as fh:
+        d = pickle.load(fh)
+    return NetworkArrays(**d)
+
+
 def _openfoam_network() -> NetworkArrays:
     with open(os.path.join(HERE, 'openfoam_2d_pfr_network.pickle'), 'rb') as fh:
         d = pickle.load(fh)
@@ -107,6 +113,11 @@ CASES: Dict[str, dict] = {
     'openfoam_2d_pfr': dict(net=_openfoam_network, **_cfg(
         'pfr', 'a', ['a -> 0'], ['a: inlet -> 1'], '0, 300', '5.0, linear', None, P=2, rtol=1e-10, atol=1e-12, rtd=True),
         solvers=('LSODA',), centroids='fixture'),
+    # ---- C3: the same mesh as a CSTR network (76 CSTRs), 2NaCl + CaCO3 <-> Na2CO3 + CaCl2 (BASELINE.json configs[2])
+    'openfoam_2d_cstr_nacl': dict(net=_openfoam_cstr_network, **_cfg(
+        'cstr', 'NaCl, CaCO3, Na2CO3, CaCl2', ['NaCl -> 0', 'CaCO3 -> 0', 'Na2CO3 -> 0', 'CaCl2 -> 0'],
+        ['NaCl: inlet -> 1', 'CaCO3: inlet -> 1', 'Na2CO3: inlet -> 0', 'CaCl2: inlet -> 0'],
+        '0, 300', '5.0, linear', 'nacl', rtol=1e-10, atol=1e-12), centroids='fixture'),
 }
 
 

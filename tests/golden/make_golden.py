@@ -143,6 +143,37 @@ def parser_kats() -> None:
     print('[golden] parser_kats.json')
 
 
+def openfoam_cstr_fixture() -> None:
+    """C3: the same OpenFOAM 2-D example compartmentalised with model = CSTR (76 CSTRs); network + geometry fixture."""
+    import openccm
+    tmp = tempfile.mkdtemp(prefix='golden_openfoam_cstr_')
+    dst = os.path.join(tmp, 'case')
+    shutil.copytree('/root/reference/examples/OpenFOAM/pipe_with_recirc', dst)
+    old = os.getcwd(); os.chdir(dst)
+    try:
+        cp = ConfigParser('CONFIG')
+        cp['COMPARTMENT MODELLING']['model'] = 'cstr'
+        cp['SIMULATION']['points_per_pfr'] = '1'
+        cp['SIMULATION']['run'] = 'False'
+        cp['POST-PROCESSING']['calculate_rtd'] = 'False'
+        openccm.run(cp)
+        with open('cache/cstr_network.pickle', 'rb') as fh:
+            network = pickle.load(fh)
+        with open('cache/cmesh.pickle', 'rb') as fh:
+            cmesh = pickle.load(fh)
+    finally:
+        os.chdir(old)
+    from openccm_b200.network import NetworkArrays
+    na = NetworkArrays.from_model_network(network)
+    d = {k: getattr(na, k) for k in ('n_models', 'volumes', 'flows', 'in_model', 'in_conn', 'in_other',
+                                     'out_model', 'out_conn', 'out_other')}
+    d['model_to_element_map'] = [[(float(a), int(b)) for a, b in m] for m in na.model_to_element_map]
+    with open(os.path.join(HERE, 'openfoam_2d_cstr_network.pickle'), 'wb') as fh:
+        pickle.dump(d, fh, protocol=4)
+    print(f'[golden] openfoam cstr fixture: {na.n_models} CSTRs, {na.flows.size} connections')
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
 def openfoam_fixture() -> None:
     """Run the reference's own pipeline on examples/OpenFOAM/pipe_with_recirc (a writable copy) and freeze the
     444-PFR model network + element geometry as a fixture (inputs only)."""
@@ -182,6 +213,9 @@ if __name__ == '__main__':
     if '--openfoam-fixture' in argv:
         argv.remove('--openfoam-fixture')
         openfoam_fixture()
+    if '--openfoam-cstr-fixture' in argv:
+        argv.remove('--openfoam-cstr-fixture')
+        openfoam_cstr_fixture()
     if '--kats' in argv:
         argv.remove('--kats')
         parser_kats()

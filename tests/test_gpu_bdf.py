@@ -44,6 +44,19 @@ def test_bdf_openfoam_network(tmp_path):
     assert info['nfev'] < 400_000
 
 
+def test_bdf_openfoam_cstr_nacl(tmp_path):
+    """C3 (BASELINE.json configs[2]): 76 CSTRs of the OpenFOAM example, 2NaCl + CaCO3 <-> Na2CO3 + CaCl2, against the
+    unmodified reference's LSODA solve at rtol 1e-10 / atol 1e-12."""
+    from openccm_b200.system_solvers import solve_system
+    g = load_golden('openfoam_2d_cstr_nacl')
+    cp, cmesh, net, mn = setup_case('openfoam_2d_cstr_nacl', 'B200-BDF', tmp_path, rtol=1e-9, atol=1e-12)
+    c, t, imap, omap, info = solve_system('cstr', mn, cp, cmesh, return_info=True)
+    assert info['status'] == 1, info
+    ref = g['c_LSODA']
+    np.testing.assert_allclose(t, g['t_LSODA'], rtol=0, atol=1e-14)
+    assert np.all(np.abs(c - ref) <= 1e-8 + 1e-6 * np.abs(ref)), np.abs(c - ref).max()
+
+
 def test_bdf_batched_members(tmp_path):
     """Members with different rate constants / flows advance in lock step with individual orders and step sizes."""
     from oracle import openccm_oracle as O

@@ -98,7 +98,9 @@ typedef struct {
     const double*  ell_w;
     const uint8_t* point_flags; /* [n_points] or NULL: 1 = evaluate this point on the generic path */
     /* optional: the same ELL operator packed as 16-byte entries {int32 src; int32 flag; double w}, column-major
-     * [ell_width][n_models], flag (column 0 only) = point_flags; enables the 128-bit fast kernels for even n_species */
+     * [ell_width][n_points], flag (column 0 only) = point_flags; enables the 128-bit fast kernels for even n_species.
+     * PFR networks: ell_width = 1, one entry per point {src = upwind point (own index on inlet nodes), flag, w = Q/dV of
+     * the PFR}; every inlet node (point % points_per_model == 0) must be flagged (ell_src / ell_w stay NULL). */
     const void*    ell_packed;
     const int32_t* flagged_points; /* [n_flagged] indices of the points with point_flags = 1 (needed with ell_packed) */
     int32_t        n_flagged;

@@ -24,6 +24,7 @@ struct OccmSysDev {
     const int* ell_src; const double* ell_w;   // column-major [ell_k][n_models]; padding = (own row, weight 0)
     const unsigned char* point_flags;          // [n_points] 1 = take the generic (CSR / table-walk) path
     int fast_ok;                               // mechanism fits the register-resident reaction form
+    int wide_ok;                               // mechanism fits the shared-memory term-list form of the fast kernels
     const int* row_ptr; const int* row_src; const double* row_w; const double* a;
     const int* pulse_ptr; const int* pulse_fn; const double* pulse_w;
     const int* tables; int tables_bytes;
@@ -180,33 +181,36 @@ __device__ __forceinline__ double occm_reaction_tables(const OccmTab& T, int s, 
 // evaluation is branch free.
 #define OCCM_NT 4   // terms per species
 #define OCCM_NF 3   // factor slots per term (a factor of order n occupies n slots)
+#define OCCM_WIDE_MAX_TERMS 32   // longest per-species term list of the shared-memory (WIDE) form of the fast kernels
 struct OccmRxnRegs {
     double coeff[OCCM_NT];
     unsigned meta[OCCM_NT];   // rxn | f0 << 8 | f1 << 16 | f2 << 24
 };
 
-__device__ __forceinline__ OccmRxnRegs occm_rxn_regs(const OccmTab& T, int s, int S) {
-    OccmRxnRegs R;
+// term i of species s in register form: coefficient and packed meta word (padding term when i is past the species' list)
+__device__ __forceinline__ void occm_rxn_term(const OccmTab& T, int s, int i, int S, double& coeff, unsigned& meta) {
     const unsigned pad = (unsigned)S;
     const int tb = T.term_ptr[s], n = T.term_ptr[s + 1] - tb;
-#pragma unroll
-    for (int i = 0; i < OCCM_NT; ++i) {
-        R.coeff[i] = 0.0;
-        unsigned meta = (pad << 8) | (pad << 16) | (pad << 24);
-        if (i < n) {
-            const int k = tb + i;
-            R.coeff[i] = T.term_coeff[k];
-            meta = (unsigned)T.term_rxn[k] & 0xffu;
-            int slot = 0;
-            for (int f = T.fac_ptr[k]; f < T.fac_ptr[k + 1]; ++f)
-                for (int q = 0; q < T.fac_ord[f]; ++q) {
-                    if (slot < OCCM_NF) meta |= ((unsigned)T.fac_sp[f] & 0xffu) << (8 + 8 * slot);
-                    ++slot;
-                }
-            for (int q = slot; q < OCCM_NF; ++q) meta |= pad << (8 + 8 * q);
-        }
-        R.meta[i] = meta;
+    coeff = 0.0;
+    meta = (pad << 8) | (pad << 16) | (pad << 24);
+    if (i < n) {
+        const int k = tb + i;
+        coeff = T.term_coeff[k];
+        meta = (unsigned)T.term_rxn[k] & 0xffu;
+        int slot = 0;
+        for (int f = T.fac_ptr[k]; f < T.fac_ptr[k + 1]; ++f)
+            for (int q = 0; q < T.fac_ord[f]; ++q) {
+                if (slot < OCCM_NF) meta |= ((unsigned)T.fac_sp[f] & 0xffu) << (8 + 8 * slot);
+                ++slot;
+            }
+        for (int q = slot; q < OCCM_NF; ++q) meta |= pad << (8 + 8 * q);
     }
+}
+
+__device__ __forceinline__ OccmRxnRegs occm_rxn_regs(const OccmTab& T, int s, int S) {
+    OccmRxnRegs R;
+#pragma unroll
+    for (int i = 0; i < OCCM_NT; ++i) occm_rxn_term(T, s, i, S, R.coeff[i], R.meta[i]);
     return R;
 }
 
@@ -224,6 +228,21 @@ __device__ __forceinline__ double occm_reaction_fast(const double (&coeffm)[OCCM
             if (nf_u > 2) v *= row[m >> 24];
             acc += v;
         }
+    }
+    return acc;
+}
+
+// the same evaluation with the species' term list in shared memory (mechanisms with more than OCCM_NT terms per species):
+// c = coefficients already scaled by the member's k_scale, mt = meta words, nt = mechanism-wide maximum (padded lists)
+__device__ __forceinline__ double occm_reaction_wide(const double* c, const unsigned* mt, const double* row, int nt, int nf_u) {
+    double acc = 0.0;
+    for (int i = 0; i < nt; ++i) {
+        const unsigned m = mt[i];
+        double v = c[i];
+        if (nf_u > 0) v *= row[(m >> 8) & 0xffu];
+        if (nf_u > 1) v *= row[(m >> 16) & 0xffu];
+        if (nf_u > 2) v *= row[m >> 24];
+        acc += v;
     }
     return acc;
 }

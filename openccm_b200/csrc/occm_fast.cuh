@@ -1,7 +1,10 @@
-// Fast path of the fused CSTR kernels (included by occm_solver.cu after the generic kernel).
+// Fast path of the fused stage kernels (included by occm_solver.cu after the generic kernel).
 //
-// Preconditions (checked on the host, otherwise the generic occm_stage kernel runs): CSTR network, even species
-// count S, mechanism in register form (fast_ok), ELL width K <= 4, ndof and all member offsets 16-byte aligned.
+// Preconditions (checked on the host, otherwise the generic occm_stage kernel runs): even species count S, mechanism
+// in register form (fast_ok: <= 4 terms per species; WIDE = 1 keeps longer term lists in shared memory instead), packed
+// ELL operator of width K <= 4, ndof and all member offsets 16-byte aligned.
+// CSTR networks: dy = qs * sum_k w_k y[src_k] + r(y).  PFR networks use the same kernel body with a one-entry row per
+// point, {src = upwind point, w = Q/dV}: dy = -(qs w)(y - y[src]) + r(y) (pfr_system.py:296); inlet nodes are flagged.
 //
 // Differences from the generic kernel:
 //   * one thread owns TWO adjacent species of a point: every own-element access is a 128-bit LDG/STG, every row
@@ -127,9 +130,9 @@ struct OccmFastPre {          // everything of a trip that can be loaded before 
 #ifndef OCCM_FAST_CTAS
 #define OCCM_FAST_CTAS 2
 #endif
-template <int STAGE, int K>
-__global__ void __launch_bounds__(OCCM_BLOCK, OCCM_FAST_CTAS)
-occm_fast_cstr(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmMemDev mem, const __grid_constant__ OccmRkDev rk,
+template <int MODEL, int STAGE, int K, int WIDE>
+__device__ __forceinline__ void
+occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk,
                const double* __restrict__ t_dev, double t_scalar, const double* __restrict__ y_in, double* __restrict__ dy_out,
                const OccmEllEntry* __restrict__ ell, int cpm, int tcv, int err_stride) {
     extern __shared__ double smem_d[];
@@ -137,14 +140,29 @@ occm_fast_cstr(const __grid_constant__ OccmSysDev sys, const __grid_constant__ O
     occm_load_tables(sys.tables, sys.tables_bytes, tab_s);
     const int S = sys.S, H = S >> 1, RS = S + 2;            // staged rows: S values + two 1.0 pads (keeps 16-byte alignment)
     double* tile = smem_d + (((sys.tables_bytes + 15) >> 4) << 1);   // [2][tcv][RS], 16-byte aligned
-    double* rxc_s = tile + 2 * tcv * RS;                    // unscaled coefficients [S][OCCM_NT]
+    double* rxc_s = tile + 2 * tcv * RS;                    // unscaled coefficients [S][OCCM_NT]  (WIDE: [S][nt_u])
     const int tid = threadIdx.x;
     const bool lane_on = tid < tcv * H;
     const int pl = tid / H;
     const int sp = 2 * (tid - pl * H);
     const int nt_u = tab_s[OCCM_H_MAX_TERMS], nf_u = tab_s[OCCM_H_MAX_SLOTS];
+    // WIDE: term lists of every species in shared memory, coefficients scaled per member in a double-buffered copy
+    const int NW = S * nt_u;
+    double* cmw_s = rxc_s + (WIDE ? NW : S * OCCM_NT);      // [2][NW]
+    unsigned* mtw_s = reinterpret_cast<unsigned*>(cmw_s + 2 * NW);
+    int cmw_m0 = -1, cmw_m1 = -1;
     unsigned meta0[OCCM_NT], meta1[OCCM_NT];
-    {
+    if (WIDE) {
+        const OccmTab T = occm_tab_views(tab_s);
+        for (int i = tid; i < NW; i += OCCM_BLOCK) {
+            const int s_ = i / nt_u;
+            double c; unsigned mt;
+            occm_rxn_term(T, s_, i - s_ * nt_u, S, c, mt);
+            rxc_s[i] = c; mtw_s[i] = mt;
+        }
+#pragma unroll
+        for (int q = 0; q < OCCM_NT; ++q) { meta0[q] = 0u; meta1[q] = 0u; }
+    } else {
         const OccmTab T = occm_tab_views(tab_s);
         const OccmRxnRegs R0 = occm_rxn_regs(T, lane_on ? sp : 0, S), R1 = occm_rxn_regs(T, lane_on ? sp + 1 : 0, S);
 #pragma unroll
@@ -154,7 +172,7 @@ occm_fast_cstr(const __grid_constant__ OccmSysDev sys, const __grid_constant__ O
         }
     }
     for (int r = tid; r < 2 * tcv; r += OCCM_BLOCK) { tile[r * RS + S] = 1.0; tile[r * RS + S + 1] = 1.0; }
-    const int n_points = (int)sys.n_points, N = sys.n_models;
+    const int n_points = (int)sys.n_points, N = n_points;     // ELL columns are [K][n_points] (CSTR: one point per model)
     const int my_tile = pl * RS + sp;
     __syncthreads();
 
@@ -200,6 +218,15 @@ occm_fast_cstr(const __grid_constant__ OccmSysDev sys, const __grid_constant__ O
         // epilogue operands of THIS trip: needed last, so they have the whole trip to arrive
         const OccmOps2 ops = occm_fast_load_ops<STAGE>(sys, rk, cc, (cur.pt >= 0 ? cur.pt : 0) * S + sp);
         if (lane_on) occm_st2(tb + my_tile, cur.own);
+        if (WIDE) {                                     // uniform: this buffer's coefficient copy belongs to another member
+            int& have = buf ? cmw_m1 : cmw_m0;
+            if (have != cc.m) {
+                double* dst = cmw_s + buf * NW;
+                for (int i = tid; i < NW; i += OCCM_BLOCK)
+                    dst[i] = rxc_s[i] * (mem.k_scale ? __ldg(mem.k_scale + (long long)cc.m * sys.n_rxn + (mtw_s[i] & 0xffu)) : 1.0);
+                have = cc.m;
+            }
+        }
         __syncthreads();
         // ---- row gathers (L2 hits), then the next trip's loads: both fly while the reactions are evaluated
         double2 g[K];
@@ -211,7 +238,7 @@ occm_fast_cstr(const __grid_constant__ OccmSysDev sys, const __grid_constant__ O
         }
         if (have_next) load(nxt, ncx);
 
-        if (coeff_m != cc.m) {                          // uniform: fold the member's rate-constant scales into the coefficients
+        if (!WIDE && coeff_m != cc.m) {                 // uniform: fold the member's rate-constant scales into the coefficients
 #pragma unroll
             for (int q = 0; q < OCCM_NT; ++q) {
                 const double k0 = mem.k_scale ? __ldg(mem.k_scale + (long long)cc.m * sys.n_rxn + (meta0[q] & 0xffu)) : 1.0;
@@ -224,12 +251,20 @@ occm_fast_cstr(const __grid_constant__ OccmSysDev sys, const __grid_constant__ O
         if (cur.pt >= 0) {
             const double* myrow = tb + pl * RS;
             if (!cur.ell[0].y) {
-                const double r0 = occm_reaction_fast(cm0, meta0, myrow, nt_u, nf_u);
-                const double r1 = occm_reaction_fast(cm1, meta1, myrow, nt_u, nf_u);
-                double2 acc = make_double2(0.0, 0.0);
+                const double r0 = WIDE ? occm_reaction_wide(cmw_s + buf * NW + sp * nt_u, mtw_s + sp * nt_u, myrow, nt_u, nf_u)
+                                       : occm_reaction_fast(cm0, meta0, myrow, nt_u, nf_u);
+                const double r1 = WIDE ? occm_reaction_wide(cmw_s + buf * NW + (sp + 1) * nt_u, mtw_s + (sp + 1) * nt_u, myrow, nt_u, nf_u)
+                                       : occm_reaction_fast(cm1, meta1, myrow, nt_u, nf_u);
+                double2 f;
+                if (MODEL == 0) {
+                    double2 acc = make_double2(0.0, 0.0);
 #pragma unroll
-                for (int k = 0; k < K; ++k) acc = occm_fma2(__hiloint2double(cur.ell[k].w, cur.ell[k].z), g[k], acc);
-                const double2 f = make_double2(cc.qs * acc.x + r0, cc.qs * acc.y + r1);
+                    for (int k = 0; k < K; ++k) acc = occm_fma2(__hiloint2double(cur.ell[k].w, cur.ell[k].z), g[k], acc);
+                    f = make_double2(cc.qs * acc.x + r0, cc.qs * acc.y + r1);
+                } else {                     // first-order upwind difference along the PFR
+                    const double na = -(cc.qs * __hiloint2double(cur.ell[0].w, cur.ell[0].z));
+                    f = make_double2(na * (cur.own.x - g[0].x) + r0, na * (cur.own.y - g[0].y) + r1);
+                }
                 err2 = occm_fast_finish<STAGE>(sys, rk, cc, ops, f, cur.own, cur.pt * S + sp, dy_out);
             }   // flagged rows (boundary / pulse / overflow entries) are left to occm_fixup, launched right after
         }
@@ -253,9 +288,26 @@ occm_fast_cstr(const __grid_constant__ OccmSysDev sys, const __grid_constant__ O
 }
 
 
-// Flagged points of the fast path: rows with boundary / pulse entries or more entries than the ELL width.  A few
-// dozen points per member; evaluated with the generic CSR / table walk, one thread per (flagged point, species).
-template <int STAGE>
+template <int STAGE, int K, int WIDE>
+__global__ void __launch_bounds__(OCCM_BLOCK, OCCM_FAST_CTAS)
+occm_fast_cstr(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmMemDev mem, const __grid_constant__ OccmRkDev rk,
+               const double* __restrict__ t_dev, double t_scalar, const double* __restrict__ y_in, double* __restrict__ dy_out,
+               const OccmEllEntry* __restrict__ ell, int cpm, int tcv, int err_stride) {
+    occm_fast_body<0, STAGE, K, WIDE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, ell, cpm, tcv, err_stride);
+}
+
+template <int STAGE, int WIDE>
+__global__ void __launch_bounds__(OCCM_BLOCK, OCCM_FAST_CTAS)
+occm_fast_pfr(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmMemDev mem, const __grid_constant__ OccmRkDev rk,
+              const double* __restrict__ t_dev, double t_scalar, const double* __restrict__ y_in, double* __restrict__ dy_out,
+              const OccmEllEntry* __restrict__ ell, int cpm, int tcv, int err_stride) {
+    occm_fast_body<1, STAGE, 1, WIDE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, ell, cpm, tcv, err_stride);
+}
+
+// Flagged points of the fast path: rows with boundary / pulse entries or more entries than the ELL width, PFR inlet
+// nodes.  Few points per member; evaluated with the generic CSR / table walk, one thread per (flagged point, species).
+// PFR: each flagged point stages [upwind row | own row] so that interior nodes (pulse sources) find their neighbour.
+template <int MODEL, int STAGE>
 __global__ void __launch_bounds__(OCCM_BLOCK)
 occm_fixup(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmMemDev mem, const __grid_constant__ OccmRkDev rk,
            const double* __restrict__ t_dev, double t_scalar, const double* __restrict__ y_in, double* __restrict__ dy_out,
@@ -284,12 +336,16 @@ occm_fixup(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmM
     in.a = STAGE <= 1 ? y_in + base : STAGE == 2 ? rk.Y[par] + base : STAGE == 3 || STAGE == 5 ? rk.YS[0] + base
          : STAGE == 4 || STAGE == 6 ? rk.YS[1] + base : rk.Y[par ^ 1] + base;
     in.b = STAGE == 1 ? mem.z + base : STAGE == 2 ? rk.KF[par] + base : nullptr; in.hb = h;
-    if (on) tile[pl * RS + s] = in(p * S + s);
+    const int row = MODEL == 1 ? 2 * pl + 1 : pl;
+    if (on) {
+        tile[row * RS + s] = in(p * S + s);
+        if (MODEL == 1) tile[(row - 1) * RS + s] = p > 0 ? in((p - 1) * S + s) : 0.0;
+    }
     __syncthreads();
     double err2 = 0.0;
     if (on) {
         const double* ksc = mem.k_scale ? mem.k_scale + (long long)m * sys.n_rxn : nullptr;
-        err2 = occm_cold_element<0, STAGE>(sys, mem, rk, tab_s, y_in, tile + pl * RS, p, s, t_stage, m, ksc, dy_out);
+        err2 = occm_cold_element<MODEL, STAGE>(sys, mem, rk, tab_s, y_in, tile + row * RS, p, s, t_stage, m, ksc, dy_out);
     }
     if (STAGE == 7) {
         const double sum = occm_block_sum(err2, scratch);

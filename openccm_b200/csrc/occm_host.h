@@ -10,6 +10,8 @@ struct occm_system {
     occm_system_desc desc;
     OccmSysDev dev;
     int sm_count;
+    int force_wide;       // OCCM_B200_FORCE_WIDE=1: fast kernels keep the term lists in shared memory even when they fit registers
+    int max_terms;        // most terms of any species (table header)
     int use_fast;         // 0: always run the generic kernels (OCCM_B200_NO_FAST=1, used by the tests to cover both)
     size_t smem_tables;   // bytes of the staged table blob (8-byte aligned)
 };

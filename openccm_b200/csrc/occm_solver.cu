@@ -74,13 +74,18 @@ extern "C" int occm_system_create(occm_system** out, const occm_system_desc* d) 
     v.n_rxn = hdr[OCCM_H_NRXN];
     v.tc = OCCM_BLOCK / d->n_species;
     v.chunks_per_member = (int)((n_points + (long long)OCCM_E * v.tc - 1) / ((long long)OCCM_E * v.tc));   // Dormand-Prince stage kernels (err_partial layout)
-    v.ell_k = d->model == OCCM_MODEL_CSTR ? d->ell_width : 0;
+    // PFR: the only ELL form is the packed one-entry row per point {upwind point, flag, Q/dV} of the fast kernels
+    v.ell_k = d->model == OCCM_MODEL_CSTR ? d->ell_width : (d->ell_packed && d->ell_width == 1 && d->point_flags ? 1 : 0);
     v.ell_src = d->ell_src; v.ell_w = d->ell_w;
     v.point_flags = d->point_flags;
     s->use_fast = getenv("OCCM_B200_NO_FAST") ? 0 : 1;
+    s->force_wide = getenv("OCCM_B200_FORCE_WIDE") ? 1 : 0;      // tests: run the shared-memory term-list variant on any mechanism
+    s->max_terms = hdr[OCCM_H_MAX_TERMS];
     v.fast_ok = hdr[OCCM_H_MAX_TERMS] <= OCCM_NT && hdr[OCCM_H_MAX_SLOTS] <= OCCM_NF && !hdr[OCCM_H_ANY_PROG] && hdr[OCCM_H_NRXN] <= 255;
-    if (d->model == OCCM_MODEL_CSTR && (v.ell_k == 0 || !d->point_flags)) v.fast_ok = 0;   // no ELL copy: CSR walk for every row
-    if (v.ell_k < 0 || v.ell_k > OCCM_KREG || (v.ell_k > 0 && (!d->ell_src || !d->ell_w))) { occm_set_error("bad ELL description"); free(s); return OCCM_ERR_INVALID; }
+    v.wide_ok = hdr[OCCM_H_MAX_TERMS] <= OCCM_WIDE_MAX_TERMS && hdr[OCCM_H_MAX_SLOTS] <= OCCM_NF && !hdr[OCCM_H_ANY_PROG] &&
+                hdr[OCCM_H_NRXN] <= 255 && d->n_species <= 254;
+    if (d->model == OCCM_MODEL_CSTR && (v.ell_k == 0 || !d->point_flags)) { v.fast_ok = 0; v.wide_ok = 0; }   // no ELL copy: CSR walk for every row
+    if (v.ell_k < 0 || v.ell_k > OCCM_KREG || (d->model == OCCM_MODEL_CSTR && v.ell_k > 0 && (!d->ell_src || !d->ell_w))) { occm_set_error("bad ELL description"); free(s); return OCCM_ERR_INVALID; }
     if (ndof >= (1ll << 31)) { occm_set_error("ndof per member must fit in int32"); free(s); return OCCM_ERR_INVALID; }
     s->smem_tables = (size_t)d->tables_bytes;
     int dev = 0;
@@ -609,14 +614,24 @@ static int occm_launch_stage_m(const occm_system* sys, const OccmMemDev& mem, co
     return OCCM_OK;
 }
 
-template <int STAGE, int K>
+typedef void (*occm_fast_fn)(const OccmSysDev, const OccmMemDev, const OccmRkDev, const double*, double, const double*, double*,
+                             const OccmEllEntry*, int, int, int);
+template <int MODEL, int STAGE, int K, int WIDE>
+static occm_fast_fn occm_fast_kernel() {
+    if constexpr (MODEL == 0) return occm_fast_cstr<STAGE, K, WIDE>;
+    else return occm_fast_pfr<STAGE, WIDE>;
+}
+
+template <int MODEL, int STAGE, int K, int WIDE>
 static int occm_launch_fast(const occm_system* sys, const OccmMemDev& mem, const OccmRkDev& rk, const double* t_dev,
                             double t_scalar, const double* y_in, double* dy_out, cudaStream_t st, int* cpm_out) {
     static size_t smem_limit = 48 * 1024;
     static int ctas_per_sm = 0;
     const int S = sys->dev.S, tcv = OCCM_BLOCK / (S / 2);
-    const size_t smem = (((size_t)sys->dev.tables_bytes + 15) & ~(size_t)15) + sizeof(double) * ((size_t)2 * tcv * (S + 2) + (size_t)S * OCCM_NT + 40);
-    auto kern = occm_fast_cstr<STAGE, K>;
+    const size_t nw = (size_t)S * sys->max_terms;          // WIDE: unscaled + two scaled coefficient copies + meta words
+    const size_t smem = (((size_t)sys->dev.tables_bytes + 15) & ~(size_t)15) +
+                        sizeof(double) * ((size_t)2 * tcv * (S + 2) + (WIDE ? 3 * nw + (nw + 1) / 2 : (size_t)S * OCCM_NT) + 40);
+    auto kern = occm_fast_kernel<MODEL, STAGE, K, WIDE>();
     if (smem > smem_limit) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_limit = smem; }
     if (ctas_per_sm == 0) {
         OCCM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, OCCM_BLOCK, smem));
@@ -634,10 +649,10 @@ static int occm_launch_fast(const occm_system* sys, const OccmMemDev& mem, const
     kern<<<grid, OCCM_BLOCK, smem, st>>>(sys->dev, mem, rk, t_dev, t_scalar, y_in, dy_out, (const OccmEllEntry*)sys->desc.ell_packed, cpm, tcv, err_stride);
     OCCM_LAUNCH_CHECK("occm_fast_cstr");
     if (nfix > 0) {
-        const size_t fsmem = (size_t)sys->dev.tables_bytes + sizeof(double) * ((size_t)tcf * (S + 1) + 8);
+        const size_t fsmem = (size_t)sys->dev.tables_bytes + sizeof(double) * ((size_t)(MODEL == 1 ? 2 : 1) * tcf * (S + 1) + 8);
         static size_t fix_limit = 48 * 1024;
-        if (fsmem > fix_limit) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(occm_fixup<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); fix_limit = fsmem; }
-        occm_fixup<STAGE><<<dim3(nfix, mem.M), OCCM_BLOCK, fsmem, st>>>(sys->dev, mem, rk, t_dev, t_scalar, y_in, dy_out, sys->desc.flagged_points,
+        if (fsmem > fix_limit) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(occm_fixup<MODEL, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); fix_limit = fsmem; }
+        occm_fixup<MODEL, STAGE><<<dim3(nfix, mem.M), OCCM_BLOCK, fsmem, st>>>(sys->dev, mem, rk, t_dev, t_scalar, y_in, dy_out, sys->desc.flagged_points,
                                                                           n_flagged, err_stride, cpm * nwarp);
         OCCM_LAUNCH_CHECK("occm_fixup");
     }
@@ -651,15 +666,26 @@ template <int STAGE>
 static int occm_launch_stage(const occm_system* sys, const OccmMemDev& mem, const OccmRkDev& rk, const double* t_dev,
                              double t_scalar, const double* y_in, double* dy_out, cudaStream_t st, int* cpm_out = nullptr) {
     const OccmSysDev& d = sys->dev;
-    const bool fast = sys->use_fast && d.model == OCCM_MODEL_CSTR && d.fast_ok && (d.S % 2 == 0) && sys->desc.ell_packed &&
+    const bool wide = !d.fast_ok || sys->force_wide;      // term lists in shared memory instead of registers
+    const bool fast = sys->use_fast && (d.fast_ok || d.wide_ok) && (d.S % 2 == 0) && sys->desc.ell_packed &&
                       (sys->desc.n_flagged == 0 || sys->desc.flagged_points) && mem.M <= 65535 && d.ell_k >= 1 &&
-                      d.ell_k <= 4 && occm_aligned16(y_in) && occm_aligned16(dy_out) && occm_aligned16(mem.z);
-    if (fast) {
+                      d.ell_k <= 4 && d.n_points * d.S < (1ll << 31) &&
+                      occm_aligned16(y_in) && occm_aligned16(dy_out) && occm_aligned16(mem.z);
+    if (fast && d.model == OCCM_MODEL_PFR && d.ell_k == 1 && sys->desc.n_flagged >= d.n_models)
+        return wide ? occm_launch_fast<1, STAGE, 1, 1>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out)
+                    : occm_launch_fast<1, STAGE, 1, 0>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
+    if (fast && d.model == OCCM_MODEL_CSTR) {
+        if (wide) switch (d.ell_k) {
+            case 1: return occm_launch_fast<0, STAGE, 1, 1>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
+            case 2: return occm_launch_fast<0, STAGE, 2, 1>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
+            case 3: return occm_launch_fast<0, STAGE, 3, 1>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
+            default: return occm_launch_fast<0, STAGE, 4, 1>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
+        }
         switch (d.ell_k) {
-            case 1: return occm_launch_fast<STAGE, 1>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
-            case 2: return occm_launch_fast<STAGE, 2>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
-            case 3: return occm_launch_fast<STAGE, 3>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
-            default: return occm_launch_fast<STAGE, 4>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
+            case 1: return occm_launch_fast<0, STAGE, 1, 0>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
+            case 2: return occm_launch_fast<0, STAGE, 2, 0>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
+            case 3: return occm_launch_fast<0, STAGE, 3, 0>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
+            default: return occm_launch_fast<0, STAGE, 4, 0>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
         }
     }
     if (cpm_out) *cpm_out = d.chunks_per_member;

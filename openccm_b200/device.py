@@ -125,6 +125,15 @@ class DeviceSystem:
             flags = np.zeros(host.n_points, dtype=np.uint8)
             if host.pulse_ptr is not None:       # every node of a PFR with a pulse source takes the generic path
                 flags[np.repeat(np.diff(host.pulse_ptr) > 0, host.P)] = 1
+            flags[::host.P] = 1                  # inlet nodes: differentiated algebraic coupling to other PFRs (pfr_system.py:313-314)
+            # one-entry row per point for the fast kernels: {upwind point, flag, Q/dV}
+            pts = np.arange(host.n_points, dtype=np.int64)
+            packed = np.zeros((1, host.n_points), dtype=np.dtype([('src', '<i4'), ('flag', '<i4'), ('w', '<f8')]))
+            packed['src'][0] = np.where(pts % host.P == 0, pts, pts - 1)
+            packed['w'][0] = np.repeat(np.asarray(host.a, dtype=np.float64), host.P)
+            packed['flag'][0] = flags
+            self.ell_k = 1
+            self.ell_packed = torch.as_tensor(packed.view(np.uint8).reshape(-1), device=self.dev)
         self.point_flags = torch.as_tensor(flags, device=self.dev)
         flagged = np.nonzero(flags)[0].astype(np.int32)
         self.flagged_points = torch.as_tensor(flagged if len(flagged) else np.zeros(1, np.int32), device=self.dev)

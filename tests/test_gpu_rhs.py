@@ -49,9 +49,10 @@ def test_rhs_batched_members_vs_oracle(name, tmp_path):
         np.testing.assert_allclose(host.to_reference_layout(out[m]), ref, rtol=1e-12, atol=1e-13 * max(1.0, np.abs(ref).max()))
 
 
-@pytest.mark.parametrize('name', ['cstr_net12_nacl', 'cstr_reversible', 'cstr_net20_timebc'])
+@pytest.mark.parametrize('name', ['cstr_net12_nacl', 'cstr_reversible', 'cstr_net20_timebc', 'pfr_single', 'pfr_net8', 'pfr_net8_nacl'])
 def test_generic_and_fast_kernels_agree(name, tmp_path, monkeypatch):
-    """The 128-bit fast CSTR kernels (even S) and the generic kernels give the same RHS and the same RK45 solution."""
+    """The 128-bit fast kernels (even S; CSTR rows and PFR upwind rows; term lists in registers or, forced here, in
+    shared memory) and the generic kernels give the same RHS and the same RK45 solution."""
     import torch
     from openccm_b200.device import DeviceSystem
     from openccm_b200.system_solvers.export import export_system
@@ -62,15 +63,59 @@ def test_generic_and_fast_kernels_agree(name, tmp_path, monkeypatch):
     y = torch.as_tensor(np.abs(rng.normal(0.5, 0.5, (M, host.ndof))), device='cuda')
     t = torch.as_tensor(rng.uniform(0, 2, M), device='cuda')
     outs, sols = [], []
-    for no_fast in ('', '1'):
-        if no_fast:
+    for mode in ('fast', 'generic', 'wide'):
+        monkeypatch.delenv('OCCM_B200_NO_FAST', raising=False)
+        monkeypatch.delenv('OCCM_B200_FORCE_WIDE', raising=False)
+        if mode == 'generic':
             monkeypatch.setenv('OCCM_B200_NO_FAST', '1')
-        else:
-            monkeypatch.delenv('OCCM_B200_NO_FAST', raising=False)
+        if mode == 'wide':
+            monkeypatch.setenv('OCCM_B200_FORCE_WIDE', '1')
         dev = DeviceSystem(host)
         outs.append(dev.rhs(y, t).cpu().numpy())
         res = dev.rk45(y, (0.0, 3.0), rtol=1e-8, atol=1e-10, first_step=1e-4, t_eval=np.linspace(0, 3, 7))
         assert np.all(res.status == 1)
         sols.append(res.y.cpu().numpy())
-    np.testing.assert_allclose(outs[0], outs[1], rtol=1e-13, atol=1e-14)
-    np.testing.assert_allclose(sols[0], sols[1], rtol=1e-9, atol=1e-12)
+    for k in (1, 2):
+        np.testing.assert_allclose(outs[0], outs[k], rtol=1e-13, atol=1e-14)
+        np.testing.assert_allclose(sols[0], sols[k], rtol=1e-9, atol=1e-12)
+    np.testing.assert_array_equal(outs[0], outs[2])          # registers vs shared memory: the same arithmetic, bit for bit
+
+
+@pytest.mark.parametrize('model', ['cstr', 'pfr'])
+def test_wide_mechanism_vs_oracle(model, tmp_path, monkeypatch):
+    """A mechanism with more terms per species than the register form holds (stiff C5 mechanism: 6) runs on the
+    shared-memory term-list kernels: RHS against the oracle, and against the generic table walk."""
+    import torch
+    from oracle import openccm_oracle as O
+    from openccm_b200 import synthetic as syn
+    from openccm_b200.device import DeviceSystem
+    from openccm_b200.system_solvers.export import export_system
+    from openccm_b200.workloads import _cmesh, _config, pfr_stiff_workload
+    if model == 'pfr':
+        _, net, cp, cmesh = pfr_stiff_workload(n_chains=3, chain_len=4, P=7, t_end=2.0, n_out=5, workdir=str(tmp_path))
+    else:
+        net = syn.random_network(40, n_io=3, seed=4)
+        species, rxn_text = syn.stiff_mechanism(12, 20, seed=0)
+        path = tmp_path / 'rxn_wide'
+        path.write_text(rxn_text)
+        cp = _config('cstr', species, str(path), t_span=(0, 2.0), t_eval='0.5, linear')
+        cmesh = _cmesh(cp, 40, 9)
+    mn = net.to_model_network()
+    host = export_system(model, mn, cp, cmesh)
+    n_terms = np.bincount([tm.specie for tm in host.tables.terms], minlength=host.S)
+    assert n_terms.max() > 4
+    ora = O.build_system(model, mn, cp, cmesh)
+    rng = np.random.default_rng(2)
+    M = 3
+    ys = np.abs(rng.normal(0.5, 0.3, (M, host.ndof)))
+    yd = torch.as_tensor(host.to_device_layout(ys), device='cuda')
+    ts = torch.zeros(M, dtype=torch.float64, device='cuda')
+    monkeypatch.delenv('OCCM_B200_NO_FAST', raising=False)
+    fast = DeviceSystem(host).rhs(yd, ts).cpu().numpy()
+    monkeypatch.setenv('OCCM_B200_NO_FAST', '1')
+    generic = DeviceSystem(host).rhs(yd, ts).cpu().numpy()
+    for m in range(M):
+        ref = ora.fun(0.0, ys[m].copy())
+        scale = max(1.0, np.abs(ref).max())
+        np.testing.assert_allclose(host.to_reference_layout(fast[m]), ref, rtol=1e-11, atol=1e-12 * scale)
+        np.testing.assert_allclose(host.to_reference_layout(generic[m]), ref, rtol=1e-11, atol=1e-12 * scale)

@@ -194,7 +194,7 @@ typedef struct {
     int64_t max_steps;        /* accepted + rejected attempts per member, 0 = unlimited */
     const double* tdiag;      /* device [n_models]: transport diagonal (CSTR: Q_div_v[j,j]; PFR: -Q_pfr/dV) for the preconditioner */
     int32_t gmres_restart;    /* Krylov dimension per Newton solve (0 = 30) */
-    double lin_tol_factor;    /* GMRES stops at |r|_rms <= factor * newton_tol in error-weight scaling (0 = 0.01) */
+    double lin_tol_factor;    /* GMRES stops at |r|_rms <= factor * newton_tol in error-weight scaling (0 = 0.05) */
     int32_t precond_mode;     /* 0: block inverses kept in the workspace (ndof * n_species doubles per member) and rebuilt only when
                                  c = h/alpha moved by > 20 %, after 20 attempts or after a slow / failed Newton solve;
                                  1: blocks rebuilt and solved on every application, nothing stored */

@@ -1,39 +1,72 @@
-"""Builds liboccm_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the source tree)."""
+"""Builds liboccm_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the source tree).
+
+Objects are compiled in parallel and cached under csrc/_obj/ (git-ignored).  occm_solver.cu is compiled nine times: once
+for the host API and controller kernels and once per Dormand-Prince / RHS stage (-DOCCM_STAGE_TU=k), because every stage
+instantiates a dozen fused kernels and they dominate the compile time."""
 from __future__ import annotations
 
 import glob
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
+OBJ = os.path.join(CSRC, '_obj')
 LIB = os.path.join(CSRC, 'liboccm_b200.so')
-NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '--threads', '0',
-              '-shared', '-Xcompiler', '-fPIC', '--use_fast_math=false']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC']
+N_STAGES = 8
 
 
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, '*.cu')))
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB):
+def _headers():
+    return glob.glob(os.path.join(CSRC, '*.h')) + glob.glob(os.path.join(CSRC, '*.cuh')) + \
+        [os.path.join(os.path.dirname(HERE), 'include', 'occm_b200.h'), os.path.abspath(__file__)]
+
+
+def _units():
+    """(object path, source, extra flags) of every translation unit."""
+    units = []
+    for src in sources():
+        stem = os.path.splitext(os.path.basename(src))[0]
+        units.append((os.path.join(OBJ, stem + '.o'), src, []))
+        if stem == 'occm_solver':
+            units += [(os.path.join(OBJ, f'{stem}_stage{k}.o'), src, [f'-DOCCM_STAGE_TU={k}']) for k in range(N_STAGES)]
+    return units
+
+
+def _newer(target: str, deps) -> bool:
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, '*.h')) + glob.glob(os.path.join(CSRC, '*.cuh')) + \
-        [os.path.join(os.path.dirname(HERE), 'include', 'occm_b200.h')]
+    t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
-        return LIB
     nvcc = os.environ.get('NVCC', 'nvcc')
-    flags = [f for f in NVCC_FLAGS if not f.startswith('--use_fast_math')]
-    cmd = [nvcc, *flags, *(['-Xptxas', '-v'] if verbose else []), '-o', LIB, *sources()]
-    print('[build]', ' '.join(cmd), file=sys.stderr)
-    subprocess.run(cmd, check=True)
+    os.makedirs(OBJ, exist_ok=True)
+    hdrs = _headers()
+    units = _units()
+    todo = [u for u in units if force or _newer(u[0], [u[1]] + hdrs)]
+
+    def compile_one(u):
+        obj, src, extra = u
+        cmd = [nvcc, *NVCC_FLAGS, *extra, *(['-Xptxas', '-v'] if verbose else []), '-c', '-o', obj, src]
+        print('[build]', ' '.join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
+
+    if todo:
+        with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 4)) as pool:
+            list(pool.map(compile_one, todo))
+    objs = [u[0] for u in units]
+    if todo or _newer(LIB, objs):
+        cmd = [nvcc, '-arch=sm_100a', '-shared', '-o', LIB, *objs]
+        print('[build]', ' '.join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
     return LIB
 
 

@@ -49,6 +49,7 @@ struct OccmBdfDev {
     // stored block inverses (precond_mode 0): Binv[m][point][j][i] = (B_point^-1)(i, j)
     int store;
     double* Binv; double* c_fact; int* need_factor; int* since_factor; int* force_factor; long long* n_factor;
+    int* reorth; double* wn2;                // second Gram-Schmidt pass wanted (DGKS test); |w|^2 before orthogonalisation
 };
 
 struct occm_bdf {
@@ -96,14 +97,18 @@ __device__ void bdf_set_change(const OccmBdfDev& b, int m, int order, double fac
 }
 
 // ------------------------------------------------------------------------------------------------ reductions
-__global__ void __launch_bounds__(128) bdf_reduce(const double* __restrict__ partial, int nchunk, int nvals, double* __restrict__ out,
+// partial sums are stored [member][slot][chunk]: one slot is a contiguous run over the chunks
+#define BDF_PIDX(b, m, ci, k) ((((long long)(m) * BDF_MAXDOT + (k)) * (b).nchunk) + (ci))
+
+__global__ void __launch_bounds__(512) bdf_reduce(const double* __restrict__ partial, int nchunk, int nvals, double* __restrict__ out,
                                                   const int* __restrict__ mask) {
-    __shared__ double scratch[8];
+    __shared__ double scratch[16];
     const int m = blockIdx.x;
     if (mask && !mask[m]) return;
     for (int k = 0; k < nvals; ++k) {
+        const double* p = partial + ((long long)m * BDF_MAXDOT + k) * nchunk;
         double v = 0.0;
-        for (int i = threadIdx.x; i < nchunk; i += blockDim.x) v += partial[((long long)m * nchunk + i) * BDF_MAXDOT + k];
+        for (int i = threadIdx.x; i < nchunk; i += blockDim.x) v += p[i];
         const double s = occm_block_sum(v, scratch);
         if (threadIdx.x == 0) out[(long long)m * BDF_MAXDOT + k] = s;
     }
@@ -169,7 +174,7 @@ __global__ void __launch_bounds__(256) bdf_newton_rhs(const OccmBdfDev b) {
             s0 += r * r; s1 += y * y;
         }
         const double t0 = occm_block_sum(s0, scratch), t1 = occm_block_sum(s1, scratch);
-        if (threadIdx.x == 0) { double* p = b.partial + (cc * BDF_MAXDOT); p[0] = t0; p[1] = t1; }
+        if (threadIdx.x == 0) { b.partial[BDF_PIDX(b, m, ci, 0)] = t0; b.partial[BDF_PIDX(b, m, ci, 1)] = t1; }
     }
 }
 
@@ -451,18 +456,18 @@ __global__ void __launch_bounds__(256) bdf_norm2(const OccmBdfDev b, const doubl
         double s0 = 0.0;
         BDF_ELEMS(b, ci, e) { const double x = v[(long long)m * b.ndof + e]; s0 += x * x; }
         const double t0 = occm_block_sum(s0, scratch);
-        if (threadIdx.x == 0) b.partial[cc * BDF_MAXDOT + 0] = t0;
+        if (threadIdx.x == 0) b.partial[BDF_PIDX(b, m, ci, 0)] = t0;
     }
 }
 
-// w~ = (z - c (f2 - f) / eps) / scale -> V[j+1];  partial[i] = <w~, V[i]>, i = 0..j
+// w~ = (z - c (f2 - f) / eps) / scale -> V[j+1];  partial[i] = <w~, V[i]>, i = 0..j;  partial[j+1] = |w~|^2
 __global__ void __launch_bounds__(256) bdf_arnoldi_w(const OccmBdfDev b) {
     __shared__ double scratch[8];
     BDF_FOR_CHUNKS(b, b.gmres_active[m]) {
         const int j = b.gmres_j[m];
         const double c = b.c[m], inv_eps = 1.0 / b.eps[m];
         double dots[BDF_MAXDOT];
-        for (int i = 0; i <= j; ++i) dots[i] = 0.0;
+        for (int i = 0; i <= j + 1; ++i) dots[i] = 0.0;
         BDF_ELEMS(b, ci, e) {
             const long long g = (long long)m * b.ndof + e;
             const double y = b.y[g], d = b.d[g];
@@ -470,10 +475,11 @@ __global__ void __launch_bounds__(256) bdf_arnoldi_w(const OccmBdfDev b) {
             const double w = (b.z[g] - c * ((b.f2[g] - b.f[g]) * inv_eps)) / scale;
             b.V[(long long)(j + 1) * b.vstride + g] = w;
             for (int i = 0; i <= j; ++i) dots[i] += w * b.V[(long long)i * b.vstride + g];
+            dots[j + 1] += w * w;
         }
-        for (int i = 0; i <= j; ++i) {
+        for (int i = 0; i <= j + 1; ++i) {
             const double tsum = occm_block_sum(dots[i], scratch);
-            if (threadIdx.x == 0) b.partial[cc * BDF_MAXDOT + i] = tsum;
+            if (threadIdx.x == 0) b.partial[BDF_PIDX(b, m, ci, i)] = tsum;
         }
     }
 }
@@ -481,7 +487,7 @@ __global__ void __launch_bounds__(256) bdf_arnoldi_w(const OccmBdfDev b) {
 // V[j+1] -= sum_i h_i V[i]  (h_i = norms[m][i]);  partial[0] = |V[j+1]|^2, partial[1 + i] = <V[j+1], V[i]> (re-orthogonalisation)
 __global__ void __launch_bounds__(256) bdf_orth(const OccmBdfDev b, int second_pass) {
     __shared__ double scratch[8];
-    BDF_FOR_CHUNKS(b, b.gmres_active[m]) {
+    BDF_FOR_CHUNKS(b, b.gmres_active[m] && (!second_pass || b.reorth[m])) {
         const int j = b.gmres_j[m];
         const double* h = b.norms + (long long)m * BDF_MAXDOT + (second_pass ? 1 : 0);
         double s0 = 0.0;
@@ -496,11 +502,11 @@ __global__ void __launch_bounds__(256) bdf_orth(const OccmBdfDev b, int second_p
             if (!second_pass) for (int i = 0; i <= j; ++i) dots[i] += w * b.V[(long long)i * b.vstride + g];
         }
         const double t0 = occm_block_sum(s0, scratch);
-        if (threadIdx.x == 0) b.partial[cc * BDF_MAXDOT + 0] = t0;
+        if (threadIdx.x == 0) b.partial[BDF_PIDX(b, m, ci, 0)] = t0;
         if (!second_pass)
             for (int i = 0; i <= j; ++i) {
                 const double tsum = occm_block_sum(dots[i], scratch);
-                if (threadIdx.x == 0) b.partial[cc * BDF_MAXDOT + 1 + i] = tsum;
+                if (threadIdx.x == 0) b.partial[BDF_PIDX(b, m, ci, 1 + i)] = tsum;
             }
     }
 }
@@ -535,7 +541,7 @@ __global__ void __launch_bounds__(256) bdf_newton_update(const OccmBdfDev b) {
             b.y[g] = y + dy; b.d[g] = d + dy;
         }
         const double t0 = occm_block_sum(s0, scratch);
-        if (threadIdx.x == 0) b.partial[cc * BDF_MAXDOT + 0] = t0;
+        if (threadIdx.x == 0) b.partial[BDF_PIDX(b, m, ci, 0)] = t0;
     }
 }
 
@@ -551,7 +557,7 @@ __global__ void __launch_bounds__(256) bdf_error(const OccmBdfDev b) {
             s0 += q * q;
         }
         const double t0 = occm_block_sum(s0, scratch);
-        if (threadIdx.x == 0) b.partial[cc * BDF_MAXDOT + 0] = t0;
+        if (threadIdx.x == 0) b.partial[BDF_PIDX(b, m, ci, 0)] = t0;
     }
 }
 
@@ -577,7 +583,7 @@ __global__ void __launch_bounds__(256) bdf_update_D(const OccmBdfDev b) {
             s0 += qm * qm; s1 += qp * qp;
         }
         const double t0 = occm_block_sum(s0, scratch), t1 = occm_block_sum(s1, scratch);
-        if (threadIdx.x == 0) { b.partial[cc * BDF_MAXDOT + 0] = t0; b.partial[cc * BDF_MAXDOT + 1] = t1; }
+        if (threadIdx.x == 0) { b.partial[BDF_PIDX(b, m, ci, 0)] = t0; b.partial[BDF_PIDX(b, m, ci, 1)] = t1; }
     }
 }
 
@@ -726,14 +732,20 @@ __global__ void bdf_ctrl_h1(const OccmBdfDev b) {
     double* nr = b.norms + (long long)m * BDF_MAXDOT;
     double* Hc = b.H + ((long long)m * BDF_MAXDOT + j) * BDF_MAXDOT;       // column j of the Hessenberg matrix
     for (int i = 0; i <= j; ++i) Hc[i] = nr[i];
+    b.wn2[m] = nr[j + 1];
 }
 
-// second pass: norms[0] = |w|^2 after pass 1, norms[1..j+1] = correction coefficients; accumulate into H
+// second pass: norms[0] = |w|^2 after pass 1, norms[1..j+1] = correction coefficients; accumulate into H.
+// The pass is only made when the first one cancelled more than half of |w|^2 (Daniel-Gragg-Kaufman-Stewart test).
 __global__ void bdf_ctrl_h2(const OccmBdfDev b) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= b.M || !b.gmres_active[m]) return;
+    if (m >= b.M) return;
+    b.reorth[m] = 0;
+    if (!b.gmres_active[m]) return;
     const int j = b.gmres_j[m];
     const double* nr = b.norms + (long long)m * BDF_MAXDOT;
+    if (!(nr[0] < 0.5 * b.wn2[m])) return;
+    b.reorth[m] = 1;
     double* Hc = b.H + ((long long)m * BDF_MAXDOT + j) * BDF_MAXDOT;
     for (int i = 0; i <= j; ++i) Hc[i] += nr[1 + i];
 }
@@ -948,6 +960,7 @@ static size_t bdf_carve(const occm_system* sys, int M, int restart, int store, O
     b.counters = (int*)take(256);
     b.c_fact = (double*)take(md); b.need_factor = (int*)take(mi); b.since_factor = (int*)take(mi); b.force_factor = (int*)take(mi);
     b.n_factor = (long long*)take(md);
+    b.reorth = (int*)take(mi); b.wn2 = (double*)take(md);
     b.Binv = store ? (double*)take((size_t)M * sys->dev.ndof * sys->dev.S * sizeof(double)) : nullptr;
     b.nchunk = nchunk;
     return o;
@@ -972,7 +985,7 @@ static int bdf_grid(const occm_system* sys, long long chunks) {
     } while (0)
 
 static int bdf_reduce_launch(occm_bdf* h, int nvals, const int* mask, cudaStream_t st) {
-    BDF_LAUNCH(bdf_reduce, h->M, 128, 0, h->d.partial, h->d.nchunk, nvals, h->d.norms, mask);
+    BDF_LAUNCH(bdf_reduce, h->M, 512, 0, h->d.partial, h->d.nchunk, nvals, h->d.norms, mask);
     return OCCM_OK;
 }
 
@@ -1091,7 +1104,7 @@ extern "C" int occm_bdf_init(occm_bdf** out, const occm_system* sys, const occm_
     b.rtol = p->rtol; b.atol = p->atol; b.t_bound = p->t_bound; b.max_steps = p->max_steps;
     const double EPS = 2.220446049250313e-16;
     b.newton_tol = fmax(10.0 * EPS / p->rtol, fmin(0.03, sqrt(p->rtol)));       // bdf.py:224
-    b.lin_tol = (p->lin_tol_factor > 0.0 ? p->lin_tol_factor : 0.01) * b.newton_tol;
+    b.lin_tol = (p->lin_tol_factor > 0.0 ? p->lin_tol_factor : 0.05) * b.newton_tol;   // CVODE's eps_lin
     b.tdiag = p->tdiag; b.q_scale = h->mem.q_scale; b.k_scale = h->mem.k_scale;
     if (cudaHostAlloc((void**)&h->h_counters, 4 * sizeof(int), cudaHostAllocDefault) != cudaSuccess) { occm_set_error("cudaHostAlloc failed"); free(h); return OCCM_ERR_CUDA; }
     const int gm = (M + 63) / 64;
@@ -1138,13 +1151,13 @@ static int bdf_attempt(occm_bdf* h, cudaStream_t st) {
             BDF_LAUNCH(bdf_ctrl_eps, gm, 64, 0, b);
             if ((rc = bdf_rhs(h, b.gmres_active, b.z, b.eps, b.f2, st))) return rc;             // f(y + eps z)
             BDF_LAUNCH(bdf_arnoldi_w, gv, 256, 0, b);
-            if ((rc = bdf_reduce_launch(h, j + 1, b.gmres_active, st))) return rc;
+            if ((rc = bdf_reduce_launch(h, j + 2, b.gmres_active, st))) return rc;
             BDF_LAUNCH(bdf_ctrl_h1, gm, 64, 0, b);
             BDF_LAUNCH(bdf_orth, gv, 256, 0, b, 0);
             if ((rc = bdf_reduce_launch(h, j + 2, b.gmres_active, st))) return rc;
             BDF_LAUNCH(bdf_ctrl_h2, gm, 64, 0, b);
-            BDF_LAUNCH(bdf_orth, gv, 256, 0, b, 1);                                             // re-orthogonalisation (CGS2)
-            if ((rc = bdf_reduce_launch(h, 1, b.gmres_active, st))) return rc;
+            BDF_LAUNCH(bdf_orth, gv, 256, 0, b, 1);                                             // re-orthogonalisation where needed
+            if ((rc = bdf_reduce_launch(h, 1, b.reorth, st))) return rc;
             OCCM_CUDA_CHECK(cudaMemsetAsync(b.counters + 2, 0, sizeof(int), st));
             // scale_col must see the pre-update gmres_j: run it with the members that stay active AFTER givens
             BDF_LAUNCH(bdf_ctrl_givens, gm, 64, 0, b);

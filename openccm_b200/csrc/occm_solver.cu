@@ -27,6 +27,7 @@
 #endif
 #define OCCM_EMAX (OCCM_E > OCCM_E0 ? OCCM_E : OCCM_E0)
 
+#ifndef OCCM_STAGE_TU
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[1024] = "";
 static std::atomic<long long> g_launches{0};
@@ -104,6 +105,8 @@ extern "C" int occm_system_create(occm_system** out, const occm_system_desc* d) 
 
 extern "C" int occm_system_destroy(occm_system* s) { free(s); return OCCM_OK; }
 extern "C" int64_t occm_system_ndof(const occm_system* s) { return s ? s->dev.ndof : -1; }
+
+#endif  // !OCCM_STAGE_TU
 
 // ------------------------------------------------------------------------------------------------ RK45 data
 // Dormand-Prince coefficients exactly as scipy builds them (scipy/integrate/_ivp/rk.py:280-320, Python float
@@ -414,6 +417,7 @@ occm_stage(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmM
 
 #include "occm_fast.cuh"
 
+#ifndef OCCM_STAGE_TU
 // ------------------------------------------------------------------------------------------------ controller
 // np.nextafter(t, +inf) for t >= 0 (the reference asserts t0 >= 0, helper_functions.py:82)
 __device__ __forceinline__ double occm_next_up(double t) { return __longlong_as_double(__double_as_longlong(t) + 1ll); }
@@ -590,6 +594,8 @@ __global__ void occm_rk45_write_initial(const double* __restrict__ y0, int M, lo
     }
 }
 
+#endif  // !OCCM_STAGE_TU
+
 // ------------------------------------------------------------------------------------------------ launch helpers
 template <int MODEL, int STAGE>
 static int occm_launch_stage_m(const occm_system* sys, const OccmMemDev& mem, const OccmRkDev& rk, const double* t_dev,
@@ -662,9 +668,11 @@ static int occm_launch_fast(const occm_system* sys, const OccmMemDev& mem, const
 
 static inline bool occm_aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
+// Every STAGE pulls in ~12 kernel instantiations; the build compiles this file once per stage with -DOCCM_STAGE_TU=<stage>
+// (explicit instantiation below) in parallel, and once without it for everything else (extern template).
 template <int STAGE>
-static int occm_launch_stage(const occm_system* sys, const OccmMemDev& mem, const OccmRkDev& rk, const double* t_dev,
-                             double t_scalar, const double* y_in, double* dy_out, cudaStream_t st, int* cpm_out = nullptr) {
+int occm_launch_stage(const occm_system* sys, const OccmMemDev& mem, const OccmRkDev& rk, const double* t_dev,
+                      double t_scalar, const double* y_in, double* dy_out, cudaStream_t st, int* cpm_out = nullptr) {
     const OccmSysDev& d = sys->dev;
     const bool wide = !d.fast_ok || sys->force_wide;      // term lists in shared memory instead of registers
     const bool fast = sys->use_fast && (d.fast_ok || d.wide_ok) && (d.S % 2 == 0) && sys->desc.ell_packed &&
@@ -692,6 +700,14 @@ static int occm_launch_stage(const occm_system* sys, const OccmMemDev& mem, cons
     return d.model == OCCM_MODEL_CSTR ? occm_launch_stage_m<0, STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st)
                                       : occm_launch_stage_m<1, STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st);
 }
+
+#define OCCM_STAGE_SIG(N) int occm_launch_stage<N>(const occm_system*, const OccmMemDev&, const OccmRkDev&, const double*, double, \
+                                                   const double*, double*, cudaStream_t, int*)
+#ifdef OCCM_STAGE_TU
+template OCCM_STAGE_SIG(OCCM_STAGE_TU);
+#else
+extern template OCCM_STAGE_SIG(0); extern template OCCM_STAGE_SIG(1); extern template OCCM_STAGE_SIG(2); extern template OCCM_STAGE_SIG(3);
+extern template OCCM_STAGE_SIG(4); extern template OCCM_STAGE_SIG(5); extern template OCCM_STAGE_SIG(6); extern template OCCM_STAGE_SIG(7);
 
 // used by occm_bdf.cu
 int occm_launch_rhs(const occm_system* sys, const OccmMemDev& mem, const double* t_dev, double t_scalar, const double* y,
@@ -951,3 +967,5 @@ extern "C" int occm_rk45_free(occm_rk45* rk) {
     free(rk);
     return OCCM_OK;
 }
+
+#endif  // !OCCM_STAGE_TU

@@ -21,7 +21,7 @@ y0 = torch.as_tensor(host.to_device_layout(host.c0.reshape(-1)), device='cuda')[
 te = np.linspace(0, t_end, 41)
 save = torch.arange(0, host.ndof, max(1, host.ndof // 1000), dtype=torch.int32, device='cuda')
 torch.cuda.synchronize(); t1 = time.time()
-res = solve_bdf(dev, y0, (0.0, t_end), rtol=1e-6, atol=1e-10, first_step=1e-4, t_eval=te, save_idx=save, max_steps=int(os.environ.get('MAXSTEPS', '0')))   # OCCM_B200_BDF_PRECOND=1: on-the-fly blocks
+res = solve_bdf(dev, y0, (0.0, t_end), rtol=1e-6, atol=1e-10, first_step=1e-4, t_eval=te, save_idx=save, max_steps=int(os.environ.get('MAXSTEPS', '0')), lin_tol_factor=float(os.environ.get('LINTOL', '0')))   # OCCM_B200_BDF_PRECOND=1: on-the-fly blocks
 torch.cuda.synchronize(); dt = time.time() - t1
 print(f'BDF M={M}: {dt:.2f}s status {res.status} acc {res.n_accepted} rej {res.n_rejected} nfev {res.nfev} gmres its {res.n_gmres} newton fails {res.n_newton_fail}')
 print(f'  preconditioner applications {res.n_precond_apply} rebuilds {res.n_precond_factor}')

@@ -160,17 +160,17 @@ __device__ __forceinline__ double occm_reaction_tables(const OccmTab& T, int s, 
     double acc = 0.0;
     const int tb = T.term_ptr[s], te = T.term_ptr[s + 1];
     for (int k = tb; k < te; ++k) {
-        double v = T.term_coeff[k];
-        if (ksc) v *= ksc[T.term_rxn[k]];
+        double v = T.term_coeff[k];            // explicit roundings (no FMA contraction): same bits as the register / shared-list forms
+        if (ksc) v = __dmul_rn(v, ksc[T.term_rxn[k]]);
         const int fb = T.fac_ptr[k], fe = T.fac_ptr[k + 1];
         for (int f = fb; f < fe; ++f) {
             const double x = row(T.fac_sp[f]);
             const int ord = T.fac_ord[f];
-            for (int q = 0; q < ord; ++q) v *= x;
+            for (int q = 0; q < ord; ++q) v = __dmul_rn(v, x);
         }
         const int prog = T.term_prog[k];
-        if (prog >= 0) v *= occm_vm_eval(T, prog, row, t, (long long)point, sys.fields, sys.n_points);
-        acc += v;
+        if (prog >= 0) v = __dmul_rn(v, occm_vm_eval(T, prog, row, t, (long long)point, sys.fields, sys.n_points));
+        acc = __dadd_rn(acc, v);
     }
     return acc;
 }
@@ -223,10 +223,10 @@ __device__ __forceinline__ double occm_reaction_fast(const double (&coeffm)[OCCM
         if (i < nt_u) {                              // uniform bound: no divergence
             const unsigned m = meta[i];
             double v = coeffm[i];
-            if (nf_u > 0) v *= row[(m >> 8) & 0xffu];
-            if (nf_u > 1) v *= row[(m >> 16) & 0xffu];
-            if (nf_u > 2) v *= row[m >> 24];
-            acc += v;
+            if (nf_u > 0) v = __dmul_rn(v, row[(m >> 8) & 0xffu]);
+            if (nf_u > 1) v = __dmul_rn(v, row[(m >> 16) & 0xffu]);
+            if (nf_u > 2) v = __dmul_rn(v, row[m >> 24]);
+            acc = __dadd_rn(acc, v);
         }
     }
     return acc;
@@ -239,10 +239,10 @@ __device__ __forceinline__ double occm_reaction_wide(const double* c, const unsi
     for (int i = 0; i < nt; ++i) {
         const unsigned m = mt[i];
         double v = c[i];
-        if (nf_u > 0) v *= row[(m >> 8) & 0xffu];
-        if (nf_u > 1) v *= row[(m >> 16) & 0xffu];
-        if (nf_u > 2) v *= row[m >> 24];
-        acc += v;
+        if (nf_u > 0) v = __dmul_rn(v, row[(m >> 8) & 0xffu]);
+        if (nf_u > 1) v = __dmul_rn(v, row[(m >> 16) & 0xffu]);
+        if (nf_u > 2) v = __dmul_rn(v, row[m >> 24]);
+        acc = __dadd_rn(acc, v);
     }
     return acc;
 }
@@ -279,14 +279,14 @@ __device__ __noinline__ double occm_point_generic(const OccmSysDev& sys, const i
             if (src >= 0) acc += w * (src == p ? myrow[s] : in(src * S + s));
             else          acc += w * (bs * occm_bc_value(T, -1 - src, s, t));
         }
-        return qs * acc + occm_pulses(sys, T, p, s, t) + occm_reaction_tables(T, s, row, ksc, t, p, sys);
+        return __dadd_rn(__dadd_rn(__dmul_rn(qs, acc), occm_pulses(sys, T, p, s, t)), occm_reaction_tables(T, s, row, ksc, t, p, sys));
     } else {
         const int P = sys.P;
         const int k = p / P;
         const int node = p - k * P;
         if (node > 0) {
-            const double conv = -(qs * __ldg(sys.a + k)) * (myrow[s] - prevrow[s]);
-            return conv + occm_pulses(sys, T, k, s, t) + occm_reaction_tables(T, s, row, ksc, t, p, sys);
+            const double conv = __dmul_rn(-(qs * __ldg(sys.a + k)), myrow[s] - prevrow[s]);
+            return __dadd_rn(__dadd_rn(conv, occm_pulses(sys, T, k, s, t)), occm_reaction_tables(T, s, row, ksc, t, p, sys));
         }
         double acc = 0.0;
         const int eb = __ldg(sys.row_ptr + k), ee = __ldg(sys.row_ptr + k + 1);

@@ -122,6 +122,46 @@ __device__ __forceinline__ double occm_fast_finish(const OccmSysDev& sys, const 
     return e0 + e1;
 }
 
+// ---- shared memory through explicit 32-bit state-space addresses.  With generic pointers the compiler rebuilt the shared
+// window base (S2UR CgaCtaId, ULEA, the table-size arithmetic ...) in front of every LDS of the reaction terms: ~10 extra
+// issue slots per term (ncu source page, r01e).  An opaque 32-bit address costs one register and one add per access.
+__device__ __forceinline__ unsigned occm_opaque_u32(unsigned v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ double occm_lds_f64(unsigned sa) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sa)); return v; }
+__device__ __forceinline__ unsigned occm_lds_u32(unsigned sa) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa)); return v; }
+__device__ __forceinline__ void occm_sts2(unsigned sa, double2 v) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(sa), "d"(v.x), "d"(v.y) : "memory"); }
+
+// Reaction rate of one species from its register-resident term list, straight-line: NTc terms x NFc factor slots are always
+// evaluated (padding terms have coefficient 0, padding slots read the 1.0 column), which gives the same bits as stopping at
+// the mechanism's own maxima and removes every uniform branch from the hot loop.  row_sa = shared address of the point's row.
+template <int NTc, int NFc>
+__device__ __forceinline__ double occm_reaction_sa(const double (&cm)[OCCM_NT], const unsigned (&meta)[OCCM_NT], unsigned row_sa) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < NTc; ++i) {
+        const unsigned m = meta[i];
+        double v = cm[i];                      // explicit roundings: every variant (registers, shared lists, table walk) gives the same bits
+        v = __dmul_rn(v, occm_lds_f64(row_sa + ((m >> 5) & 0x7f8u)));
+        if (NFc > 1) v = __dmul_rn(v, occm_lds_f64(row_sa + ((m >> 13) & 0x7f8u)));
+        if (NFc > 2) v = __dmul_rn(v, occm_lds_f64(row_sa + ((m >> 21) & 0x7f8u)));
+        acc = __dadd_rn(acc, v);
+    }
+    return acc;
+}
+// term list in shared memory (WIDE): c_sa / mt_sa = shared addresses of the species' scaled coefficients and meta words
+template <int NFc>
+__device__ __forceinline__ double occm_reaction_wide_sa(unsigned c_sa, unsigned mt_sa, unsigned row_sa, int nt) {
+    double acc = 0.0;
+    for (int i = 0; i < nt; ++i) {
+        const unsigned m = occm_lds_u32(mt_sa + 4u * i);
+        double v = occm_lds_f64(c_sa + 8u * i);
+        v = __dmul_rn(v, occm_lds_f64(row_sa + ((m >> 5) & 0x7f8u)));
+        if (NFc > 1) v = __dmul_rn(v, occm_lds_f64(row_sa + ((m >> 13) & 0x7f8u)));
+        if (NFc > 2) v = __dmul_rn(v, occm_lds_f64(row_sa + ((m >> 21) & 0x7f8u)));
+        acc = __dadd_rn(acc, v);
+    }
+    return acc;
+}
+
 template <int STAGE, int K>
 struct OccmFastPre {          // everything of a trip that can be loaded before the tile barrier
     double2 own; int4 ell[K]; int pt; int ci;
@@ -174,6 +214,9 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
     for (int r = tid; r < 2 * tcv; r += OCCM_BLOCK) { tile[r * RS + S] = 1.0; tile[r * RS + S + 1] = 1.0; }
     const int n_points = (int)sys.n_points, N = n_points;     // ELL columns are [K][n_points] (CSTR: one point per model)
     const int my_tile = pl * RS + sp;
+    const unsigned tile_sa = occm_opaque_u32((unsigned)__cvta_generic_to_shared(tile));
+    const unsigned cmw_sa = WIDE ? occm_opaque_u32((unsigned)__cvta_generic_to_shared(cmw_s)) : 0u;
+    const unsigned mtw_sa = WIDE ? occm_opaque_u32((unsigned)__cvta_generic_to_shared(mtw_s)) : 0u;
     __syncthreads();
 
     // ---- cursor over this CTA's (member, chunk) trips, skipping members that are not running
@@ -214,10 +257,10 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
 
     auto process = [&](const OccmFastPre<STAGE, K>& cur, const OccmFastCtx<STAGE>& cc, OccmFastPre<STAGE, K>& nxt,
                        OccmFastCtx<STAGE>& ncx, bool have_next, int buf) {
-        double* tb = tile + buf * tcv * RS;
+        const unsigned row_sa = occm_opaque_u32(tile_sa + 8u * (unsigned)((buf * tcv + pl) * RS));   // this point's staged row
         // epilogue operands of THIS trip: needed last, so they have the whole trip to arrive
         const OccmOps2 ops = occm_fast_load_ops<STAGE>(sys, rk, cc, (cur.pt >= 0 ? cur.pt : 0) * S + sp);
-        if (lane_on) occm_st2(tb + my_tile, cur.own);
+        if (lane_on) occm_sts2(row_sa + 8u * sp, cur.own);
         if (WIDE) {                                     // uniform: this buffer's coefficient copy belongs to another member
             int& have = buf ? cmw_m1 : cmw_m0;
             if (have != cc.m) {
@@ -249,21 +292,33 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
         }
         double err2 = 0.0;
         if (cur.pt >= 0) {
-            const double* myrow = tb + pl * RS;
             if (!cur.ell[0].y) {
-                const double r0 = WIDE ? occm_reaction_wide(cmw_s + buf * NW + sp * nt_u, mtw_s + sp * nt_u, myrow, nt_u, nf_u)
-                                       : occm_reaction_fast(cm0, meta0, myrow, nt_u, nf_u);
-                const double r1 = WIDE ? occm_reaction_wide(cmw_s + buf * NW + (sp + 1) * nt_u, mtw_s + (sp + 1) * nt_u, myrow, nt_u, nf_u)
-                                       : occm_reaction_fast(cm1, meta1, myrow, nt_u, nf_u);
+                double r0, r1;
+                if (WIDE) {
+                    const unsigned c0 = cmw_sa + 8u * (unsigned)(buf * NW + sp * nt_u), m0 = mtw_sa + 4u * (unsigned)(sp * nt_u);
+                    if (nf_u <= 2) {
+                        r0 = occm_reaction_wide_sa<2>(c0, m0, row_sa, nt_u);
+                        r1 = occm_reaction_wide_sa<2>(c0 + 8u * nt_u, m0 + 4u * nt_u, row_sa, nt_u);
+                    } else {
+                        r0 = occm_reaction_wide_sa<3>(c0, m0, row_sa, nt_u);
+                        r1 = occm_reaction_wide_sa<3>(c0 + 8u * nt_u, m0 + 4u * nt_u, row_sa, nt_u);
+                    }
+                } else if (nf_u <= 2) {                 // uniform: one of four straight-line variants
+                    if (nt_u <= 2) { r0 = occm_reaction_sa<2, 2>(cm0, meta0, row_sa); r1 = occm_reaction_sa<2, 2>(cm1, meta1, row_sa); }
+                    else           { r0 = occm_reaction_sa<4, 2>(cm0, meta0, row_sa); r1 = occm_reaction_sa<4, 2>(cm1, meta1, row_sa); }
+                } else {
+                    if (nt_u <= 2) { r0 = occm_reaction_sa<2, 3>(cm0, meta0, row_sa); r1 = occm_reaction_sa<2, 3>(cm1, meta1, row_sa); }
+                    else           { r0 = occm_reaction_sa<4, 3>(cm0, meta0, row_sa); r1 = occm_reaction_sa<4, 3>(cm1, meta1, row_sa); }
+                }
                 double2 f;
                 if (MODEL == 0) {
                     double2 acc = make_double2(0.0, 0.0);
 #pragma unroll
                     for (int k = 0; k < K; ++k) acc = occm_fma2(__hiloint2double(cur.ell[k].w, cur.ell[k].z), g[k], acc);
-                    f = make_double2(cc.qs * acc.x + r0, cc.qs * acc.y + r1);
+                    f = make_double2(__dadd_rn(__dmul_rn(cc.qs, acc.x), r0), __dadd_rn(__dmul_rn(cc.qs, acc.y), r1));
                 } else {                     // first-order upwind difference along the PFR
                     const double na = -(cc.qs * __hiloint2double(cur.ell[0].w, cur.ell[0].z));
-                    f = make_double2(na * (cur.own.x - g[0].x) + r0, na * (cur.own.y - g[0].y) + r1);
+                    f = make_double2(__dadd_rn(__dmul_rn(na, cur.own.x - g[0].x), r0), __dadd_rn(__dmul_rn(na, cur.own.y - g[0].y), r1));
                 }
                 err2 = occm_fast_finish<STAGE>(sys, rk, cc, ops, f, cur.own, cur.pt * S + sp, dy_out);
             }   // flagged rows (boundary / pulse / overflow entries) are left to occm_fixup, launched right after

@@ -387,14 +387,14 @@ occm_stage(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmM
                 double acc = 0.0;
 #pragma unroll
                 for (int k = 0; k < OCCM_KREG; ++k) acc += ew[i][k] * g[i][k];
-                f = qs * acc + r;
+                f = __dadd_rn(__dmul_rn(qs, acc), r);
             } else {
                 const int P = sys.P;
                 const int k = pt[i] / P;
                 const int node = pt[i] - k * P;
                 if (!fast || slow[i] || node == 0) { slow[i] = 1; any_slow = 1; continue; }
-                const double conv = -(qs * __ldg(sys.a + k)) * (own[i] - myrow[s - RS]);
-                f = conv + occm_reaction_fast(coeffm, meta, myrow, nt_u, nf_u);
+                const double conv = __dmul_rn(-(qs * __ldg(sys.a + k)), own[i] - myrow[s - RS]);
+                f = __dadd_rn(conv, occm_reaction_fast(coeffm, meta, myrow, nt_u, nf_u));
             }
             err2 += occm_finish<STAGE>(rk, ops[i], f, h, par, base, pt[i] * S + s, own[i], dy_out);
         }

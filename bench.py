@@ -67,11 +67,16 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.rows = []
+        self.first = 0
         self.proc = None
+
+    def mark(self):
+        """Start of the timed region: earlier samples are discarded."""
+        self.first = len(self.rows)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200',
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '500',
                                           '-i', str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -90,6 +95,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        self.rows = self.rows[self.first:]
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
         reasons = set()
@@ -227,6 +233,11 @@ def main():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     lib = _lib.load()
+    # nvidia-smi takes seconds to attach (NVML init) and perturbs the GPU while it does (measured: +15..40 % on the solves
+    # that overlap it): start it before anything else and only keep the samples taken inside the timed region
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
 
     model, net, cp, cmesh = build_workload(args)
     solver = EnsembleSolver(model, net, cp, cmesh)
@@ -262,19 +273,21 @@ def main():
     for _ in range(args.warmup):
         one_solve()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     launches0 = lib.occm_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     nfev_total = 0
+    step_events = [ev0]
     for _ in range(args.steps):
         nfev, attempts, status = one_solve()
         nfev_total += nfev
+        step_events.append(torch.cuda.Event(enable_timing=True))
+        step_events[-1].record()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    step_ms = [round(a.elapsed_time(b), 2) for a, b in zip(step_events[:-1], step_events[1:])]
     launches = lib.occm_launch_count() - launches0
     assert np.all(status == 1), f'members failed: {np.unique(status)}'
     t_ms = torch.tensor([ms], dtype=torch.float64, device=device)
@@ -378,7 +391,7 @@ def main():
                 "config": {"workload": WORKLOAD, "members_per_gpu": M_loc, "members_total": M_glob, "n_cstr": N, "n_species": S,
                            "l2": f"inputs larger than L2: {11 * M_loc * ndof * 8 / 2**30:.1f} GiB of state vectors per GPU",
                            "parallelism": f"members sharded over {world_size} GPU(s), no data-path collective"},
-                "ode_solves_per_s": solves_per_s, "rhs_evals_total": evals,
+                "ode_solves_per_s": solves_per_s, "rhs_evals_total": evals, "step_ms": step_ms,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "solves_per_s": M_glob * args.steps / float(t_e.item())},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "plain_rhs": plain, "cpu_baseline": cpu}

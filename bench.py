@@ -60,53 +60,76 @@ def build_workload(args):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock, power and clock-event reasons sampled DURING the timed region (B200_PROFILING.md clocks line).
+
+    NVML is polled in-process (nvidia_ml_py, 4 Hz): a separate `nvidia-smi -lms` process takes seconds to attach and
+    perturbed the solves it overlapped.  Falls back to one-shot nvidia-smi queries if the binding is missing."""
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []          # (sm_mhz, power_w, reasons bitmask)
         self.first = 0
-        self.proc = None
+        self.max_mhz = None
+        self.thread = None
+        self._stop = threading.Event()
+
+    def _handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        idx = int(vis.split(',')[self.gpu]) if vis and all(v.strip().isdigit() for v in vis.split(',')) else self.gpu
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+
+    def start(self):
+        if os.environ.get('BENCH_NO_SAMPLER'):
+            return
+        try:
+            nv, h = self._handle()
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                          nv.nvmlDeviceGetPowerUsage(h) / 1000.0, int(get_reasons(h))))
+                    except Exception:
+                        pass
+                    self._stop.wait(0.25)
+        except Exception:
+            def poll():
+                q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active'
+                while not self._stop.is_set():
+                    try:
+                        out = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-i', str(self.gpu)],
+                                             capture_output=True, text=True, timeout=10).stdout.strip().split(',')
+                        self.max_mhz = float(out[1])
+                        self.rows.append((float(out[0]), float(out[2]), int(out[3].strip(), 16)))
+                    except Exception:
+                        pass
+                    self._stop.wait(0.5)
+        self.thread = threading.Thread(target=poll, daemon=True)
+        self.thread.start()
 
     def mark(self):
         """Start of the timed region: earlier samples are discarded."""
         self.first = len(self.rows)
 
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '500',
-                                          '-i', str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([v.strip() for v in line.split(',')])
-
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.rows = self.rows[self.first:]
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
-        reasons = set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
-            if len(r) >= 9:
-                for n, v in zip(names, r[5:9]):
-                    if v.lower().startswith('active') and 'not' not in v.lower():
-                        reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler unavailable"]}
+        self._stop.set()
+        self.thread.join(timeout=5)
+        rows = self.rows[self.first:] or self.rows
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+        mask = 0
+        for r in rows:
+            mask |= r[2]
+        return {"sm_mhz": float(np.median([r[0] for r in rows])), "sm_min_mhz": float(min(r[0] for r in rows)),
+                "sm_max_mhz": self.max_mhz, "power_w": float(np.median([r[1] for r in rows])),
+                "reasons": sorted(n for b, n in self.REASONS.items() if mask & b), "samples": len(rows)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU / reference arm

@@ -83,6 +83,22 @@ __device__ __forceinline__ OccmOps2 occm_fast_load_ops(const OccmSysDev& sys, co
     return o;
 }
 
+// L2 prefetch of the epilogue operands of the NEXT trip (no registers held): when that trip starts, its operand loads are
+// L2 hits instead of DRAM round trips.  One lane in eight covers a 128-byte line.
+__device__ __forceinline__ void occm_prefetch_l2(const double* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+template <int STAGE>
+__device__ __forceinline__ void occm_fast_prefetch_ops(const OccmSysDev& sys, const OccmRkDev& rk, const OccmFastCtx<STAGE>& c, int e) {
+    if (STAGE <= 1 || (threadIdx.x & 7) != 0) return;
+    const long long g = (long long)c.m * sys.ndof + e;
+    occm_prefetch_l2(rk.Y[c.par] + g);
+    if (STAGE != 7) occm_prefetch_l2(rk.KF[c.par] + g);
+    if (STAGE == 3) { occm_prefetch_l2(rk.K2 + g); }
+    if (STAGE == 4) { occm_prefetch_l2(rk.K2 + g); occm_prefetch_l2(rk.K3 + g); }
+    if (STAGE == 5) { occm_prefetch_l2(rk.K2 + g); occm_prefetch_l2(rk.K3 + g); occm_prefetch_l2(rk.K4 + g); }
+    if (STAGE == 6) { occm_prefetch_l2(rk.K3 + g); occm_prefetch_l2(rk.K4 + g); occm_prefetch_l2(rk.K5 + g); }
+    if (STAGE == 7) { occm_prefetch_l2(rk.K2 + g); }
+}
+
 // one species of the epilogue (same arithmetic as occm_finish); returns the squared scaled error in stage 7
 template <int STAGE>
 __device__ __forceinline__ double occm_fast_comb(const OccmRkDev& rk, double ye, double k1, double ka, double kb, double kc, double kd,
@@ -253,6 +269,9 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
         pre.own = occm_fast_in<STAGE>(occm_fast_in_a<STAGE>(sys, rk, y_in, cx), occm_fast_in_b<STAGE>(sys, mem, rk, cx), cx.h, e);
 #pragma unroll
         for (int k = 0; k < K; ++k) pre.ell[k] = __ldg(reinterpret_cast<const int4*>(ell + (size_t)k * N + pp));
+#ifndef OCCM_NO_PREFETCH
+        if (pre.pt >= 0) occm_fast_prefetch_ops<STAGE>(sys, rk, cx, e);
+#endif
     };
 
     auto process = [&](const OccmFastPre<STAGE, K>& cur, const OccmFastCtx<STAGE>& cc, OccmFastPre<STAGE, K>& nxt,

@@ -229,6 +229,16 @@ int occm_rtd(const double* out, int32_t n_members, int32_t n_times, int32_t n_sa
              const int32_t* sel_idx, const double* sel_w, const int32_t* sel_species, int32_t n_sel, int32_t n_species,
              double q_in_total, double* rtd, double* moments, void* stream);
 
+/*
+ * Recorded solution -> mesh elements.  Replaces the time x species x dof loops of `export_to_vtu_openfoam`
+ * (postprocessing/vtu_output.py:311-322) over `create_dof_to_element_map` (mesh/__init__.py:142-198):
+ *   out[t][s][element] = y[t][el_dof*S + s] * el_w + y[t][el_other*S + s] * (1 - el_w);  -1 where el_dof[element] < 0.
+ * y: device [n_times][ndof] (device layout, as written by occm_rk45 / occm_bdf with save_idx = NULL); out: device
+ * [n_times][n_species][n_elements].  Products and sum are rounded separately (bit-identical to the numpy expression).
+ */
+int occm_dofs_to_elements(const double* y, int32_t n_times, int32_t n_species, int64_t ndof, int32_t n_elements,
+                          const int32_t* el_dof, const int32_t* el_other, const double* el_w, double* out, void* stream);
+
 /* Development/measurement aid: launch Dormand-Prince stage kernel `stage` (2..7) `reps` times back to back on the
  * handle's current buffers and return the mean duration (CUDA events on `stream`). Leaves y, t, h untouched. */
 int occm_rk45_time_stage(occm_rk45* rk, int32_t stage, int32_t reps, float* ms_per_launch, void* stream);

@@ -82,3 +82,43 @@ extern "C" int occm_rtd(const double* out, int32_t n_members, int32_t n_times, i
     OCCM_LAUNCH_CHECK("occm_rtd_kernel");
     return OCCM_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ results -> mesh elements
+// Replaces the time x species x dof Python loops of `export_to_vtu_openfoam` (postprocessing/vtu_output.py:316-322):
+//   field[t][s][element] = c[dof] * w + c[dof_other] * (1 - w),   -1 for elements outside every compartment (:314).
+// y is the solver's recorded output [n_times][ndof] in device layout (point-major, species innermost).
+// Products and sum are rounded separately (no FMA): the same bits as the reference's numpy arithmetic.
+__global__ void __launch_bounds__(256)
+occm_elements_kernel(const double* __restrict__ y, int n_times, int S, long long ndof, int n_elements, const int* __restrict__ el_dof,
+                     const int* __restrict__ el_other, const double* __restrict__ el_w, double* __restrict__ out) {
+    const long long total = (long long)n_times * n_elements;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i / n_elements);
+        const int el = (int)(i - (long long)t * n_elements);
+        const int dof = el_dof[el];
+        double* o = out + (long long)t * S * n_elements + el;
+        if (dof < 0) {
+            for (int s = 0; s < S; ++s) o[(long long)s * n_elements] = -1.0;
+            continue;
+        }
+        const int other = el_other[el];
+        const double w = el_w[el], w1 = 1.0 - w;
+        const double* a = y + (long long)t * ndof + (long long)dof * S;
+        const double* b = y + (long long)t * ndof + (long long)other * S;
+        for (int s = 0; s < S; ++s) o[(long long)s * n_elements] = __dadd_rn(__dmul_rn(a[s], w), __dmul_rn(b[s], w1));
+    }
+}
+
+extern "C" int occm_dofs_to_elements(const double* y, int32_t n_times, int32_t n_species, int64_t ndof, int32_t n_elements,
+                                     const int32_t* el_dof, const int32_t* el_other, const double* el_w, double* out, void* stream) {
+    if (!y || !el_dof || !el_other || !el_w || !out) { occm_set_error("occm_dofs_to_elements: null argument"); return OCCM_ERR_INVALID; }
+    if (n_times < 1 || n_species < 1 || n_elements < 1 || ndof < n_species || ndof % n_species) {
+        occm_set_error("occm_dofs_to_elements: bad sizes"); return OCCM_ERR_INVALID;
+    }
+    const long long total = (long long)n_times * n_elements;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    occm_elements_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(y, n_times, n_species, ndof, n_elements, el_dof, el_other, el_w, out);
+    OCCM_LAUNCH_CHECK("occm_elements_kernel");
+    return OCCM_OK;
+}

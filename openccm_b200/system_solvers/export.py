@@ -109,6 +109,67 @@ def element_dofs(model_to_element_map: Optional[list], n_models: int, P: int) ->
     return model * P + idx, elem
 
 
+def element_interpolation(model_to_element_map: Optional[list], n_models: int, P: int, n_elements: int):
+    """Per mesh element the two DOFs and the weight its value is interpolated from:
+    ``(el_dof, el_other, el_w)`` with ``value = c[el_dof] * el_w + c[el_other] * (1 - el_w)`` and ``el_dof = -1`` for
+    elements outside every compartment.
+
+    Vectorised form of create_dof_to_element_map (mesh/__init__.py:142-198) for distance-sorted element lists.  Along a
+    PFR the reference walks the list once; point 0 takes the prefix with dist <= delta, a middle point i first the
+    prefix with dist <= dof_dist[i] (interpolating towards point i-1), then the prefix with dist <= dof_dist[i] + delta
+    (towards point i+1), the last point the rest — "prefix" meaning up to the first element that exceeds the bound."""
+    if model_to_element_map is None:
+        model_to_element_map = [[(0.0, i)] for i in range(n_models)]
+    counts = np.fromiter((len(m) for m in model_to_element_map), dtype=np.int64, count=len(model_to_element_map))
+    total = int(counts.sum())
+    dist = np.empty(total); elem = np.empty(total, dtype=np.int64)
+    k = 0
+    for m in model_to_element_map:
+        n = len(m)
+        if n:
+            arr = np.asarray(m, dtype=np.float64)
+            dist[k:k + n] = arr[:, 0]; elem[k:k + n] = arr[:, 1].astype(np.int64)
+            k += n
+    model = np.repeat(np.arange(len(model_to_element_map), dtype=np.int64), counts)
+    ndof = len(model_to_element_map) * P
+    if P == 1:
+        # the "last point" branch with delta = 1e20 (:160,:171-174): weight clips to 1, dof_other = dof - 1 (index -1 wraps)
+        dof = model
+        other = (dof - 1) % ndof
+        w = np.clip(1.0 + (dist - 1.0) / (2 * 1e20), 0.0, 1.0)
+    else:
+        dof_dist = np.linspace(0.0, 1.0, num=P)
+        delta = 1.0 / (P - 1) / 2
+        # bounds of the successive prefixes: [delta | d_1, d_1 + delta | d_2, d_2 + delta | ...]; past the end = last point
+        bounds = np.empty(1 + 2 * (P - 2))
+        bounds[0] = delta
+        bounds[1::2] = dof_dist[1:P - 1]
+        bounds[2::2] = dof_dist[1:P - 1] + delta
+        run = dist.copy()
+        starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
+        for s0, n in zip(starts.tolist(), counts.tolist()):
+            if n > 1:
+                np.maximum.accumulate(run[s0:s0 + n], out=run[s0:s0 + n])
+        seg = np.searchsorted(bounds, run, side='left')
+        last = seg == len(bounds)
+        point = np.where(last, P - 1, (seg + 1) // 2)
+        before = (~last) & (seg % 2 == 1)                    # middle point, interpolating towards point - 1
+        first = seg == 0
+        dof = model * P + point
+        other = np.where(first | ((~last) & ~before), dof + 1, dof - 1)
+        with np.errstate(invalid='ignore'):
+            w = np.where(last, 1.0 + (dist - 1.0) / (2 * delta),
+                 np.where(first, 1.0 - dist / (2 * delta),
+                 np.where(before, (dist - dof_dist[np.maximum(point - 1, 0)]) / (2 * delta),
+                          (dof_dist[np.minimum(point + 1, P - 1)] - dist) / (2 * delta))))
+        w = np.clip(w, 0.0, 1.0)
+    el_dof = -np.ones(n_elements, dtype=np.int32)
+    el_other = np.zeros(n_elements, dtype=np.int32)
+    el_w = np.zeros(n_elements, dtype=np.float64)
+    el_dof[elem] = dof; el_other[elem] = other; el_w[elem] = w      # an element listed twice keeps its last entry (:322 overwrites)
+    return el_dof, el_other, el_w
+
+
 # ------------------------------------------------------------------------------------------- initial conditions
 def _lambdify_xyz(text: str):
     return sp.lambdify([_X, _Y, _Z, T_SYM], text, 'numpy')

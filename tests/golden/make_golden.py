@@ -143,6 +143,51 @@ def parser_kats() -> None:
     print('[golden] parser_kats.json')
 
 
+VTU_CASES = ('pfr_net8', 'cstr_net20_timebc', 'pfr_single', 'openfoam_2d_pfr')
+
+
+def vtu_golden(name: str) -> None:
+    """f-3: the per-(time, species) element buffers the UNMODIFIED `export_to_vtu_openfoam` hands to its file writer, for
+    the golden solution of `name` (the writer is replaced by a capture, the folder layout is prepared in a scratch dir)."""
+    import openccm.postprocessing.vtu_output as ref_vtu
+    case = C.CASES[name]
+    g = np.load(os.path.join(HERE, f'{name}.npz'))
+    solver = 'RK45' if 'c_RK45' in g.files else 'LSODA'
+    c, ts = g[f'c_{solver}'], g[f't_{solver}']
+    keep = np.unique(np.linspace(0, len(ts) - 1, 4).astype(int))           # a few output times are enough
+    c, ts = np.ascontiguousarray(c[:, :, keep]), ts[keep]
+    net = case['net']()
+    tmp = tempfile.mkdtemp(prefix=f'golden_vtu_{name}_')
+    old = os.getcwd(); os.chdir(tmp)
+    captured = []
+    orig = ref_vtu.write_buffer_to_file_openfoam
+    ref_vtu.write_buffer_to_file_openfoam = lambda buffer, path, t, var, cmesh: captured.append(np.array(buffer, copy=True))
+    try:
+        os.makedirs('cache', exist_ok=True)
+        with open('CONFIG', 'w') as fh:
+            fh.write(C.config_text(name, solver, 'reactions'))
+        cp = ConfigParser('CONFIG')
+        cp['SETUP']['output_folder_path'] = tmp + '/out/'
+        cp['POST-PROCESSING']['vtu_dir'] = 'vtu/'
+        cp.need_to_update_paths = False
+        t0 = cp.get_list(['SIMULATION', 't_span'], float)[0]
+        os.makedirs(os.path.join(tmp, 'out', 'vtu', str(t0)), exist_ok=True)
+        if ts[0] != t0:                      # the reference creates the first folder with exist_ok only for i_t == 0
+            os.makedirs(os.path.join(tmp, 'out', 'vtu', str(ts[0])), exist_ok=True)
+        gb = GroupedBCs(cp)
+        cmesh = C.make_cmesh(name, net, gb)
+        m2e = net.to_model_network()[-1]
+        ref_vtu.export_to_vtu_openfoam(c, ts, m2e, cp, cmesh)
+    finally:
+        ref_vtu.write_buffer_to_file_openfoam = orig
+        os.chdir(old)
+        shutil.rmtree(tmp, ignore_errors=True)
+    S = c.shape[0]
+    fields = np.array(captured).reshape(len(ts), S, -1)
+    np.savez_compressed(os.path.join(HERE, f'vtu_{name}.npz'), fields=fields, time_index=keep)
+    print(f'[golden] vtu_{name}: fields{fields.shape} unmapped {(fields[0, 0] == -1).sum()}')
+
+
 def openfoam_cstr_fixture() -> None:
     """C3: the same OpenFOAM 2-D example compartmentalised with model = CSTR (76 CSTRs); network + geometry fixture."""
     import openccm
@@ -216,6 +261,12 @@ if __name__ == '__main__':
     if '--openfoam-cstr-fixture' in argv:
         argv.remove('--openfoam-cstr-fixture')
         openfoam_cstr_fixture()
+    if '--vtu' in argv:
+        argv.remove('--vtu')
+        for n in VTU_CASES:
+            vtu_golden(n)
+        if not argv:
+            sys.exit(0)
     if '--kats' in argv:
         argv.remove('--kats')
         parser_kats()

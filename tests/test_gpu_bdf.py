@@ -83,3 +83,24 @@ def test_bdf_batched_members(tmp_path):
         r = scipy.integrate.solve_ivp(fun, (0, 30), syso.y0, method='LSODA', rtol=1e-10, atol=1e-13, t_eval=res.t)
         c_dev = res.y[m].reshape(len(res.t), N, S).transpose(2, 1, 0).reshape(S * N, -1)
         assert np.all(np.abs(c_dev - r.y) <= 5e-9 + 1e-6 * np.abs(r.y)), (m, np.abs(c_dev - r.y).max())
+
+
+@pytest.mark.parametrize('name', ['cstr_net12_nacl', 'pfr_net8_nacl'])
+def test_bdf_stored_and_on_the_fly_preconditioner_agree(name, tmp_path, monkeypatch):
+    """precond_mode 0 (block inverses kept in HBM, rebuilt lazily) and 1 (rebuilt on every application) solve the same
+    Newton systems: the solutions agree far inside the tolerance band, and the stored variant rebuilds rarely."""
+    import torch
+    from openccm_b200.bdf import solve_bdf
+    from openccm_b200.device import DeviceSystem
+    from openccm_b200.system_solvers.export import export_system
+    cp, cmesh, net, mn = setup_case(name, 'B200-BDF', tmp_path, rtol=1e-8, atol=1e-11)
+    host = export_system(C.CASES[name]['model'], mn, cp, cmesh)
+    dev = DeviceSystem(host)
+    y0 = torch.as_tensor(host.to_device_layout(host.c0.reshape(-1)), device='cuda').reshape(1, -1)
+    te = np.linspace(0.0, 10.0, 11)
+    res = [solve_bdf(dev, y0, (0.0, 10.0), rtol=1e-8, atol=1e-11, first_step=1e-4, t_eval=te, precond_mode=mode) for mode in (0, 1)]
+    assert all(np.all(r.status == 1) for r in res)
+    a, b = res[0].y.cpu().numpy(), res[1].y.cpu().numpy()
+    assert np.all(np.abs(a - b) <= 1e-10 + 1e-6 * np.abs(b)), np.abs(a - b).max()
+    assert res[1].n_precond_factor.sum() == 0
+    assert 0 < res[0].n_precond_factor[0] < res[0].n_accepted[0]

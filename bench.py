@@ -93,7 +93,9 @@ class ClockSampler:
                 while not self._stop.is_set():
                     try:
                         self.rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
-                                          nv.nvmlDeviceGetPowerUsage(h) / 1000.0, int(get_reasons(h))))
+                                          nv.nvmlDeviceGetPowerUsage(h) / 1000.0, int(get_reasons(h)), time.perf_counter(),
+                                          float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_MEM)),
+                                          float(nv.nvmlDeviceGetTemperature(h, nv.NVML_TEMPERATURE_GPU))))
                     except Exception:
                         pass
                     self._stop.wait(0.25)
@@ -115,6 +117,7 @@ class ClockSampler:
     def mark(self):
         """Start of the timed region: earlier samples are discarded."""
         self.first = len(self.rows)
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.thread is None:
@@ -127,6 +130,11 @@ class ClockSampler:
         mask = 0
         for r in rows:
             mask |= r[2]
+        if os.environ.get('BENCH_TRACE'):
+            print('[trace] t_s, sm_mhz, power_w, reasons, mem_mhz, temp_c', file=sys.stderr)
+            for r in self.rows:
+                if len(r) >= 6:
+                    print(f'[trace] {r[3] - getattr(self, "t_mark", r[3]):8.2f} {r[0]:6.0f} {r[1]:7.1f} {r[2]:#x} {r[4]:6.0f} {r[5]:4.0f}', file=sys.stderr)
         return {"sm_mhz": float(np.median([r[0] for r in rows])), "sm_min_mhz": float(min(r[0] for r in rows)),
                 "sm_max_mhz": self.max_mhz, "power_w": float(np.median([r[1] for r in rows])),
                 "reasons": sorted(n for b, n in self.REASONS.items() if mask & b), "samples": len(rows)}

@@ -186,6 +186,9 @@ struct OccmFastPre {          // everything of a trip that can be loaded before 
 #ifndef OCCM_FAST_CTAS
 #define OCCM_FAST_CTAS 2
 #endif
+#ifndef OCCM_FAST_BLOCK
+#define OCCM_FAST_BLOCK 256        // threads per CTA of the fast kernels (the fix-up kernel keeps OCCM_BLOCK)
+#endif
 template <int MODEL, int STAGE, int K, int WIDE>
 __device__ __forceinline__ void
 occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk,
@@ -210,7 +213,7 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
     unsigned meta0[OCCM_NT], meta1[OCCM_NT];
     if (WIDE) {
         const OccmTab T = occm_tab_views(tab_s);
-        for (int i = tid; i < NW; i += OCCM_BLOCK) {
+        for (int i = tid; i < NW; i += OCCM_FAST_BLOCK) {
             const int s_ = i / nt_u;
             double c; unsigned mt;
             occm_rxn_term(T, s_, i - s_ * nt_u, S, c, mt);
@@ -227,7 +230,7 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
             if (lane_on && pl == 0) { rxc_s[sp * OCCM_NT + q] = R0.coeff[q]; rxc_s[(sp + 1) * OCCM_NT + q] = R1.coeff[q]; }
         }
     }
-    for (int r = tid; r < 2 * tcv; r += OCCM_BLOCK) { tile[r * RS + S] = 1.0; tile[r * RS + S + 1] = 1.0; }
+    for (int r = tid; r < 2 * tcv; r += OCCM_FAST_BLOCK) { tile[r * RS + S] = 1.0; tile[r * RS + S + 1] = 1.0; }
     const int n_points = (int)sys.n_points, N = n_points;     // ELL columns are [K][n_points] (CSTR: one point per model)
     const int my_tile = pl * RS + sp;
     const unsigned tile_sa = occm_opaque_u32((unsigned)__cvta_generic_to_shared(tile));
@@ -284,7 +287,7 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
             int& have = buf ? cmw_m1 : cmw_m0;
             if (have != cc.m) {
                 double* dst = cmw_s + buf * NW;
-                for (int i = tid; i < NW; i += OCCM_BLOCK)
+                for (int i = tid; i < NW; i += OCCM_FAST_BLOCK)
                     dst[i] = rxc_s[i] * (mem.k_scale ? __ldg(mem.k_scale + (long long)cc.m * sys.n_rxn + (mtw_s[i] & 0xffu)) : 1.0);
                 have = cc.m;
             }
@@ -346,7 +349,7 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
             double v = err2;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-            if ((tid & 31) == 0) rk.err_partial[(long long)cc.m * err_stride + cur.ci * (OCCM_BLOCK / 32) + (tid >> 5)] = v;
+            if ((tid & 31) == 0) rk.err_partial[(long long)cc.m * err_stride + cur.ci * (OCCM_FAST_BLOCK / 32) + (tid >> 5)] = v;
         }
     };
 
@@ -363,7 +366,7 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
 
 
 template <int STAGE, int K, int WIDE>
-__global__ void __launch_bounds__(OCCM_BLOCK, OCCM_FAST_CTAS)
+__global__ void __launch_bounds__(OCCM_FAST_BLOCK, OCCM_FAST_CTAS)
 occm_fast_cstr(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmMemDev mem, const __grid_constant__ OccmRkDev rk,
                const double* __restrict__ t_dev, double t_scalar, const double* __restrict__ y_in, double* __restrict__ dy_out,
                const OccmEllEntry* __restrict__ ell, int cpm, int tcv, int err_stride) {
@@ -371,7 +374,7 @@ occm_fast_cstr(const __grid_constant__ OccmSysDev sys, const __grid_constant__ O
 }
 
 template <int STAGE, int WIDE>
-__global__ void __launch_bounds__(OCCM_BLOCK, OCCM_FAST_CTAS)
+__global__ void __launch_bounds__(OCCM_FAST_BLOCK, OCCM_FAST_CTAS)
 occm_fast_pfr(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmMemDev mem, const __grid_constant__ OccmRkDev rk,
               const double* __restrict__ t_dev, double t_scalar, const double* __restrict__ y_in, double* __restrict__ dy_out,
               const OccmEllEntry* __restrict__ ell, int cpm, int tcv, int err_stride) {

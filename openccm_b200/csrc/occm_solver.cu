@@ -633,14 +633,14 @@ static int occm_launch_fast(const occm_system* sys, const OccmMemDev& mem, const
                             double t_scalar, const double* y_in, double* dy_out, cudaStream_t st, int* cpm_out) {
     static size_t smem_limit = 48 * 1024;
     static int ctas_per_sm = 0;
-    const int S = sys->dev.S, tcv = OCCM_BLOCK / (S / 2);
+    const int S = sys->dev.S, tcv = OCCM_FAST_BLOCK / (S / 2);
     const size_t nw = (size_t)S * sys->max_terms;          // WIDE: unscaled + two scaled coefficient copies + meta words
     const size_t smem = (((size_t)sys->dev.tables_bytes + 15) & ~(size_t)15) +
                         sizeof(double) * ((size_t)2 * tcv * (S + 2) + (WIDE ? 3 * nw + (nw + 1) / 2 : (size_t)S * OCCM_NT) + 40);
     auto kern = occm_fast_kernel<MODEL, STAGE, K, WIDE>();
     if (smem > smem_limit) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_limit = smem; }
     if (ctas_per_sm == 0) {
-        OCCM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, OCCM_BLOCK, smem));
+        OCCM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, OCCM_FAST_BLOCK, smem));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
     const int cpm = (int)((sys->dev.n_points + tcv - 1) / tcv);
@@ -650,9 +650,9 @@ static int occm_launch_fast(const occm_system* sys, const OccmMemDev& mem, const
     const int n_flagged = sys->desc.n_flagged;
     const int tcf = OCCM_BLOCK / S;
     const int nfix = n_flagged > 0 ? (n_flagged + tcf - 1) / tcf : 0;
-    const int nwarp = OCCM_BLOCK / 32;
+    const int nwarp = OCCM_FAST_BLOCK / 32;
     const int err_stride = cpm * nwarp + nfix;            // partial sums per member: one per warp and chunk, then fix-up blocks
-    kern<<<grid, OCCM_BLOCK, smem, st>>>(sys->dev, mem, rk, t_dev, t_scalar, y_in, dy_out, (const OccmEllEntry*)sys->desc.ell_packed, cpm, tcv, err_stride);
+    kern<<<grid, OCCM_FAST_BLOCK, smem, st>>>(sys->dev, mem, rk, t_dev, t_scalar, y_in, dy_out, (const OccmEllEntry*)sys->desc.ell_packed, cpm, tcv, err_stride);
     OCCM_LAUNCH_CHECK("occm_fast_cstr");
     if (nfix > 0) {
         const size_t fsmem = (size_t)sys->dev.tables_bytes + sizeof(double) * ((size_t)(MODEL == 1 ? 2 : 1) * tcf * (S + 1) + 8);

@@ -55,6 +55,7 @@ def solve_bdf(system: DeviceSystem, y0: torch.Tensor, t_span: Sequence[float], *
               all_capacity: int = 4096, return_final: bool = False, precond_mode: Optional[int] = None) -> BdfResult:
     """``precond_mode``: 0 keeps the block inverses of the preconditioner in HBM (ndof * S doubles per member, rebuilt by
     CVODE's setup policy), 1 rebuilds and solves the blocks on every application; None = ``OCCM_B200_BDF_PRECOND`` or 0."""
+    auto_mode = precond_mode is None and 'OCCM_B200_BDF_PRECOND' not in os.environ
     if precond_mode is None:
         precond_mode = int(os.environ.get('OCCM_B200_BDF_PRECOND', '0'))
     assert y0.is_cuda and y0.dtype == torch.float64 and y0.is_contiguous()
@@ -78,6 +79,12 @@ def solve_bdf(system: DeviceSystem, y0: torch.Tensor, t_span: Sequence[float], *
     out_t = torch.empty((M, T), dtype=torch.float64, device=system.dev)
     tdiag = transport_diagonal(system)
     ws_bytes = lib.occm_bdf_workspace_bytes(system.handle, M, gmres_restart, int(precond_mode))
+    if auto_mode and precond_mode == 0:
+        # the stored block inverses are optional: drop them when they would not fit next to the Krylov vectors
+        free_bytes = torch.cuda.mem_get_info(system.dev)[0]
+        if ws_bytes > 0.9 * free_bytes:
+            precond_mode = 1
+            ws_bytes = lib.occm_bdf_workspace_bytes(system.handle, M, gmres_restart, 1)
     ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=system.dev)
     ws_ptr = (ws.data_ptr() + 255) & ~255
     prob = _lib.BdfProblem(float(t_span[0]), float(t_span[1]), float(first_step), float(rtol), float(atol), y0.data_ptr(),

@@ -16,6 +16,7 @@
 //     NEXT trip are already in flight (registers), so only the L2 latency of the row gathers is exposed;
 //   * the staged tile is double buffered: one __syncthreads per trip.
 #pragma once
+#include <type_traits>
 
 struct __align__(16) OccmEllEntry { int src; int flag; double w; };
 
@@ -145,34 +146,41 @@ __device__ __forceinline__ unsigned occm_opaque_u32(unsigned v) { asm volatile("
 __device__ __forceinline__ double occm_lds_f64(unsigned sa) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sa)); return v; }
 __device__ __forceinline__ unsigned occm_lds_u32(unsigned sa) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa)); return v; }
 __device__ __forceinline__ void occm_sts2(unsigned sa, double2 v) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(sa), "d"(v.x), "d"(v.y) : "memory"); }
+// the same with a compile-time byte offset folded into the instruction: the two tile buffers sit OCCM_TILE_BUF_BYTES apart, so
+// the per-thread slot addresses are loop invariants (the compiler keeps as many of them in registers as it can afford)
+template <unsigned OFF>
+__device__ __forceinline__ double occm_lds_f64_at(unsigned sa) { double v; asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(sa), "n"(OFF)); return v; }
+template <unsigned OFF>
+__device__ __forceinline__ void occm_sts2_at(unsigned sa, double2 v) { asm volatile("st.shared.v2.f64 [%0+%3], {%1, %2};" :: "r"(sa), "d"(v.x), "d"(v.y), "n"(OFF) : "memory"); }
+#define OCCM_TILE_BUF_BYTES (OCCM_FAST_BLOCK * 32)      // >= tcv * (S + 2) * 8 for every even S >= 2
 
 // Reaction rate of one species from its register-resident term list, straight-line: NTc terms x NFc factor slots are always
 // evaluated (padding terms have coefficient 0, padding slots read the 1.0 column), which gives the same bits as stopping at
 // the mechanism's own maxima and removes every uniform branch from the hot loop.  row_sa = shared address of the point's row.
-template <int NTc, int NFc>
+template <int NTc, int NFc, unsigned BO>
 __device__ __forceinline__ double occm_reaction_sa(const double (&cm)[OCCM_NT], const unsigned (&meta)[OCCM_NT], unsigned row_sa) {
     double acc = 0.0;
 #pragma unroll
     for (int i = 0; i < NTc; ++i) {
         const unsigned m = meta[i];
         double v = cm[i];                      // explicit roundings: every variant (registers, shared lists, table walk) gives the same bits
-        v = __dmul_rn(v, occm_lds_f64(row_sa + ((m >> 5) & 0x7f8u)));
-        if (NFc > 1) v = __dmul_rn(v, occm_lds_f64(row_sa + ((m >> 13) & 0x7f8u)));
-        if (NFc > 2) v = __dmul_rn(v, occm_lds_f64(row_sa + ((m >> 21) & 0x7f8u)));
+        v = __dmul_rn(v, occm_lds_f64_at<BO>(row_sa + ((m >> 5) & 0x7f8u)));
+        if (NFc > 1) v = __dmul_rn(v, occm_lds_f64_at<BO>(row_sa + ((m >> 13) & 0x7f8u)));
+        if (NFc > 2) v = __dmul_rn(v, occm_lds_f64_at<BO>(row_sa + ((m >> 21) & 0x7f8u)));
         acc = __dadd_rn(acc, v);
     }
     return acc;
 }
 // term list in shared memory (WIDE): c_sa / mt_sa = shared addresses of the species' scaled coefficients and meta words
-template <int NFc>
+template <int NFc, unsigned BO>
 __device__ __forceinline__ double occm_reaction_wide_sa(unsigned c_sa, unsigned mt_sa, unsigned row_sa, int nt) {
     double acc = 0.0;
     for (int i = 0; i < nt; ++i) {
         const unsigned m = occm_lds_u32(mt_sa + 4u * i);
         double v = occm_lds_f64(c_sa + 8u * i);
-        v = __dmul_rn(v, occm_lds_f64(row_sa + ((m >> 5) & 0x7f8u)));
-        if (NFc > 1) v = __dmul_rn(v, occm_lds_f64(row_sa + ((m >> 13) & 0x7f8u)));
-        if (NFc > 2) v = __dmul_rn(v, occm_lds_f64(row_sa + ((m >> 21) & 0x7f8u)));
+        v = __dmul_rn(v, occm_lds_f64_at<BO>(row_sa + ((m >> 5) & 0x7f8u)));
+        if (NFc > 1) v = __dmul_rn(v, occm_lds_f64_at<BO>(row_sa + ((m >> 13) & 0x7f8u)));
+        if (NFc > 2) v = __dmul_rn(v, occm_lds_f64_at<BO>(row_sa + ((m >> 21) & 0x7f8u)));
         acc = __dadd_rn(acc, v);
     }
     return acc;
@@ -198,8 +206,8 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
     int* tab_s = reinterpret_cast<int*>(smem_d);
     occm_load_tables(sys.tables, sys.tables_bytes, tab_s);
     const int S = sys.S, H = S >> 1, RS = S + 2;            // staged rows: S values + two 1.0 pads (keeps 16-byte alignment)
-    double* tile = smem_d + (((sys.tables_bytes + 15) >> 4) << 1);   // [2][tcv][RS], 16-byte aligned
-    double* rxc_s = tile + 2 * tcv * RS;                    // unscaled coefficients [S][OCCM_NT]  (WIDE: [S][nt_u])
+    double* tile = smem_d + (((sys.tables_bytes + 15) >> 4) << 1);   // two buffers [tcv][RS], OCCM_TILE_BUF_BYTES apart, 16-byte aligned
+    double* rxc_s = tile + 2 * (OCCM_TILE_BUF_BYTES / 8);                    // unscaled coefficients [S][OCCM_NT]  (WIDE: [S][nt_u])
     const int tid = threadIdx.x;
     const bool lane_on = tid < tcv * H;
     const int pl = tid / H;
@@ -230,10 +238,13 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
             if (lane_on && pl == 0) { rxc_s[sp * OCCM_NT + q] = R0.coeff[q]; rxc_s[(sp + 1) * OCCM_NT + q] = R1.coeff[q]; }
         }
     }
-    for (int r = tid; r < 2 * tcv; r += OCCM_FAST_BLOCK) { tile[r * RS + S] = 1.0; tile[r * RS + S + 1] = 1.0; }
+    for (int r = tid; r < 2 * tcv; r += OCCM_FAST_BLOCK) {
+        double* row = tile + (r >= tcv ? OCCM_TILE_BUF_BYTES / 8 + (r - tcv) * RS : r * RS);
+        row[S] = 1.0; row[S + 1] = 1.0;
+    }
     const int n_points = (int)sys.n_points, N = n_points;     // ELL columns are [K][n_points] (CSTR: one point per model)
     const int my_tile = pl * RS + sp;
-    const unsigned tile_sa = occm_opaque_u32((unsigned)__cvta_generic_to_shared(tile));
+    const unsigned row0_sa = occm_opaque_u32((unsigned)__cvta_generic_to_shared(tile) + 8u * (unsigned)(pl * RS));   // this thread's row, buffer 0
     const unsigned cmw_sa = WIDE ? occm_opaque_u32((unsigned)__cvta_generic_to_shared(cmw_s)) : 0u;
     const unsigned mtw_sa = WIDE ? occm_opaque_u32((unsigned)__cvta_generic_to_shared(mtw_s)) : 0u;
     __syncthreads();
@@ -278,11 +289,16 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
     };
 
     auto process = [&](const OccmFastPre<STAGE, K>& cur, const OccmFastCtx<STAGE>& cc, OccmFastPre<STAGE, K>& nxt,
-                       OccmFastCtx<STAGE>& ncx, bool have_next, int buf) {
-        const unsigned row_sa = occm_opaque_u32(tile_sa + 8u * (unsigned)((buf * tcv + pl) * RS));   // this point's staged row
+                       OccmFastCtx<STAGE>& ncx, bool have_next, auto buf_c) {
+        constexpr int buf = decltype(buf_c)::value;
+        constexpr unsigned BO = (unsigned)buf * OCCM_TILE_BUF_BYTES;      // byte offset of this trip's tile buffer
+        // Plain RHS / J*v kernels have registers to spare: their slot addresses row0_sa + offset stay loop invariants (hoisted,
+        // -12 % time).  The Dormand-Prince stages hold up to 20 operand registers: there the hoisting spilled (stage 5 +30 %),
+        // so the row address is made opaque per trip and the slot offsets are added in the loop.
+        const unsigned row_sa = STAGE <= 1 ? row0_sa : occm_opaque_u32(row0_sa);
         // epilogue operands of THIS trip: needed last, so they have the whole trip to arrive
         const OccmOps2 ops = occm_fast_load_ops<STAGE>(sys, rk, cc, (cur.pt >= 0 ? cur.pt : 0) * S + sp);
-        if (lane_on) occm_sts2(row_sa + 8u * sp, cur.own);
+        if (lane_on) occm_sts2_at<BO>(row_sa + 8u * sp, cur.own);
         if (WIDE) {                                     // uniform: this buffer's coefficient copy belongs to another member
             int& have = buf ? cmw_m1 : cmw_m0;
             if (have != cc.m) {
@@ -319,18 +335,18 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
                 if (WIDE) {
                     const unsigned c0 = cmw_sa + 8u * (unsigned)(buf * NW + sp * nt_u), m0 = mtw_sa + 4u * (unsigned)(sp * nt_u);
                     if (nf_u <= 2) {
-                        r0 = occm_reaction_wide_sa<2>(c0, m0, row_sa, nt_u);
-                        r1 = occm_reaction_wide_sa<2>(c0 + 8u * nt_u, m0 + 4u * nt_u, row_sa, nt_u);
+                        r0 = occm_reaction_wide_sa<2, BO>(c0, m0, row_sa, nt_u);
+                        r1 = occm_reaction_wide_sa<2, BO>(c0 + 8u * nt_u, m0 + 4u * nt_u, row_sa, nt_u);
                     } else {
-                        r0 = occm_reaction_wide_sa<3>(c0, m0, row_sa, nt_u);
-                        r1 = occm_reaction_wide_sa<3>(c0 + 8u * nt_u, m0 + 4u * nt_u, row_sa, nt_u);
+                        r0 = occm_reaction_wide_sa<3, BO>(c0, m0, row_sa, nt_u);
+                        r1 = occm_reaction_wide_sa<3, BO>(c0 + 8u * nt_u, m0 + 4u * nt_u, row_sa, nt_u);
                     }
                 } else if (nf_u <= 2) {                 // uniform: one of four straight-line variants
-                    if (nt_u <= 2) { r0 = occm_reaction_sa<2, 2>(cm0, meta0, row_sa); r1 = occm_reaction_sa<2, 2>(cm1, meta1, row_sa); }
-                    else           { r0 = occm_reaction_sa<4, 2>(cm0, meta0, row_sa); r1 = occm_reaction_sa<4, 2>(cm1, meta1, row_sa); }
+                    if (nt_u <= 2) { r0 = occm_reaction_sa<2, 2, BO>(cm0, meta0, row_sa); r1 = occm_reaction_sa<2, 2, BO>(cm1, meta1, row_sa); }
+                    else           { r0 = occm_reaction_sa<4, 2, BO>(cm0, meta0, row_sa); r1 = occm_reaction_sa<4, 2, BO>(cm1, meta1, row_sa); }
                 } else {
-                    if (nt_u <= 2) { r0 = occm_reaction_sa<2, 3>(cm0, meta0, row_sa); r1 = occm_reaction_sa<2, 3>(cm1, meta1, row_sa); }
-                    else           { r0 = occm_reaction_sa<4, 3>(cm0, meta0, row_sa); r1 = occm_reaction_sa<4, 3>(cm1, meta1, row_sa); }
+                    if (nt_u <= 2) { r0 = occm_reaction_sa<2, 3, BO>(cm0, meta0, row_sa); r1 = occm_reaction_sa<2, 3, BO>(cm1, meta1, row_sa); }
+                    else           { r0 = occm_reaction_sa<4, 3, BO>(cm0, meta0, row_sa); r1 = occm_reaction_sa<4, 3, BO>(cm1, meta1, row_sa); }
                 }
                 double2 f;
                 if (MODEL == 0) {
@@ -357,10 +373,10 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
     if (valid) load(A, cxA);
     while (valid) {
         bool vn = advance();                 // (m, ci) now name the next trip
-        process(A, cxA, B, cxB, vn, 0);
+        process(A, cxA, B, cxB, vn, std::integral_constant<int, 0>{});
         if (!vn) break;
         valid = advance();
-        process(B, cxB, A, cxA, valid, 1);
+        process(B, cxB, A, cxA, valid, std::integral_constant<int, 1>{});
     }
 }
 

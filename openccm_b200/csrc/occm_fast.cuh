@@ -18,6 +18,13 @@
 #pragma once
 #include <type_traits>
 
+#ifndef OCCM_FAST_CTAS
+#define OCCM_FAST_CTAS 2
+#endif
+#ifndef OCCM_FAST_BLOCK
+#define OCCM_FAST_BLOCK 256        // threads per CTA of the fast kernels (the fix-up kernel keeps OCCM_BLOCK)
+#endif
+
 struct __align__(16) OccmEllEntry { int src; int flag; double w; };
 
 struct OccmOps2 { double2 ye, k1, ka, kb, kc, kd; };
@@ -98,6 +105,47 @@ __device__ __forceinline__ void occm_fast_prefetch_ops(const OccmSysDev& sys, co
     if (STAGE == 5) { occm_prefetch_l2(rk.K2 + g); occm_prefetch_l2(rk.K3 + g); occm_prefetch_l2(rk.K4 + g); }
     if (STAGE == 6) { occm_prefetch_l2(rk.K3 + g); occm_prefetch_l2(rk.K4 + g); occm_prefetch_l2(rk.K5 + g); }
     if (STAGE == 7) { occm_prefetch_l2(rk.K2 + g); }
+}
+
+// ---- epilogue operands staged through shared memory with cp.async, one trip ahead (Dormand-Prince stages).
+// Every thread copies its own 16-byte operands into its own slots and reads them back itself: no barrier, only
+// cp.async.wait_group.  Nothing is held in registers while the trip computes (the register version kept up to 20).
+#ifndef OCCM_OPS_ASYNC
+#define OCCM_OPS_ASYNC 1
+#endif
+// Measured per stage (C4, B200): staging helps the stages with few operands (2: -1 %, 3: -1 %, 7: -9 %) and costs 2-5 % in
+// stages 4-6, whose operands then pass through 40 KB of shared memory per CTA: those keep the register version + L2 prefetch.
+template <int STAGE> struct OccmOpsAsync { static constexpr bool value = OCCM_OPS_ASYNC && (STAGE == 2 || STAGE == 3 || STAGE == 7); };
+template <int STAGE> struct OccmNops { static constexpr int value = STAGE == 2 ? 2 : STAGE == 3 ? 3 : STAGE == 4 ? 4 : STAGE == 5 ? 5 : STAGE == 6 ? 5 : STAGE == 7 ? 2 : 0; };
+#define OCCM_OPS_STRIDE (OCCM_FAST_BLOCK * 16)          // bytes between two operands of the ring (one 16-byte slot per thread)
+__device__ __forceinline__ void occm_cp16(unsigned sa, const double* g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(g) : "memory"); }
+template <unsigned OFF>
+__device__ __forceinline__ double2 occm_lds2_at(unsigned sa) { double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(sa), "n"(OFF)); return v; }
+
+// sa = this thread's slot of operand 0 in the ring buffer that belongs to the trip
+template <int STAGE>
+__device__ __forceinline__ void occm_fast_issue_ops(const OccmSysDev& sys, const OccmRkDev& rk, const OccmFastCtx<STAGE>& c, int e, unsigned sa) {
+    const long long g = (long long)c.m * sys.ndof + e;
+    occm_cp16(sa, rk.Y[c.par] + g);
+    if (STAGE != 7) occm_cp16(sa + OCCM_OPS_STRIDE, rk.KF[c.par] + g);
+    if (STAGE == 3) { occm_cp16(sa + 2 * OCCM_OPS_STRIDE, rk.K2 + g); }
+    if (STAGE == 4) { occm_cp16(sa + 2 * OCCM_OPS_STRIDE, rk.K2 + g); occm_cp16(sa + 3 * OCCM_OPS_STRIDE, rk.K3 + g); }
+    if (STAGE == 5) { occm_cp16(sa + 2 * OCCM_OPS_STRIDE, rk.K2 + g); occm_cp16(sa + 3 * OCCM_OPS_STRIDE, rk.K3 + g); occm_cp16(sa + 4 * OCCM_OPS_STRIDE, rk.K4 + g); }
+    if (STAGE == 6) { occm_cp16(sa + 2 * OCCM_OPS_STRIDE, rk.K3 + g); occm_cp16(sa + 3 * OCCM_OPS_STRIDE, rk.K4 + g); occm_cp16(sa + 4 * OCCM_OPS_STRIDE, rk.K5 + g); }
+    if (STAGE == 7) { occm_cp16(sa + OCCM_OPS_STRIDE, rk.K2 + g); }
+}
+template <int STAGE, unsigned RO>            // RO = byte offset of the trip's ring buffer
+__device__ __forceinline__ OccmOps2 occm_fast_read_ops(unsigned sa) {
+    OccmOps2 o;
+    const double2 z = make_double2(0.0, 0.0);
+    o.ye = o.k1 = o.ka = o.kb = o.kc = o.kd = z;
+    o.ye = occm_lds2_at<RO>(sa);
+    if (STAGE != 7) o.k1 = occm_lds2_at<RO + OCCM_OPS_STRIDE>(sa);
+    if (STAGE == 3) { o.ka = occm_lds2_at<RO + 2 * OCCM_OPS_STRIDE>(sa); }
+    if (STAGE == 4) { o.ka = occm_lds2_at<RO + 2 * OCCM_OPS_STRIDE>(sa); o.kb = occm_lds2_at<RO + 3 * OCCM_OPS_STRIDE>(sa); }
+    if (STAGE == 5 || STAGE == 6) { o.ka = occm_lds2_at<RO + 2 * OCCM_OPS_STRIDE>(sa); o.kb = occm_lds2_at<RO + 3 * OCCM_OPS_STRIDE>(sa); o.kc = occm_lds2_at<RO + 4 * OCCM_OPS_STRIDE>(sa); }
+    if (STAGE == 7) { o.ka = occm_lds2_at<RO + OCCM_OPS_STRIDE>(sa); }
+    return o;
 }
 
 // one species of the epilogue (same arithmetic as occm_finish); returns the squared scaled error in stage 7
@@ -191,12 +239,6 @@ struct OccmFastPre {          // everything of a trip that can be loaded before 
     double2 own; int4 ell[K]; int pt; int ci;
 };
 
-#ifndef OCCM_FAST_CTAS
-#define OCCM_FAST_CTAS 2
-#endif
-#ifndef OCCM_FAST_BLOCK
-#define OCCM_FAST_BLOCK 256        // threads per CTA of the fast kernels (the fix-up kernel keeps OCCM_BLOCK)
-#endif
 template <int MODEL, int STAGE, int K, int WIDE>
 __device__ __forceinline__ void
 occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk,
@@ -207,7 +249,10 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
     occm_load_tables(sys.tables, sys.tables_bytes, tab_s);
     const int S = sys.S, H = S >> 1, RS = S + 2;            // staged rows: S values + two 1.0 pads (keeps 16-byte alignment)
     double* tile = smem_d + (((sys.tables_bytes + 15) >> 4) << 1);   // two buffers [tcv][RS], OCCM_TILE_BUF_BYTES apart, 16-byte aligned
-    double* rxc_s = tile + 2 * (OCCM_TILE_BUF_BYTES / 8);                    // unscaled coefficients [S][OCCM_NT]  (WIDE: [S][nt_u])
+    constexpr bool ASYNC = OccmOpsAsync<STAGE>::value;
+    constexpr unsigned RING_BYTES = ASYNC ? OccmNops<STAGE>::value * OCCM_OPS_STRIDE : 0;      // one of the two operand buffers
+    double* ops_ring = tile + 2 * (OCCM_TILE_BUF_BYTES / 8);
+    double* rxc_s = ops_ring + 2 * (RING_BYTES / 8);                    // unscaled coefficients [S][OCCM_NT]  (WIDE: [S][nt_u])
     const int tid = threadIdx.x;
     const bool lane_on = tid < tcv * H;
     const int pl = tid / H;
@@ -245,6 +290,7 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
     const int n_points = (int)sys.n_points, N = n_points;     // ELL columns are [K][n_points] (CSTR: one point per model)
     const int my_tile = pl * RS + sp;
     const unsigned row0_sa = occm_opaque_u32((unsigned)__cvta_generic_to_shared(tile) + 8u * (unsigned)(pl * RS));   // this thread's row, buffer 0
+    const unsigned ops_sa = occm_opaque_u32((unsigned)__cvta_generic_to_shared(ops_ring) + 16u * (unsigned)tid);   // my slot of operand 0, buffer 0
     const unsigned cmw_sa = WIDE ? occm_opaque_u32((unsigned)__cvta_generic_to_shared(cmw_s)) : 0u;
     const unsigned mtw_sa = WIDE ? occm_opaque_u32((unsigned)__cvta_generic_to_shared(mtw_s)) : 0u;
     __syncthreads();
@@ -273,7 +319,7 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
 #pragma unroll
     for (int q = 0; q < OCCM_NT; ++q) { cm0[q] = 0.0; cm1[q] = 0.0; }
 
-    auto load = [&](OccmFastPre<STAGE, K>& pre, OccmFastCtx<STAGE>& cx) {
+    auto load = [&](OccmFastPre<STAGE, K>& pre, OccmFastCtx<STAGE>& cx, unsigned ring_off) {
         if (cx.m != m) cx = occm_fast_ctx<STAGE>(sys, mem, rk, m);
         pre.ci = ci;
         const int p = ci * tcv + pl;
@@ -283,9 +329,8 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
         pre.own = occm_fast_in<STAGE>(occm_fast_in_a<STAGE>(sys, rk, y_in, cx), occm_fast_in_b<STAGE>(sys, mem, rk, cx), cx.h, e);
 #pragma unroll
         for (int k = 0; k < K; ++k) pre.ell[k] = __ldg(reinterpret_cast<const int4*>(ell + (size_t)k * N + pp));
-#ifndef OCCM_NO_PREFETCH
-        if (pre.pt >= 0) occm_fast_prefetch_ops<STAGE>(sys, rk, cx, e);
-#endif
+        if (ASYNC) { if (pre.pt >= 0) occm_fast_issue_ops<STAGE>(sys, rk, cx, e, ops_sa + ring_off); }
+        else if (pre.pt >= 0) occm_fast_prefetch_ops<STAGE>(sys, rk, cx, e);
     };
 
     auto process = [&](const OccmFastPre<STAGE, K>& cur, const OccmFastCtx<STAGE>& cc, OccmFastPre<STAGE, K>& nxt,
@@ -296,8 +341,10 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
         // -12 % time).  The Dormand-Prince stages hold up to 20 operand registers: there the hoisting spilled (stage 5 +30 %),
         // so the row address is made opaque per trip and the slot offsets are added in the loop.
         const unsigned row_sa = STAGE <= 1 ? row0_sa : occm_opaque_u32(row0_sa);
-        // epilogue operands of THIS trip: needed last, so they have the whole trip to arrive
-        const OccmOps2 ops = occm_fast_load_ops<STAGE>(sys, rk, cc, (cur.pt >= 0 ? cur.pt : 0) * S + sp);
+        constexpr unsigned RO = (unsigned)buf * RING_BYTES;               // this trip's operand buffer; the next trip's is the other one
+        // register version: epilogue operands of THIS trip are requested here, they have the whole trip to arrive
+        OccmOps2 ops;
+        if (!ASYNC) ops = occm_fast_load_ops<STAGE>(sys, rk, cc, (cur.pt >= 0 ? cur.pt : 0) * S + sp);
         if (lane_on) occm_sts2_at<BO>(row_sa + 8u * sp, cur.own);
         if (WIDE) {                                     // uniform: this buffer's coefficient copy belongs to another member
             int& have = buf ? cmw_m1 : cmw_m0;
@@ -317,7 +364,8 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
 #pragma unroll
             for (int k = 0; k < K; ++k) g[k] = occm_fast_in<STAGE>(ga, gb, cc.h, cur.ell[k].x * S + sp);
         }
-        if (have_next) load(nxt, ncx);
+        if (have_next) load(nxt, ncx, RING_BYTES - RO);
+        if (ASYNC) asm volatile("cp.async.commit_group;" ::: "memory");     // exactly one group per trip (empty after the last one)
 
         if (!WIDE && coeff_m != cc.m) {                 // uniform: fold the member's rate-constant scales into the coefficients
 #pragma unroll
@@ -358,6 +406,10 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
                     const double na = -(cc.qs * __hiloint2double(cur.ell[0].w, cur.ell[0].z));
                     f = make_double2(__dadd_rn(__dmul_rn(na, cur.own.x - g[0].x), r0), __dadd_rn(__dmul_rn(na, cur.own.y - g[0].y), r1));
                 }
+                if (ASYNC) {
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");    // everything but the next trip's group has landed
+                    ops = occm_fast_read_ops<STAGE, RO>(ops_sa);
+                }
                 err2 = occm_fast_finish<STAGE>(sys, rk, cc, ops, f, cur.own, cur.pt * S + sp, dy_out);
             }   // flagged rows (boundary / pulse / overflow entries) are left to occm_fixup, launched right after
         }
@@ -370,7 +422,7 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
     };
 
     bool valid = skip();
-    if (valid) load(A, cxA);
+    if (valid) { load(A, cxA, 0u); if (ASYNC) asm volatile("cp.async.commit_group;" ::: "memory"); }
     while (valid) {
         bool vn = advance();                 // (m, ci) now name the next trip
         process(A, cxA, B, cxB, vn, std::integral_constant<int, 0>{});

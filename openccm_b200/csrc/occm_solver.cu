@@ -636,7 +636,8 @@ static int occm_launch_fast(const occm_system* sys, const OccmMemDev& mem, const
     const int S = sys->dev.S, tcv = OCCM_FAST_BLOCK / (S / 2);
     const size_t nw = (size_t)S * sys->max_terms;          // WIDE: unscaled + two scaled coefficient copies + meta words
     const size_t smem = (((size_t)sys->dev.tables_bytes + 15) & ~(size_t)15) +
-                        sizeof(double) * ((size_t)2 * (OCCM_TILE_BUF_BYTES / 8) + (WIDE ? 3 * nw + (nw + 1) / 2 : (size_t)S * OCCM_NT) + 40);
+                        sizeof(double) * ((size_t)2 * (OCCM_TILE_BUF_BYTES / 8) + (WIDE ? 3 * nw + (nw + 1) / 2 : (size_t)S * OCCM_NT) + 40) +
+                        (OccmOpsAsync<STAGE>::value ? (size_t)2 * OccmNops<STAGE>::value * OCCM_OPS_STRIDE : 0);
     auto kern = occm_fast_kernel<MODEL, STAGE, K, WIDE>();
     if (smem > smem_limit) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_limit = smem; }
     if (ctas_per_sm == 0) {

@@ -142,19 +142,35 @@ __global__ void __launch_bounds__(256) bdf_change_D(const OccmBdfDev b) {
     }
 }
 
+// The order is uniform per member: the element loops are instantiated per order so that the difference rows live in
+// registers (a runtime-indexed array went to local memory) and gamma_i is folded at compile time.
+template <int O>
+__device__ __forceinline__ void bdf_predict_elems(const OccmBdfDev& b, int m, int ci) {
+    double gam[O + 1];
+#pragma unroll
+    for (int i = 0; i <= O; ++i) gam[i] = bdf_gamma(i);
+    const double inv_alpha = 1.0 / bdf_alpha(O);
+    BDF_ELEMS(b, ci, e) {
+        const long long g = (long long)m * b.ndof + e;
+        double yp = b.D[g], ps = 0.0;
+#pragma unroll
+        for (int i = 1; i <= O; ++i) {
+            const double di = b.D[i * b.vstride + g];
+            yp += di;
+            ps += di * gam[i];
+        }
+        b.y[g] = yp; b.psi[g] = ps * inv_alpha; b.d[g] = 0.0;
+    }
+}
+
 __global__ void __launch_bounds__(256) bdf_predict(const OccmBdfDev b) {      // bdf.py:358-362
     BDF_FOR_CHUNKS(b, b.status[m] == OCCM_MEMBER_RUNNING) {
-        const int o = b.order[m];
-        const double inv_alpha = 1.0 / bdf_alpha(o);
-        BDF_ELEMS(b, ci, e) {
-            const long long g = (long long)m * b.ndof + e;
-            double yp = b.D[g], ps = 0.0;
-            for (int i = 1; i <= o; ++i) {
-                const double di = b.D[i * b.vstride + g];
-                yp += di;
-                ps += di * bdf_gamma(i);
-            }
-            b.y[g] = yp; b.psi[g] = ps * inv_alpha; b.d[g] = 0.0;
+        switch (b.order[m]) {
+            case 1: bdf_predict_elems<1>(b, m, ci); break;
+            case 2: bdf_predict_elems<2>(b, m, ci); break;
+            case 3: bdf_predict_elems<3>(b, m, ci); break;
+            case 4: bdf_predict_elems<4>(b, m, ci); break;
+            default: bdf_predict_elems<5>(b, m, ci); break;
         }
     }
 }
@@ -563,24 +579,38 @@ __global__ void __launch_bounds__(256) bdf_error(const OccmBdfDev b) {
 
 // accepted step: D[o+2] = d - D[o+1]; D[o+1] = d; D[i] += D[i+1] (i = o..0);                      (bdf.py:419-422)
 // partial[0] = |error_const[o-1] D[o] / scale|^2, partial[1] = |error_const[o+1] D[o+2] / scale|^2   (:427-437)
+template <int O>
+__device__ __forceinline__ void bdf_update_D_elems(const OccmBdfDev& b, int m, int ci, double ecm, double ecp, double& s0, double& s1) {
+    BDF_ELEMS(b, ci, e) {
+        const long long g = (long long)m * b.ndof + e;
+        const double d = b.d[g];
+        double Dv[O + 3];
+#pragma unroll
+        for (int i = 0; i <= O + 1; ++i) Dv[i] = b.D[i * b.vstride + g];
+        Dv[O + 2] = d - Dv[O + 1];
+        Dv[O + 1] = d;
+#pragma unroll
+        for (int i = O; i >= 0; --i) Dv[i] += Dv[i + 1];
+#pragma unroll
+        for (int i = 0; i <= O + 2; ++i) b.D[i * b.vstride + g] = Dv[i];
+        const double scale = b.atol + b.rtol * fabs(b.y[g]);
+        const double qm = ecm * Dv[O] / scale, qp = ecp * Dv[O + 2] / scale;
+        s0 += qm * qm; s1 += qp * qp;
+    }
+}
+
 __global__ void __launch_bounds__(256) bdf_update_D(const OccmBdfDev b) {
     __shared__ double scratch[8];
     BDF_FOR_CHUNKS(b, b.accepted_now[m]) {
         const int o = b.order[m];
         const double ecm = o > 1 ? bdf_error_const(o - 1) : 0.0, ecp = o < BDF_MAX_ORDER ? bdf_error_const(o + 1) : 0.0;
         double s0 = 0.0, s1 = 0.0;
-        BDF_ELEMS(b, ci, e) {
-            const long long g = (long long)m * b.ndof + e;
-            const double d = b.d[g];
-            double Dv[BDF_NVEC_D];
-            for (int i = 0; i <= o + 1; ++i) Dv[i] = b.D[i * b.vstride + g];
-            Dv[o + 2] = d - Dv[o + 1];
-            Dv[o + 1] = d;
-            for (int i = o; i >= 0; --i) Dv[i] += Dv[i + 1];
-            for (int i = 0; i <= o + 2; ++i) b.D[i * b.vstride + g] = Dv[i];
-            const double scale = b.atol + b.rtol * fabs(b.y[g]);
-            const double qm = ecm * Dv[o] / scale, qp = ecp * Dv[o + 2] / scale;
-            s0 += qm * qm; s1 += qp * qp;
+        switch (o) {
+            case 1: bdf_update_D_elems<1>(b, m, ci, ecm, ecp, s0, s1); break;
+            case 2: bdf_update_D_elems<2>(b, m, ci, ecm, ecp, s0, s1); break;
+            case 3: bdf_update_D_elems<3>(b, m, ci, ecm, ecp, s0, s1); break;
+            case 4: bdf_update_D_elems<4>(b, m, ci, ecm, ecp, s0, s1); break;
+            default: bdf_update_D_elems<5>(b, m, ci, ecm, ecp, s0, s1); break;
         }
         const double t0 = occm_block_sum(s0, scratch), t1 = occm_block_sum(s1, scratch);
         if (threadIdx.x == 0) { b.partial[BDF_PIDX(b, m, ci, 0)] = t0; b.partial[BDF_PIDX(b, m, ci, 1)] = t1; }

@@ -119,3 +119,77 @@ def test_wide_mechanism_vs_oracle(model, tmp_path, monkeypatch):
         scale = max(1.0, np.abs(ref).max())
         np.testing.assert_allclose(host.to_reference_layout(fast[m]), ref, rtol=1e-11, atol=1e-12 * scale)
         np.testing.assert_allclose(host.to_reference_layout(generic[m]), ref, rtol=1e-11, atol=1e-12 * scale)
+
+
+def _random_mechanism(n_species, n_reactions, max_order, seed):
+    """Reactions file text: random reactants (total order <= max_order, stoichiometric coefficients 1..2), 1-2 products."""
+    from openccm_b200 import synthetic as syn
+    rng = np.random.default_rng(seed)
+    names = syn.species_names(n_species)
+    lines_r, lines_k, used = ['[REACTIONS]'], ['[RATE CONSTANTS]'], set()
+
+    def side(idx, coeffs):
+        return ' + '.join((f'{c}' if c > 1 else '') + names[i] for i, c in zip(idx, coeffs))
+    r = 0
+    for _ in range(n_reactions):
+        n_react = int(rng.integers(1, 3))
+        reactants = rng.choice(n_species, size=n_react, replace=False)
+        coeffs = [1] * n_react
+        while sum(coeffs) < max_order and rng.random() < 0.5:
+            coeffs[int(rng.integers(0, n_react))] += 1
+        rest = [i for i in range(n_species) if i not in reactants]
+        products = rng.choice(rest, size=min(len(rest), int(rng.integers(1, 3))), replace=False)
+        r += 1
+        lines_r.append(f'R{r}: {side(reactants, coeffs)} -> {side(products, [int(rng.integers(1, 3)) for _ in products])}')
+        lines_k.append(f'R{r}: {10 ** rng.uniform(-1.5, 0.5):.6e}')
+        used.update(int(i) for i in reactants); used.update(int(i) for i in products)
+    for s in range(n_species):
+        if s not in used:
+            r += 1
+            lines_r.append(f'R{r}: {names[s]} -> {names[(s + 1) % n_species]}')
+            lines_k.append(f'R{r}: 0.3')
+    return names, '\n'.join(lines_r) + '\n\n' + '\n'.join(lines_k) + '\n'
+
+
+@pytest.mark.parametrize('model,n_species,n_reactions,max_order,seed', [
+    ('cstr', 2, 1, 1, 0), ('cstr', 2, 2, 2, 1), ('cstr', 4, 3, 3, 2), ('cstr', 6, 9, 3, 3), ('cstr', 16, 12, 2, 4),
+    ('pfr', 2, 1, 2, 5), ('pfr', 4, 6, 3, 6), ('pfr', 8, 14, 2, 7), ('pfr', 6, 2, 1, 8), ('cstr', 3, 4, 3, 9)])
+def test_random_mechanisms_all_kernel_forms(model, n_species, n_reactions, max_order, seed, tmp_path, monkeypatch):
+    """Random mechanisms (orders 1..3, short and long term lists, even and odd species counts) on random networks: every
+    kernel form the dispatcher can pick — register lists, shared-memory lists, generic table walk — against the oracle."""
+    import torch
+    from oracle import openccm_oracle as O
+    from openccm_b200 import synthetic as syn
+    from openccm_b200.device import DeviceSystem
+    from openccm_b200.system_solvers.export import export_system
+    from openccm_b200.workloads import _cmesh, _config
+    species, text = _random_mechanism(n_species, n_reactions, max_order, seed)
+    path = tmp_path / 'rxn'
+    path.write_text(text)
+    n_models = 30 if model == 'cstr' else 9
+    net = syn.random_network(n_models, n_io=2, seed=seed + 20, elements_per_model=2 if model == 'pfr' else 1)
+    cp = _config(model, species, str(path), t_span=(0, 1.0), t_eval='0.5, linear', P=7)
+    cmesh = _cmesh(cp, n_models * (2 if model == 'pfr' else 1), seed)
+    mn = net.to_model_network()
+    host = export_system(model, mn, cp, cmesh)
+    ora = O.build_system(model, mn, cp, cmesh)
+    rng = np.random.default_rng(seed)
+    M = 3
+    ys = np.abs(rng.normal(0.6, 0.3, (M, host.ndof)))
+    yd = torch.as_tensor(host.to_device_layout(ys), device='cuda')
+    ts = torch.zeros(M, dtype=torch.float64, device='cuda')
+    outs = {}
+    for mode in ('fast', 'wide', 'generic'):
+        monkeypatch.delenv('OCCM_B200_NO_FAST', raising=False)
+        monkeypatch.delenv('OCCM_B200_FORCE_WIDE', raising=False)
+        if mode == 'generic':
+            monkeypatch.setenv('OCCM_B200_NO_FAST', '1')
+        if mode == 'wide':
+            monkeypatch.setenv('OCCM_B200_FORCE_WIDE', '1')
+        outs[mode] = DeviceSystem(host).rhs(yd, ts).cpu().numpy()
+    for m in range(M):
+        ref = ora.fun(0.0, ys[m].copy())
+        scale = max(1.0, np.abs(ref).max())
+        for mode, out in outs.items():
+            np.testing.assert_allclose(host.to_reference_layout(out[m]), ref, rtol=1e-11, atol=1e-12 * scale, err_msg=mode)
+    np.testing.assert_array_equal(outs['fast'], outs['wide'])

@@ -188,6 +188,35 @@ def vtu_golden(name: str) -> None:
     print(f'[golden] vtu_{name}: fields{fields.shape} unmapped {(fields[0, 0] == -1).sum()}')
 
 
+FLOW_CASES = ((8, 1), (40, 2), (300, 3), (1500, 4))
+
+
+def flow_case(n: int, seed: int):
+    """Inputs of a flow-balancing case (shared with tests/test_flow_balance.py): a random network whose flows are perturbed
+    by 0.1 % so that no model conserves mass."""
+    from types import SimpleNamespace
+    from openccm_b200 import synthetic as syn
+    net = syn.random_network(n, n_io=2, seed=seed)
+    conn = net.to_model_network()[0]
+    rng = np.random.default_rng(seed)
+    flows = net.flows * (1 + 1e-3 * rng.standard_normal(net.flows.shape))
+    ids_in = sorted({o for (i, _) in conn.values() for o in i.values() if o < 0})
+    ids_out = sorted({o for (_, oo) in conn.values() for o in oo.values() if o < 0})
+    return conn, flows, SimpleNamespace(domain_inlets=tuple(ids_in), domain_outlets=tuple(ids_out))
+
+
+def flows_golden() -> None:
+    """f-2: volumetric flows after the UNMODIFIED `tweak_final_flows` (helpers.py:268-438)."""
+    from openccm.compartment_models.helpers import tweak_final_flows
+    out = {}
+    for n, seed in FLOW_CASES:
+        conn, flows, gb = flow_case(n, seed)
+        tweak_final_flows(conn, flows, gb, 1e-9)
+        out[f'flows_{n}_{seed}'] = flows
+    np.savez_compressed(os.path.join(HERE, 'flow_balance.npz'), **out)
+    print('[golden] flow_balance.npz: ' + ', '.join(f'{k}{v.shape}' for k, v in out.items()))
+
+
 def openfoam_cstr_fixture() -> None:
     """C3: the same OpenFOAM 2-D example compartmentalised with model = CSTR (76 CSTRs); network + geometry fixture."""
     import openccm
@@ -261,6 +290,11 @@ if __name__ == '__main__':
     if '--openfoam-cstr-fixture' in argv:
         argv.remove('--openfoam-cstr-fixture')
         openfoam_cstr_fixture()
+    if '--flows' in argv:
+        argv.remove('--flows')
+        flows_golden()
+        if not argv:
+            sys.exit(0)
     if '--vtu' in argv:
         argv.remove('--vtu')
         for n in VTU_CASES:

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(CSRC, '_obj')
 LIB = os.path.join(CSRC, 'liboccm_b200.so')
-NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC'] + \
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC', '-diag-suppress', '177'] + \
     os.environ.get('OCCM_NVCC_EXTRA', '').split()          # experiments: e.g. OCCM_NVCC_EXTRA='-DOCCM_FAST_BLOCK=128 -DOCCM_FAST_CTAS=4'
 N_STAGES = 8
 

@@ -232,21 +232,6 @@ __device__ __forceinline__ double occm_reaction_fast(const double (&coeffm)[OCCM
     return acc;
 }
 
-// the same evaluation with the species' term list in shared memory (mechanisms with more than OCCM_NT terms per species):
-// c = coefficients already scaled by the member's k_scale, mt = meta words, nt = mechanism-wide maximum (padded lists)
-__device__ __forceinline__ double occm_reaction_wide(const double* c, const unsigned* mt, const double* row, int nt, int nf_u) {
-    double acc = 0.0;
-    for (int i = 0; i < nt; ++i) {
-        const unsigned m = mt[i];
-        double v = c[i];
-        if (nf_u > 0) v = __dmul_rn(v, row[(m >> 8) & 0xffu]);
-        if (nf_u > 1) v = __dmul_rn(v, row[(m >> 16) & 0xffu]);
-        if (nf_u > 2) v = __dmul_rn(v, row[m >> 24]);
-        acc = __dadd_rn(acc, v);
-    }
-    return acc;
-}
-
 __device__ __forceinline__ double occm_pulses(const OccmSysDev& sys, const OccmTab& T, int model, int s, double t) {
     double acc = 0.0;
     if (sys.pulse_ptr) {

@@ -193,7 +193,6 @@ __device__ __forceinline__ double occm_fast_finish(const OccmSysDev& sys, const 
 __device__ __forceinline__ unsigned occm_opaque_u32(unsigned v) { asm volatile("" : "+r"(v)); return v; }
 __device__ __forceinline__ double occm_lds_f64(unsigned sa) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sa)); return v; }
 __device__ __forceinline__ unsigned occm_lds_u32(unsigned sa) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa)); return v; }
-__device__ __forceinline__ void occm_sts2(unsigned sa, double2 v) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(sa), "d"(v.x), "d"(v.y) : "memory"); }
 // the same with a compile-time byte offset folded into the instruction: the two tile buffers sit OCCM_TILE_BUF_BYTES apart, so
 // the per-thread slot addresses are loop invariants (the compiler keeps as many of them in registers as it can afford)
 template <unsigned OFF>
@@ -288,7 +287,6 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
         row[S] = 1.0; row[S + 1] = 1.0;
     }
     const int n_points = (int)sys.n_points, N = n_points;     // ELL columns are [K][n_points] (CSTR: one point per model)
-    const int my_tile = pl * RS + sp;
     const unsigned row0_sa = occm_opaque_u32((unsigned)__cvta_generic_to_shared(tile) + 8u * (unsigned)(pl * RS));   // this thread's row, buffer 0
     const unsigned ops_sa = occm_opaque_u32((unsigned)__cvta_generic_to_shared(ops_ring) + 16u * (unsigned)tid);   // my slot of operand 0, buffer 0
     const unsigned cmw_sa = WIDE ? occm_opaque_u32((unsigned)__cvta_generic_to_shared(cmw_s)) : 0u;

@@ -14,7 +14,8 @@
 //   * straight-line code templated on K, 32-bit element offsets against per-member base pointers;
 //   * software pipelining: while a trip computes, the own values, epilogue operands and ELL entries of the CTA's
 //     NEXT trip are already in flight (registers), so only the L2 latency of the row gathers is exposed;
-//   * the staged tile is double buffered: one __syncthreads per trip.
+//   * the staged tile is double buffered: one barrier per trip — a __syncwarp in the light stages, where a warp owns whole
+//     points (OccmWarpMap), a __syncthreads in the dense block mapping of stages 3-6.
 #pragma once
 #include <type_traits>
 
@@ -116,6 +117,7 @@ __device__ __forceinline__ void occm_fast_prefetch_ops(const OccmSysDev& sys, co
 // Measured per stage (C4, B200): staging helps the stages with few operands (2: -1 %, 3: -1 %, 7: -9 %) and costs 2-5 % in
 // stages 4-6, whose operands then pass through 40 KB of shared memory per CTA: those keep the register version + L2 prefetch.
 template <int STAGE> struct OccmOpsAsync { static constexpr bool value = OCCM_OPS_ASYNC && (STAGE == 2 || STAGE == 3 || STAGE == 7); };
+template <int STAGE> struct OccmWarpMap { static constexpr bool value = STAGE <= 2 || STAGE == 7; };
 template <int STAGE> struct OccmNops { static constexpr int value = STAGE == 2 ? 2 : STAGE == 3 ? 3 : STAGE == 4 ? 4 : STAGE == 5 ? 5 : STAGE == 6 ? 5 : STAGE == 7 ? 2 : 0; };
 #define OCCM_OPS_STRIDE (OCCM_FAST_BLOCK * 16)          // bytes between two operands of the ring (one 16-byte slot per thread)
 __device__ __forceinline__ void occm_cp16(unsigned sa, const double* g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(g) : "memory"); }
@@ -253,9 +255,17 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
     double* ops_ring = tile + 2 * (OCCM_TILE_BUF_BYTES / 8);
     double* rxc_s = ops_ring + 2 * (RING_BYTES / 8);                    // unscaled coefficients [S][OCCM_NT]  (WIDE: [S][nt_u])
     const int tid = threadIdx.x;
-    const bool lane_on = tid < tcv * H;
-    const int pl = tid / H;
-    const int sp = 2 * (tid - pl * H);
+    // Warp-autonomous mapping: a warp owns 32 / H whole points (H = S / 2 threads per point), so the staged rows a thread
+    // reads were written by its own warp and the per-trip barrier is a __syncwarp (the block barrier cost 15 % of the issue
+    // slots in stalls).  The 32 % H left-over lanes of a warp idle (S = 10: 2 of 32).
+    // Measured per stage (C4): the light stages gain (stage 2 -10 %, stage 7 -3 %, plain RHS -3 %), the operand-heavy stages
+    // 3-6 lose the 6 % of idle lanes, so those keep the dense block mapping and the block barrier (OccmWarpMap).
+    constexpr bool WARPMAP = OccmWarpMap<STAGE>::value && !WIDE;
+    const int lane_w = tid & 31, pw = lane_w / H;
+    const int ppw = 32 / H;                                   // points per warp and trip
+    const bool lane_on = WARPMAP ? pw < ppw : tid < tcv * H;
+    const int pl = WARPMAP ? (tid >> 5) * ppw + pw : tid / H;
+    const int sp = WARPMAP ? 2 * (lane_w - pw * H) : 2 * (tid - pl * H);
     const int nt_u = tab_s[OCCM_H_MAX_TERMS], nf_u = tab_s[OCCM_H_MAX_SLOTS];
     // WIDE: term lists of every species in shared memory, coefficients scaled per member in a double-buffered copy
     const int NW = S * nt_u;
@@ -279,7 +289,7 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
 #pragma unroll
         for (int q = 0; q < OCCM_NT; ++q) {
             meta0[q] = R0.meta[q]; meta1[q] = R1.meta[q];
-            if (lane_on && pl == 0) { rxc_s[sp * OCCM_NT + q] = R0.coeff[q]; rxc_s[(sp + 1) * OCCM_NT + q] = R1.coeff[q]; }
+            if (lane_on && pl == 0) { rxc_s[sp * OCCM_NT + q] = R0.coeff[q]; rxc_s[(sp + 1) * OCCM_NT + q] = R1.coeff[q]; }   // warp 0, first point
         }
     }
     for (int r = tid; r < 2 * tcv; r += OCCM_FAST_BLOCK) {
@@ -353,7 +363,8 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
                 have = cc.m;
             }
         }
-        __syncthreads();
+        if (WARPMAP) __syncwarp();      // the staged rows of a warp's points are written and read by that warp only
+        else __syncthreads();
         // ---- row gathers (L2 hits), then the next trip's loads: both fly while the reactions are evaluated
         double2 g[K];
         {

@@ -633,7 +633,9 @@ static int occm_launch_fast(const occm_system* sys, const OccmMemDev& mem, const
                             double t_scalar, const double* y_in, double* dy_out, cudaStream_t st, int* cpm_out) {
     static size_t smem_limit = 48 * 1024;
     static int ctas_per_sm = 0;
-    const int S = sys->dev.S, tcv = OCCM_FAST_BLOCK / (S / 2);
+    const int S = sys->dev.S;
+    const int tcv = (OccmWarpMap<STAGE>::value && !WIDE) ? (OCCM_FAST_BLOCK / 32) * (32 / (S / 2))      // a warp owns 32 / (S/2) whole points
+                                                          : OCCM_FAST_BLOCK / (S / 2);
     const size_t nw = (size_t)S * sys->max_terms;          // WIDE: unscaled + two scaled coefficient copies + meta words
     const size_t smem = (((size_t)sys->dev.tables_bytes + 15) & ~(size_t)15) +
                         sizeof(double) * ((size_t)2 * (OCCM_TILE_BUF_BYTES / 8) + (WIDE ? 3 * nw + (nw + 1) / 2 : (size_t)S * OCCM_NT) + 40) +

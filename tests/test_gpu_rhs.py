@@ -153,7 +153,8 @@ def _random_mechanism(n_species, n_reactions, max_order, seed):
 
 @pytest.mark.parametrize('model,n_species,n_reactions,max_order,seed', [
     ('cstr', 2, 1, 1, 0), ('cstr', 2, 2, 2, 1), ('cstr', 4, 3, 3, 2), ('cstr', 6, 9, 3, 3), ('cstr', 16, 12, 2, 4),
-    ('pfr', 2, 1, 2, 5), ('pfr', 4, 6, 3, 6), ('pfr', 8, 14, 2, 7), ('pfr', 6, 2, 1, 8), ('cstr', 3, 4, 3, 9)])
+    ('pfr', 2, 1, 2, 5), ('pfr', 4, 6, 3, 6), ('pfr', 8, 14, 2, 7), ('pfr', 6, 2, 1, 8), ('cstr', 3, 4, 3, 9),
+    ('cstr', 34, 24, 2, 10), ('cstr', 64, 40, 2, 11), ('pfr', 22, 30, 3, 12)])
 def test_random_mechanisms_all_kernel_forms(model, n_species, n_reactions, max_order, seed, tmp_path, monkeypatch):
     """Random mechanisms (orders 1..3, short and long term lists, even and odd species counts) on random networks: every
     kernel form the dispatcher can pick — register lists, shared-memory lists, generic table walk — against the oracle."""

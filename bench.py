@@ -262,6 +262,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world_size > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     lib = _lib.load()
     # nvidia-smi takes seconds to attach (NVML init) and perturbs the GPU while it does (measured: +15..40 % on the solves

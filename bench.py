@@ -241,12 +241,33 @@ def run_reference_arm(args):
             "config": {"workload": WORKLOAD, "members_per_step": n, "note": "bounded sample of the ensemble per step"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ device arm
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Everything any library writes to fd 1 from here on (NCCL prints its version banner there) goes to stderr; the one JSON
+    line of the contract is written to the original stdout by `_emit`."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse_args()
+    _claim_stdout()
     if args.impl == 'reference':
         run_reference_arm(args)
         return
@@ -262,8 +283,6 @@ def main():
     torch.cuda.set_device(local_rank)
     if world_size > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     lib = _lib.load()
     # nvidia-smi takes seconds to attach (NVML init) and perturbs the GPU while it does (measured: +15..40 % on the solves
@@ -431,7 +450,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "solves_per_s": M_glob * args.steps / float(t_e.item())},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "plain_rhs": plain, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        _emit(line)
     if world_size > 1:
         dist.destroy_process_group()
 

@@ -1,6 +1,6 @@
 // Fast path of the fused stage kernels (included by occm_solver.cu after the generic kernel).
 //
-// Preconditions (checked on the host, otherwise the generic occm_stage kernel runs): even species count S, mechanism
+// Preconditions (checked on the host, otherwise the generic occm_stage kernel runs): mechanism
 // in register form (fast_ok: <= 4 terms per species; WIDE = 1 keeps longer term lists in shared memory instead), packed
 // ELL operator of width K <= 4, ndof and all member offsets 16-byte aligned.
 // CSTR networks: dy = qs * sum_k w_k y[src_k] + r(y).  PFR networks use the same kernel body with a one-entry row per
@@ -30,8 +30,17 @@ struct __align__(16) OccmEllEntry { int src; int flag; double w; };
 
 struct OccmOps2 { double2 ye, k1, ka, kb, kc, kd; };
 
-__device__ __forceinline__ double2 occm_ld2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
-__device__ __forceinline__ void occm_st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+// V = values per thread: 2 = two adjacent species (128-bit accesses), 1 = one species (odd species counts: 64-bit accesses, the
+// .y lane of every double2 is dead code)
+template <int V>
+__device__ __forceinline__ double2 occm_ld2(const double* p) {
+    if (V == 2) return __ldg(reinterpret_cast<const double2*>(p));
+    return make_double2(__ldg(p), 0.0);
+}
+template <int V>
+__device__ __forceinline__ void occm_st2(double* p, double2 v) {
+    if (V == 2) *reinterpret_cast<double2*>(p) = v; else *p = v.x;
+}
 __device__ __forceinline__ double2 occm_fma2(double a, double2 x, double2 y) { return make_double2(fma(a, x.x, y.x), fma(a, x.y, y.y)); }
 
 // Per-member context of a trip.  Only the values that cost a global load are kept (6 registers); the array pointers
@@ -67,28 +76,28 @@ __device__ __forceinline__ const double* occm_fast_in_b(const OccmSysDev& sys, c
     return STAGE == 1 ? mem.z + base : rk.KF[c.par] + base;
 }
 
-template <int STAGE>
+template <int STAGE, int V>
 __device__ __forceinline__ double2 occm_fast_in(const double* in_a, const double* in_b, double hb, int e) {
-    const double2 a = occm_ld2(in_a + e);
-    if (STAGE == 2) { const double2 b = occm_ld2(in_b + e); return make_double2(a.x + (dp::A21 * b.x) * hb, a.y + (dp::A21 * b.y) * hb); }
-    if (STAGE == 1) { const double2 b = occm_ld2(in_b + e); return make_double2(a.x + b.x * hb, a.y + b.y * hb); }
+    const double2 a = occm_ld2<V>(in_a + e);
+    if (STAGE == 2) { const double2 b = occm_ld2<V>(in_b + e); return make_double2(a.x + (dp::A21 * b.x) * hb, a.y + (dp::A21 * b.y) * hb); }
+    if (STAGE == 1) { const double2 b = occm_ld2<V>(in_b + e); return make_double2(a.x + b.x * hb, a.y + b.y * hb); }
     return a;
 }
 
-template <int STAGE>
+template <int STAGE, int V>
 __device__ __forceinline__ OccmOps2 occm_fast_load_ops(const OccmSysDev& sys, const OccmRkDev& rk, const OccmFastCtx<STAGE>& c, int e) {
     OccmOps2 o;
     const double2 z = make_double2(0.0, 0.0);
     o.ye = o.k1 = o.ka = o.kb = o.kc = o.kd = z;
     if (STAGE <= 1) return o;
     const long long g = (long long)c.m * sys.ndof + e;
-    o.ye = occm_ld2(rk.Y[c.par] + g);
-    if (STAGE != 7) o.k1 = occm_ld2(rk.KF[c.par] + g);
-    if (STAGE == 3) { o.ka = occm_ld2(rk.K2 + g); }
-    if (STAGE == 4) { o.ka = occm_ld2(rk.K2 + g); o.kb = occm_ld2(rk.K3 + g); }
-    if (STAGE == 5) { o.ka = occm_ld2(rk.K2 + g); o.kb = occm_ld2(rk.K3 + g); o.kc = occm_ld2(rk.K4 + g); }
-    if (STAGE == 6) { o.ka = occm_ld2(rk.K3 + g); o.kb = occm_ld2(rk.K4 + g); o.kc = occm_ld2(rk.K5 + g); }
-    if (STAGE == 7) { o.ka = occm_ld2(rk.K2 + g); }        // partial error combination written by stage 6
+    o.ye = occm_ld2<V>(rk.Y[c.par] + g);
+    if (STAGE != 7) o.k1 = occm_ld2<V>(rk.KF[c.par] + g);
+    if (STAGE == 3) { o.ka = occm_ld2<V>(rk.K2 + g); }
+    if (STAGE == 4) { o.ka = occm_ld2<V>(rk.K2 + g); o.kb = occm_ld2<V>(rk.K3 + g); }
+    if (STAGE == 5) { o.ka = occm_ld2<V>(rk.K2 + g); o.kb = occm_ld2<V>(rk.K3 + g); o.kc = occm_ld2<V>(rk.K4 + g); }
+    if (STAGE == 6) { o.ka = occm_ld2<V>(rk.K3 + g); o.kb = occm_ld2<V>(rk.K4 + g); o.kc = occm_ld2<V>(rk.K5 + g); }
+    if (STAGE == 7) { o.ka = occm_ld2<V>(rk.K2 + g); }        // partial error combination written by stage 6
     return o;
 }
 
@@ -120,33 +129,42 @@ template <int STAGE> struct OccmOpsAsync { static constexpr bool value = OCCM_OP
 template <int STAGE> struct OccmWarpMap { static constexpr bool value = STAGE <= 2 || STAGE == 7; };
 template <int STAGE> struct OccmNops { static constexpr int value = STAGE == 2 ? 2 : STAGE == 3 ? 3 : STAGE == 4 ? 4 : STAGE == 5 ? 5 : STAGE == 6 ? 5 : STAGE == 7 ? 2 : 0; };
 #define OCCM_OPS_STRIDE (OCCM_FAST_BLOCK * 16)          // bytes between two operands of the ring (one 16-byte slot per thread)
-__device__ __forceinline__ void occm_cp16(unsigned sa, const double* g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(g) : "memory"); }
-template <unsigned OFF>
-__device__ __forceinline__ double2 occm_lds2_at(unsigned sa) { double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(sa), "n"(OFF)); return v; }
+template <int V>
+__device__ __forceinline__ void occm_cp16(unsigned sa, const double* g) {
+    if (V == 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(g) : "memory");
+    else        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sa), "l"(g) : "memory");
+}
+template <unsigned OFF, int V>
+__device__ __forceinline__ double2 occm_lds2_at(unsigned sa) {
+    double2 v;
+    if (V == 2) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(sa), "n"(OFF));
+    else { asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v.x) : "r"(sa), "n"(OFF)); v.y = 0.0; }
+    return v;
+}
 
 // sa = this thread's slot of operand 0 in the ring buffer that belongs to the trip
-template <int STAGE>
+template <int STAGE, int V>
 __device__ __forceinline__ void occm_fast_issue_ops(const OccmSysDev& sys, const OccmRkDev& rk, const OccmFastCtx<STAGE>& c, int e, unsigned sa) {
     const long long g = (long long)c.m * sys.ndof + e;
-    occm_cp16(sa, rk.Y[c.par] + g);
-    if (STAGE != 7) occm_cp16(sa + OCCM_OPS_STRIDE, rk.KF[c.par] + g);
-    if (STAGE == 3) { occm_cp16(sa + 2 * OCCM_OPS_STRIDE, rk.K2 + g); }
-    if (STAGE == 4) { occm_cp16(sa + 2 * OCCM_OPS_STRIDE, rk.K2 + g); occm_cp16(sa + 3 * OCCM_OPS_STRIDE, rk.K3 + g); }
-    if (STAGE == 5) { occm_cp16(sa + 2 * OCCM_OPS_STRIDE, rk.K2 + g); occm_cp16(sa + 3 * OCCM_OPS_STRIDE, rk.K3 + g); occm_cp16(sa + 4 * OCCM_OPS_STRIDE, rk.K4 + g); }
-    if (STAGE == 6) { occm_cp16(sa + 2 * OCCM_OPS_STRIDE, rk.K3 + g); occm_cp16(sa + 3 * OCCM_OPS_STRIDE, rk.K4 + g); occm_cp16(sa + 4 * OCCM_OPS_STRIDE, rk.K5 + g); }
-    if (STAGE == 7) { occm_cp16(sa + OCCM_OPS_STRIDE, rk.K2 + g); }
+    occm_cp16<V>(sa, rk.Y[c.par] + g);
+    if (STAGE != 7) occm_cp16<V>(sa + OCCM_OPS_STRIDE, rk.KF[c.par] + g);
+    if (STAGE == 3) { occm_cp16<V>(sa + 2 * OCCM_OPS_STRIDE, rk.K2 + g); }
+    if (STAGE == 4) { occm_cp16<V>(sa + 2 * OCCM_OPS_STRIDE, rk.K2 + g); occm_cp16<V>(sa + 3 * OCCM_OPS_STRIDE, rk.K3 + g); }
+    if (STAGE == 5) { occm_cp16<V>(sa + 2 * OCCM_OPS_STRIDE, rk.K2 + g); occm_cp16<V>(sa + 3 * OCCM_OPS_STRIDE, rk.K3 + g); occm_cp16<V>(sa + 4 * OCCM_OPS_STRIDE, rk.K4 + g); }
+    if (STAGE == 6) { occm_cp16<V>(sa + 2 * OCCM_OPS_STRIDE, rk.K3 + g); occm_cp16<V>(sa + 3 * OCCM_OPS_STRIDE, rk.K4 + g); occm_cp16<V>(sa + 4 * OCCM_OPS_STRIDE, rk.K5 + g); }
+    if (STAGE == 7) { occm_cp16<V>(sa + OCCM_OPS_STRIDE, rk.K2 + g); }
 }
-template <int STAGE, unsigned RO>            // RO = byte offset of the trip's ring buffer
+template <int STAGE, unsigned RO, int V>     // RO = byte offset of the trip's ring buffer
 __device__ __forceinline__ OccmOps2 occm_fast_read_ops(unsigned sa) {
     OccmOps2 o;
     const double2 z = make_double2(0.0, 0.0);
     o.ye = o.k1 = o.ka = o.kb = o.kc = o.kd = z;
-    o.ye = occm_lds2_at<RO>(sa);
-    if (STAGE != 7) o.k1 = occm_lds2_at<RO + OCCM_OPS_STRIDE>(sa);
-    if (STAGE == 3) { o.ka = occm_lds2_at<RO + 2 * OCCM_OPS_STRIDE>(sa); }
-    if (STAGE == 4) { o.ka = occm_lds2_at<RO + 2 * OCCM_OPS_STRIDE>(sa); o.kb = occm_lds2_at<RO + 3 * OCCM_OPS_STRIDE>(sa); }
-    if (STAGE == 5 || STAGE == 6) { o.ka = occm_lds2_at<RO + 2 * OCCM_OPS_STRIDE>(sa); o.kb = occm_lds2_at<RO + 3 * OCCM_OPS_STRIDE>(sa); o.kc = occm_lds2_at<RO + 4 * OCCM_OPS_STRIDE>(sa); }
-    if (STAGE == 7) { o.ka = occm_lds2_at<RO + OCCM_OPS_STRIDE>(sa); }
+    o.ye = occm_lds2_at<RO, V>(sa);
+    if (STAGE != 7) o.k1 = occm_lds2_at<RO + OCCM_OPS_STRIDE, V>(sa);
+    if (STAGE == 3) { o.ka = occm_lds2_at<RO + 2 * OCCM_OPS_STRIDE, V>(sa); }
+    if (STAGE == 4) { o.ka = occm_lds2_at<RO + 2 * OCCM_OPS_STRIDE, V>(sa); o.kb = occm_lds2_at<RO + 3 * OCCM_OPS_STRIDE, V>(sa); }
+    if (STAGE == 5 || STAGE == 6) { o.ka = occm_lds2_at<RO + 2 * OCCM_OPS_STRIDE, V>(sa); o.kb = occm_lds2_at<RO + 3 * OCCM_OPS_STRIDE, V>(sa); o.kc = occm_lds2_at<RO + 4 * OCCM_OPS_STRIDE, V>(sa); }
+    if (STAGE == 7) { o.ka = occm_lds2_at<RO + OCCM_OPS_STRIDE, V>(sa); }
     return o;
 }
 
@@ -168,24 +186,24 @@ __device__ __forceinline__ double occm_fast_comb(const OccmRkDev& rk, double ye,
     return 0.0;
 }
 
-template <int STAGE>
+template <int STAGE, int V>
 __device__ __forceinline__ double occm_fast_finish(const OccmSysDev& sys, const OccmRkDev& rk, const OccmFastCtx<STAGE>& c, const OccmOps2& o,
                                                    double2 f, double2 yn, int e, double* __restrict__ dy_out) {
     const long long g = (long long)c.m * sys.ndof + e;
-    if (STAGE <= 1) { occm_st2(dy_out + g, f); return 0.0; }
+    if (STAGE <= 1) { occm_st2<V>(dy_out + g, f); return 0.0; }
     double2 nx = make_double2(0.0, 0.0);
     const double e0 = occm_fast_comb<STAGE>(rk, o.ye.x, o.k1.x, o.ka.x, o.kb.x, o.kc.x, o.kd.x, f.x, c.h, yn.x, nx.x);
-    const double e1 = occm_fast_comb<STAGE>(rk, o.ye.y, o.k1.y, o.ka.y, o.kb.y, o.kc.y, o.kd.y, f.y, c.h, yn.y, nx.y);
-    if (STAGE == 2) { occm_st2(rk.K2 + g, f); occm_st2(rk.YS[0] + g, nx); }
-    else if (STAGE == 3) { occm_st2(rk.K3 + g, f); occm_st2(rk.YS[1] + g, nx); }
-    else if (STAGE == 4) { occm_st2(rk.K4 + g, f); occm_st2(rk.YS[0] + g, nx); }
-    else if (STAGE == 5) { occm_st2(rk.K5 + g, f); occm_st2(rk.YS[1] + g, nx); }
+    const double e1 = V == 2 ? occm_fast_comb<STAGE>(rk, o.ye.y, o.k1.y, o.ka.y, o.kb.y, o.kc.y, o.kd.y, f.y, c.h, yn.y, nx.y) : 0.0;
+    if (STAGE == 2) { occm_st2<V>(rk.K2 + g, f); occm_st2<V>(rk.YS[0] + g, nx); }
+    else if (STAGE == 3) { occm_st2<V>(rk.K3 + g, f); occm_st2<V>(rk.YS[1] + g, nx); }
+    else if (STAGE == 4) { occm_st2<V>(rk.K4 + g, f); occm_st2<V>(rk.YS[0] + g, nx); }
+    else if (STAGE == 5) { occm_st2<V>(rk.K5 + g, f); occm_st2<V>(rk.YS[1] + g, nx); }
     else if (STAGE == 6) {
-        occm_st2(rk.K6 + g, f); occm_st2(rk.Y[c.par ^ 1] + g, nx);
-        occm_st2(rk.K2 + g, make_double2(dp::E1 * o.k1.x + dp::E3 * o.ka.x + dp::E4 * o.kb.x + dp::E5 * o.kc.x + dp::E6 * f.x,
+        occm_st2<V>(rk.K6 + g, f); occm_st2<V>(rk.Y[c.par ^ 1] + g, nx);
+        occm_st2<V>(rk.K2 + g, make_double2(dp::E1 * o.k1.x + dp::E3 * o.ka.x + dp::E4 * o.kb.x + dp::E5 * o.kc.x + dp::E6 * f.x,
                                           dp::E1 * o.k1.y + dp::E3 * o.ka.y + dp::E4 * o.kb.y + dp::E5 * o.kc.y + dp::E6 * f.y));
     }
-    else { occm_st2(rk.KF[c.par ^ 1] + g, f); }
+    else { occm_st2<V>(rk.KF[c.par ^ 1] + g, f); }
     return e0 + e1;
 }
 
@@ -199,8 +217,11 @@ __device__ __forceinline__ unsigned occm_lds_u32(unsigned sa) { unsigned v; asm 
 // the per-thread slot addresses are loop invariants (the compiler keeps as many of them in registers as it can afford)
 template <unsigned OFF>
 __device__ __forceinline__ double occm_lds_f64_at(unsigned sa) { double v; asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(sa), "n"(OFF)); return v; }
-template <unsigned OFF>
-__device__ __forceinline__ void occm_sts2_at(unsigned sa, double2 v) { asm volatile("st.shared.v2.f64 [%0+%3], {%1, %2};" :: "r"(sa), "d"(v.x), "d"(v.y), "n"(OFF) : "memory"); }
+template <unsigned OFF, int V>
+__device__ __forceinline__ void occm_sts2_at(unsigned sa, double2 v) {
+    if (V == 2) asm volatile("st.shared.v2.f64 [%0+%3], {%1, %2};" :: "r"(sa), "d"(v.x), "d"(v.y), "n"(OFF) : "memory");
+    else        asm volatile("st.shared.f64 [%0+%2], %1;" :: "r"(sa), "d"(v.x), "n"(OFF) : "memory");
+}
 #define OCCM_TILE_BUF_BYTES (OCCM_FAST_BLOCK * 32)      // >= tcv * (S + 2) * 8 for every even S >= 2
 
 // Reaction rate of one species from its register-resident term list, straight-line: NTc terms x NFc factor slots are always
@@ -240,7 +261,7 @@ struct OccmFastPre {          // everything of a trip that can be loaded before 
     double2 own; int4 ell[K]; int pt; int ci;
 };
 
-template <int MODEL, int STAGE, int K, int WIDE>
+template <int MODEL, int STAGE, int K, int WIDE, int V>
 __device__ __forceinline__ void
 occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk,
                const double* __restrict__ t_dev, double t_scalar, const double* __restrict__ y_in, double* __restrict__ dy_out,
@@ -248,7 +269,7 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
     extern __shared__ double smem_d[];
     int* tab_s = reinterpret_cast<int*>(smem_d);
     occm_load_tables(sys.tables, sys.tables_bytes, tab_s);
-    const int S = sys.S, H = S >> 1, RS = S + 2;            // staged rows: S values + two 1.0 pads (keeps 16-byte alignment)
+    const int S = sys.S, H = S / V, RS = S + 2;            // staged rows: S values + two 1.0 pads (keeps 16-byte alignment)
     double* tile = smem_d + (((sys.tables_bytes + 15) >> 4) << 1);   // two buffers [tcv][RS], OCCM_TILE_BUF_BYTES apart, 16-byte aligned
     constexpr bool ASYNC = OccmOpsAsync<STAGE>::value;
     constexpr unsigned RING_BYTES = ASYNC ? OccmNops<STAGE>::value * OCCM_OPS_STRIDE : 0;      // one of the two operand buffers
@@ -265,7 +286,7 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
     const int ppw = 32 / H;                                   // points per warp and trip
     const bool lane_on = WARPMAP ? pw < ppw : tid < tcv * H;
     const int pl = WARPMAP ? (tid >> 5) * ppw + pw : tid / H;
-    const int sp = WARPMAP ? 2 * (lane_w - pw * H) : 2 * (tid - pl * H);
+    const int sp = WARPMAP ? V * (lane_w - pw * H) : V * (tid - pl * H);
     const int nt_u = tab_s[OCCM_H_MAX_TERMS], nf_u = tab_s[OCCM_H_MAX_SLOTS];
     // WIDE: term lists of every species in shared memory, coefficients scaled per member in a double-buffered copy
     const int NW = S * nt_u;
@@ -285,11 +306,11 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
         for (int q = 0; q < OCCM_NT; ++q) { meta0[q] = 0u; meta1[q] = 0u; }
     } else {
         const OccmTab T = occm_tab_views(tab_s);
-        const OccmRxnRegs R0 = occm_rxn_regs(T, lane_on ? sp : 0, S), R1 = occm_rxn_regs(T, lane_on ? sp + 1 : 0, S);
+        const OccmRxnRegs R0 = occm_rxn_regs(T, lane_on ? sp : 0, S), R1 = occm_rxn_regs(T, (lane_on && V == 2) ? sp + 1 : 0, S);
 #pragma unroll
         for (int q = 0; q < OCCM_NT; ++q) {
             meta0[q] = R0.meta[q]; meta1[q] = R1.meta[q];
-            if (lane_on && pl == 0) { rxc_s[sp * OCCM_NT + q] = R0.coeff[q]; rxc_s[(sp + 1) * OCCM_NT + q] = R1.coeff[q]; }   // warp 0, first point
+            if (lane_on && pl == 0) { rxc_s[sp * OCCM_NT + q] = R0.coeff[q]; if (V == 2) rxc_s[(sp + 1) * OCCM_NT + q] = R1.coeff[q]; }   // warp 0, first point
         }
     }
     for (int r = tid; r < 2 * tcv; r += OCCM_FAST_BLOCK) {
@@ -334,10 +355,10 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
         pre.pt = (lane_on && p < n_points) ? p : -1;
         const int pp = pre.pt >= 0 ? pre.pt : 0;
         const int e = pp * S + sp;
-        pre.own = occm_fast_in<STAGE>(occm_fast_in_a<STAGE>(sys, rk, y_in, cx), occm_fast_in_b<STAGE>(sys, mem, rk, cx), cx.h, e);
+        pre.own = occm_fast_in<STAGE, V>(occm_fast_in_a<STAGE>(sys, rk, y_in, cx), occm_fast_in_b<STAGE>(sys, mem, rk, cx), cx.h, e);
 #pragma unroll
         for (int k = 0; k < K; ++k) pre.ell[k] = __ldg(reinterpret_cast<const int4*>(ell + (size_t)k * N + pp));
-        if (ASYNC) { if (pre.pt >= 0) occm_fast_issue_ops<STAGE>(sys, rk, cx, e, ops_sa + ring_off); }
+        if (ASYNC) { if (pre.pt >= 0) occm_fast_issue_ops<STAGE, V>(sys, rk, cx, e, ops_sa + ring_off); }
         else if (pre.pt >= 0) occm_fast_prefetch_ops<STAGE>(sys, rk, cx, e);
     };
 
@@ -352,8 +373,8 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
         constexpr unsigned RO = (unsigned)buf * RING_BYTES;               // this trip's operand buffer; the next trip's is the other one
         // register version: epilogue operands of THIS trip are requested here, they have the whole trip to arrive
         OccmOps2 ops;
-        if (!ASYNC) ops = occm_fast_load_ops<STAGE>(sys, rk, cc, (cur.pt >= 0 ? cur.pt : 0) * S + sp);
-        if (lane_on) occm_sts2_at<BO>(row_sa + 8u * sp, cur.own);
+        if (!ASYNC) ops = occm_fast_load_ops<STAGE, V>(sys, rk, cc, (cur.pt >= 0 ? cur.pt : 0) * S + sp);
+        if (lane_on) occm_sts2_at<BO, V>(row_sa + 8u * sp, cur.own);
         if (WIDE) {                                     // uniform: this buffer's coefficient copy belongs to another member
             int& have = buf ? cmw_m1 : cmw_m0;
             if (have != cc.m) {
@@ -371,7 +392,7 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
             const double* ga = occm_fast_in_a<STAGE>(sys, rk, y_in, cc);
             const double* gb = occm_fast_in_b<STAGE>(sys, mem, rk, cc);
 #pragma unroll
-            for (int k = 0; k < K; ++k) g[k] = occm_fast_in<STAGE>(ga, gb, cc.h, cur.ell[k].x * S + sp);
+            for (int k = 0; k < K; ++k) g[k] = occm_fast_in<STAGE, V>(ga, gb, cc.h, cur.ell[k].x * S + sp);
         }
         if (have_next) load(nxt, ncx, RING_BYTES - RO);
         if (ASYNC) asm volatile("cp.async.commit_group;" ::: "memory");     // exactly one group per trip (empty after the last one)
@@ -381,7 +402,7 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
             for (int q = 0; q < OCCM_NT; ++q) {
                 const double k0 = mem.k_scale ? __ldg(mem.k_scale + (long long)cc.m * sys.n_rxn + (meta0[q] & 0xffu)) : 1.0;
                 const double k1 = mem.k_scale ? __ldg(mem.k_scale + (long long)cc.m * sys.n_rxn + (meta1[q] & 0xffu)) : 1.0;
-                cm0[q] = rxc_s[sp * OCCM_NT + q] * k0; cm1[q] = rxc_s[(sp + 1) * OCCM_NT + q] * k1;
+                cm0[q] = rxc_s[sp * OCCM_NT + q] * k0; cm1[q] = V == 2 ? rxc_s[(sp + 1) * OCCM_NT + q] * k1 : 0.0;
             }
             coeff_m = cc.m;
         }
@@ -393,17 +414,17 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
                     const unsigned c0 = cmw_sa + 8u * (unsigned)(buf * NW + sp * nt_u), m0 = mtw_sa + 4u * (unsigned)(sp * nt_u);
                     if (nf_u <= 2) {
                         r0 = occm_reaction_wide_sa<2, BO>(c0, m0, row_sa, nt_u);
-                        r1 = occm_reaction_wide_sa<2, BO>(c0 + 8u * nt_u, m0 + 4u * nt_u, row_sa, nt_u);
+                        r1 = V == 2 ? occm_reaction_wide_sa<2, BO>(c0 + 8u * nt_u, m0 + 4u * nt_u, row_sa, nt_u) : 0.0;
                     } else {
                         r0 = occm_reaction_wide_sa<3, BO>(c0, m0, row_sa, nt_u);
-                        r1 = occm_reaction_wide_sa<3, BO>(c0 + 8u * nt_u, m0 + 4u * nt_u, row_sa, nt_u);
+                        r1 = V == 2 ? occm_reaction_wide_sa<3, BO>(c0 + 8u * nt_u, m0 + 4u * nt_u, row_sa, nt_u) : 0.0;
                     }
                 } else if (nf_u <= 2) {                 // uniform: one of four straight-line variants
-                    if (nt_u <= 2) { r0 = occm_reaction_sa<2, 2, BO>(cm0, meta0, row_sa); r1 = occm_reaction_sa<2, 2, BO>(cm1, meta1, row_sa); }
-                    else           { r0 = occm_reaction_sa<4, 2, BO>(cm0, meta0, row_sa); r1 = occm_reaction_sa<4, 2, BO>(cm1, meta1, row_sa); }
+                    if (nt_u <= 2) { r0 = occm_reaction_sa<2, 2, BO>(cm0, meta0, row_sa); r1 = V == 2 ? occm_reaction_sa<2, 2, BO>(cm1, meta1, row_sa) : 0.0; }
+                    else           { r0 = occm_reaction_sa<4, 2, BO>(cm0, meta0, row_sa); r1 = V == 2 ? occm_reaction_sa<4, 2, BO>(cm1, meta1, row_sa) : 0.0; }
                 } else {
-                    if (nt_u <= 2) { r0 = occm_reaction_sa<2, 3, BO>(cm0, meta0, row_sa); r1 = occm_reaction_sa<2, 3, BO>(cm1, meta1, row_sa); }
-                    else           { r0 = occm_reaction_sa<4, 3, BO>(cm0, meta0, row_sa); r1 = occm_reaction_sa<4, 3, BO>(cm1, meta1, row_sa); }
+                    if (nt_u <= 2) { r0 = occm_reaction_sa<2, 3, BO>(cm0, meta0, row_sa); r1 = V == 2 ? occm_reaction_sa<2, 3, BO>(cm1, meta1, row_sa) : 0.0; }
+                    else           { r0 = occm_reaction_sa<4, 3, BO>(cm0, meta0, row_sa); r1 = V == 2 ? occm_reaction_sa<4, 3, BO>(cm1, meta1, row_sa) : 0.0; }
                 }
                 double2 f;
                 if (MODEL == 0) {
@@ -417,9 +438,9 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
                 }
                 if (ASYNC) {
                     asm volatile("cp.async.wait_group 1;" ::: "memory");    // everything but the next trip's group has landed
-                    ops = occm_fast_read_ops<STAGE, RO>(ops_sa);
+                    ops = occm_fast_read_ops<STAGE, RO, V>(ops_sa);
                 }
-                err2 = occm_fast_finish<STAGE>(sys, rk, cc, ops, f, cur.own, cur.pt * S + sp, dy_out);
+                err2 = occm_fast_finish<STAGE, V>(sys, rk, cc, ops, f, cur.own, cur.pt * S + sp, dy_out);
             }   // flagged rows (boundary / pulse / overflow entries) are left to occm_fixup, launched right after
         }
         if (STAGE == 7) {          // one partial per warp: no block barrier in the hot loop (summed in fixed order by the controller)
@@ -442,20 +463,20 @@ occm_fast_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
 }
 
 
-template <int STAGE, int K, int WIDE>
+template <int STAGE, int K, int WIDE, int V>
 __global__ void __launch_bounds__(OCCM_FAST_BLOCK, OCCM_FAST_CTAS)
 occm_fast_cstr(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmMemDev mem, const __grid_constant__ OccmRkDev rk,
                const double* __restrict__ t_dev, double t_scalar, const double* __restrict__ y_in, double* __restrict__ dy_out,
                const OccmEllEntry* __restrict__ ell, int cpm, int tcv, int err_stride) {
-    occm_fast_body<0, STAGE, K, WIDE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, ell, cpm, tcv, err_stride);
+    occm_fast_body<0, STAGE, K, WIDE, V>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, ell, cpm, tcv, err_stride);
 }
 
-template <int STAGE, int WIDE>
+template <int STAGE, int WIDE, int V>
 __global__ void __launch_bounds__(OCCM_FAST_BLOCK, OCCM_FAST_CTAS)
 occm_fast_pfr(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmMemDev mem, const __grid_constant__ OccmRkDev rk,
               const double* __restrict__ t_dev, double t_scalar, const double* __restrict__ y_in, double* __restrict__ dy_out,
               const OccmEllEntry* __restrict__ ell, int cpm, int tcv, int err_stride) {
-    occm_fast_body<1, STAGE, 1, WIDE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, ell, cpm, tcv, err_stride);
+    occm_fast_body<1, STAGE, 1, WIDE, V>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, ell, cpm, tcv, err_stride);
 }
 
 // Flagged points of the fast path: rows with boundary / pulse entries or more entries than the ELL width, PFR inlet

@@ -622,25 +622,27 @@ static int occm_launch_stage_m(const occm_system* sys, const OccmMemDev& mem, co
 
 typedef void (*occm_fast_fn)(const OccmSysDev, const OccmMemDev, const OccmRkDev, const double*, double, const double*, double*,
                              const OccmEllEntry*, int, int, int);
-template <int MODEL, int STAGE, int K, int WIDE>
+template <int MODEL, int STAGE, int K, int WIDE, int V>
 static occm_fast_fn occm_fast_kernel() {
-    if constexpr (MODEL == 0) return occm_fast_cstr<STAGE, K, WIDE>;
-    else return occm_fast_pfr<STAGE, WIDE>;
+    if constexpr (MODEL == 0) return occm_fast_cstr<STAGE, K, WIDE, V>;
+    else return occm_fast_pfr<STAGE, WIDE, V>;
 }
 
-template <int MODEL, int STAGE, int K, int WIDE>
+// V = values per thread: 2 (even species counts, 128-bit accesses) or 1 (odd species counts, 64-bit accesses)
+template <int MODEL, int STAGE, int K, int WIDE, int V>
 static int occm_launch_fast(const occm_system* sys, const OccmMemDev& mem, const OccmRkDev& rk, const double* t_dev,
                             double t_scalar, const double* y_in, double* dy_out, cudaStream_t st, int* cpm_out) {
     static size_t smem_limit = 48 * 1024;
     static int ctas_per_sm = 0;
     const int S = sys->dev.S;
-    const int tcv = (OccmWarpMap<STAGE>::value && !WIDE) ? (OCCM_FAST_BLOCK / 32) * (32 / (S / 2))      // a warp owns 32 / (S/2) whole points
-                                                          : OCCM_FAST_BLOCK / (S / 2);
+    const int H = S / V;                                                                                // threads per point
+    const int tcv = (OccmWarpMap<STAGE>::value && !WIDE) ? (OCCM_FAST_BLOCK / 32) * (32 / H)            // a warp owns 32 / H whole points
+                                                          : OCCM_FAST_BLOCK / H;
     const size_t nw = (size_t)S * sys->max_terms;          // WIDE: unscaled + two scaled coefficient copies + meta words
     const size_t smem = (((size_t)sys->dev.tables_bytes + 15) & ~(size_t)15) +
                         sizeof(double) * ((size_t)2 * (OCCM_TILE_BUF_BYTES / 8) + (WIDE ? 3 * nw + (nw + 1) / 2 : (size_t)S * OCCM_NT) + 40) +
                         (OccmOpsAsync<STAGE>::value ? (size_t)2 * OccmNops<STAGE>::value * OCCM_OPS_STRIDE : 0);
-    auto kern = occm_fast_kernel<MODEL, STAGE, K, WIDE>();
+    auto kern = occm_fast_kernel<MODEL, STAGE, K, WIDE, V>();
     if (smem > smem_limit) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_limit = smem; }
     if (ctas_per_sm == 0) {
         OCCM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, OCCM_FAST_BLOCK, smem));
@@ -678,27 +680,31 @@ int occm_launch_stage(const occm_system* sys, const OccmMemDev& mem, const OccmR
                       double t_scalar, const double* y_in, double* dy_out, cudaStream_t st, int* cpm_out = nullptr) {
     const OccmSysDev& d = sys->dev;
     const bool wide = !d.fast_ok || sys->force_wide;      // term lists in shared memory instead of registers
-    const bool fast = sys->use_fast && (d.fast_ok || d.wide_ok) && (d.S % 2 == 0) && sys->desc.ell_packed &&
+    const bool even = d.S % 2 == 0;                        // two species per thread (128-bit) or one (64-bit)
+    const bool fast = sys->use_fast && (d.fast_ok || d.wide_ok) && d.S / (even ? 2 : 1) <= 32 && sys->desc.ell_packed &&
                       (sys->desc.n_flagged == 0 || sys->desc.flagged_points) && mem.M <= 65535 && d.ell_k >= 1 &&
                       d.ell_k <= 4 && d.n_points * d.S < (1ll << 31) &&
-                      occm_aligned16(y_in) && occm_aligned16(dy_out) && occm_aligned16(mem.z);
+                      (!even || (occm_aligned16(y_in) && occm_aligned16(dy_out) && occm_aligned16(mem.z)));
+#define OCCM_FAST_CALL(MODEL, K, WIDE, V) occm_launch_fast<MODEL, STAGE, K, WIDE, V>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out)
+#define OCCM_FAST_CALL_V(MODEL, K, WIDE) (even ? OCCM_FAST_CALL(MODEL, K, WIDE, 2) : OCCM_FAST_CALL(MODEL, K, WIDE, 1))
     if (fast && d.model == OCCM_MODEL_PFR && d.ell_k == 1 && sys->desc.n_flagged >= d.n_models)
-        return wide ? occm_launch_fast<1, STAGE, 1, 1>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out)
-                    : occm_launch_fast<1, STAGE, 1, 0>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
+        return wide ? OCCM_FAST_CALL_V(1, 1, 1) : OCCM_FAST_CALL_V(1, 1, 0);
     if (fast && d.model == OCCM_MODEL_CSTR) {
         if (wide) switch (d.ell_k) {
-            case 1: return occm_launch_fast<0, STAGE, 1, 1>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
-            case 2: return occm_launch_fast<0, STAGE, 2, 1>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
-            case 3: return occm_launch_fast<0, STAGE, 3, 1>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
-            default: return occm_launch_fast<0, STAGE, 4, 1>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
+            case 1: return OCCM_FAST_CALL_V(0, 1, 1);
+            case 2: return OCCM_FAST_CALL_V(0, 2, 1);
+            case 3: return OCCM_FAST_CALL_V(0, 3, 1);
+            default: return OCCM_FAST_CALL_V(0, 4, 1);
         }
         switch (d.ell_k) {
-            case 1: return occm_launch_fast<0, STAGE, 1, 0>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
-            case 2: return occm_launch_fast<0, STAGE, 2, 0>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
-            case 3: return occm_launch_fast<0, STAGE, 3, 0>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
-            default: return occm_launch_fast<0, STAGE, 4, 0>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
+            case 1: return OCCM_FAST_CALL_V(0, 1, 0);
+            case 2: return OCCM_FAST_CALL_V(0, 2, 0);
+            case 3: return OCCM_FAST_CALL_V(0, 3, 0);
+            default: return OCCM_FAST_CALL_V(0, 4, 0);
         }
     }
+#undef OCCM_FAST_CALL_V
+#undef OCCM_FAST_CALL
     if (cpm_out) *cpm_out = d.chunks_per_member;
     return d.model == OCCM_MODEL_CSTR ? occm_launch_stage_m<0, STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st)
                                       : occm_launch_stage_m<1, STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st);

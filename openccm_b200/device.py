@@ -246,6 +246,7 @@ class Rk45Run:
         if self.handle:
             self.lib.occm_rk45_free(self.handle)
             self.handle = C.c_void_p()
+        self.ws = None            # the workspace (11 state-sized vectors) goes back to the allocator right away
 
     def run(self, max_launch_steps: int = 0) -> int:
         running = C.c_int32(0)

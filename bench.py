@@ -317,9 +317,16 @@ def main():
         torch.cuda.synchronize()
 
     def one_solve():
+        t_a = time.perf_counter()
         with dev.open_rk45(y0, solver.t_span, rtol=solver.rtol, atol=solver.atol, first_step=solver.first_step,
                            t_eval=te, save_idx=save_dev, members=mem) as run:
-            run.run(); run.stats()
+            t_b = time.perf_counter()
+            run.run()
+            t_c = time.perf_counter()
+            run.stats()
+            t_d = time.perf_counter()
+            if os.environ.get('BENCH_TRACE'):
+                print(f'[trace] solve: open {1e3 * (t_b - t_a):.1f} ms, run {1e3 * (t_c - t_b):.1f} ms, stats {1e3 * (t_d - t_c):.1f} ms', file=sys.stderr)
             return int(run.nfev.sum()), int(run.n_acc.sum() + run.n_rej.sum()), np.array(run.status)
 
     # The solves run at the 1000 W power cap; the power controller needs ~5 s of load to settle (measured: the solve that

@@ -1136,7 +1136,8 @@ extern "C" int occm_bdf_init(occm_bdf** out, const occm_system* sys, const occm_
     b.newton_tol = fmax(10.0 * EPS / p->rtol, fmin(0.03, sqrt(p->rtol)));       // bdf.py:224
     b.lin_tol = (p->lin_tol_factor > 0.0 ? p->lin_tol_factor : 0.05) * b.newton_tol;   // CVODE's eps_lin
     b.tdiag = p->tdiag; b.q_scale = h->mem.q_scale; b.k_scale = h->mem.k_scale;
-    if (cudaHostAlloc((void**)&h->h_counters, 4 * sizeof(int), cudaHostAllocDefault) != cudaSuccess) { occm_set_error("cudaHostAlloc failed"); free(h); return OCCM_ERR_CUDA; }
+    h->h_counters = (int*)occm_pinned_acquire();
+    if (!h->h_counters) { occm_set_error("host allocation failed"); free(h); return OCCM_ERR_CUDA; }
     const int gm = (M + 63) / 64;
     BDF_LAUNCH(bdf_ctrl_init, gm, 64, 0, b, p->t0, p->first_step, p->t_eval ? 0 : 1);
     // f(t0, y0) -> b.f ; D[0] = y0, D[1] = f h
@@ -1279,7 +1280,7 @@ extern "C" int occm_bdf_get_state(occm_bdf* h, double* y_out, void* stream) {
 
 extern "C" int occm_bdf_free(occm_bdf* h) {
     if (!h) return OCCM_OK;
-    if (h->h_counters) cudaFreeHost(h->h_counters);
+    occm_pinned_release(h->h_counters);
     free(h);
     return OCCM_OK;
 }

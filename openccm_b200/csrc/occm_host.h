@@ -18,6 +18,10 @@ struct occm_system {
 
 void occm_set_error(const char* fmt, ...);
 void occm_count_launch(int n = 1);
+// 64-byte slots of one pinned page that lives as long as the process: cudaHostAlloc / cudaFreeHost per integrator handle
+// cost up to hundreds of milliseconds on a busy host (they serialise on driver locks)
+void* occm_pinned_acquire(void);
+void occm_pinned_release(void* p);
 struct occm_system;
 struct OccmMemDev;
 int occm_launch_rhs(const occm_system* sys, const OccmMemDev& mem, const double* t_dev, double t_scalar, const double* y,

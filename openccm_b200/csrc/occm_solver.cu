@@ -40,6 +40,26 @@ void occm_set_error(const char* fmt, ...) {
 }
 void occm_count_launch(int n) { g_launches += n; }
 
+#include <mutex>
+static std::mutex g_pin_mutex;
+static char* g_pin_page = nullptr;          // 64 slots x 64 bytes, pinned, never freed
+static unsigned long long g_pin_used = 0;   // bitmap
+void* occm_pinned_acquire(void) {
+    std::lock_guard<std::mutex> lock(g_pin_mutex);
+    if (!g_pin_page && cudaHostAlloc((void**)&g_pin_page, 64 * 64, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); g_pin_page = nullptr; }
+    if (g_pin_page)
+        for (int i = 0; i < 64; ++i)
+            if (!(g_pin_used >> i & 1ull)) { g_pin_used |= 1ull << i; return g_pin_page + 64 * i; }
+    return calloc(1, 64);                   // pool exhausted (or no pinned memory): pageable memory works too, copies just stage
+}
+void occm_pinned_release(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_pin_mutex);
+    const char* c = (const char*)p;
+    if (g_pin_page && c >= g_pin_page && c < g_pin_page + 64 * 64) g_pin_used &= ~(1ull << ((c - g_pin_page) / 64));
+    else free(p);
+}
+
 extern "C" const char* occm_last_error(void) { return g_err; }
 extern "C" int occm_abi_version(void) { return OCCM_ABI_VERSION; }
 extern "C" int64_t occm_launch_count(void) { return g_launches.load(); }
@@ -801,8 +821,9 @@ extern "C" int occm_rk45_init(occm_rk45** out, const occm_system* sys, const occ
     d.n_running = (int*)(w + L.off_running);
     d.rtol = p->rtol; d.atol = p->atol; d.t_bound = p->t_bound; d.max_steps = p->max_steps;
 
-    if (cudaHostAlloc((void**)&rk->h_running, sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
-        occm_set_error("cudaHostAlloc failed"); free(rk); return OCCM_ERR_CUDA;
+    rk->h_running = (int*)occm_pinned_acquire();
+    if (!rk->h_running) {
+        occm_set_error("host allocation failed"); free(rk); return OCCM_ERR_CUDA;
     }
     const size_t state_bytes = (size_t)M * sys->dev.ndof * sizeof(double);
     OCCM_CUDA_CHECK(cudaMemcpyAsync(d.Y[0], p->y0, state_bytes, cudaMemcpyDeviceToDevice, st));
@@ -869,6 +890,18 @@ static void occm_rk45_build_graph(occm_rk45* rk, cudaStream_t st) {
     rk->graph_state = 1;
 }
 
+// OCCM_B200_TIMING=1: report host calls of the run loop that take longer than 50 ms (diagnosis of stalls on shared hosts)
+#include <chrono>
+struct OccmSlowCall {
+    const char* what; bool on; std::chrono::steady_clock::time_point t0;
+    explicit OccmSlowCall(const char* w) : what(w), on(getenv("OCCM_B200_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    ~OccmSlowCall() {
+        if (!on) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > 50.0) fprintf(stderr, "[occm timing] %s took %.1f ms on the host\n", what, ms);
+    }
+};
+
 extern "C" int occm_rk45_run(occm_rk45* rk, int64_t max_launch_steps, int32_t* n_running, void* stream) {
     if (!rk) { occm_set_error("occm_rk45_run: null handle"); return OCCM_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -882,16 +915,20 @@ extern "C" int occm_rk45_run(occm_rk45* rk, int64_t max_launch_steps, int32_t* n
         if (rk->graph_state == 0 && rk->launched_steps + launched >= 1) occm_rk45_build_graph(rk, st);
         while (i < todo) {
             if (rk->graph_state == 1 && todo - i >= OCCM_GRAPH_STEPS) {
+                OccmSlowCall tm("cudaGraphLaunch");
                 OCCM_CUDA_CHECK(cudaGraphLaunch(rk->graph_exec, st));
                 occm_count_launch(rk->launches_per_step * OCCM_GRAPH_STEPS);
                 i += OCCM_GRAPH_STEPS;
             } else {
+                OccmSlowCall tm("occm_rk45_launch_step");
                 int rc = occm_rk45_launch_step(rk, st);
                 if (rc) return rc;
                 ++i;
             }
         }
         launched += todo;
+        // capture and instantiate the step graph while the GPU is busy with the first batch (it used to idle meanwhile)
+        if (rk->graph_state == 0 && rk->launched_steps + launched >= 1) { OccmSlowCall tm("graph capture + instantiate"); occm_rk45_build_graph(rk, st); }
         occm_count_running<<<1, 256, 0, st>>>(rk->d.status, rk->M, rk->d.n_running);
         OCCM_LAUNCH_CHECK("occm_count_running");
         OCCM_CUDA_CHECK(cudaMemcpyAsync(rk->h_running, rk->d.n_running, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -971,7 +1008,7 @@ extern "C" int occm_rk45_time_stage(occm_rk45* rk, int32_t stage, int32_t reps, 
 
 extern "C" int occm_rk45_free(occm_rk45* rk) {
     if (!rk) return OCCM_OK;
-    if (rk->h_running) cudaFreeHost(rk->h_running);
+    occm_pinned_release(rk->h_running);
     if (rk->graph_exec) cudaGraphExecDestroy(rk->graph_exec);
     free(rk);
     return OCCM_OK;

@@ -13,8 +13,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-OBJ = os.path.join(CSRC, '_obj')
-LIB = os.path.join(CSRC, 'liboccm_b200.so')
+# kernel experiments: OCCM_BUILD_VARIANT=name OCCM_NVCC_EXTRA='-D...' builds build/variants/liboccm_b200_<name>.so (load it with OCCM_B200_LIB)
+VARIANT = os.environ.get('OCCM_BUILD_VARIANT', '')
+OBJ = os.path.join(CSRC, '_obj' + ('_' + VARIANT if VARIANT else ''))
+LIB = os.path.join(CSRC, 'liboccm_b200.so') if not VARIANT else \
+    os.path.join(os.path.dirname(HERE), 'build', 'variants', f'liboccm_b200_{VARIANT}.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC', '-diag-suppress', '177'] + \
     os.environ.get('OCCM_NVCC_EXTRA', '').split()          # experiments: e.g. OCCM_NVCC_EXTRA='-DOCCM_FAST_BLOCK=128 -DOCCM_FAST_CTAS=4'
 N_STAGES = 8
@@ -50,6 +53,7 @@ def _newer(target: str, deps) -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get('NVCC', 'nvcc')
     os.makedirs(OBJ, exist_ok=True)
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
     hdrs = _headers()
     units = _units()
     todo = [u for u in units if force or _newer(u[0], [u[1]] + hdrs)]

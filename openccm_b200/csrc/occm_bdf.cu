@@ -736,7 +736,10 @@ __global__ void bdf_ctrl_gmres_start(const OccmBdfDev b) {
     const double beta = sqrt(nr[0]);
     b.ynorm[m] = sqrt(nr[1]);
     b.gmres_j[m] = 0;
-    if (!(beta / sqrt((double)b.ndof) > b.lin_tol)) return;       // also catches NaN: handled as dy = 0 -> Newton test fails later
+    // non-finite right-hand side (bdf.py:52-53: `if not np.all(np.isfinite(f)): break`): the Newton iteration stops without
+    // convergence and the step is halved (bdf_ctrl_newton sees converged == -1)
+    if (!isfinite(beta)) { b.converged[m] = -1; return; }
+    if (!(beta / sqrt((double)b.ndof) > b.lin_tol)) return;       // residual already below the linear tolerance: dy = 0
     b.gmres_active[m] = 1;
     double* gv = b.gv + (long long)m * BDF_MAXDOT;
     for (int i = 0; i <= b.restart; ++i) gv[i] = 0.0;
@@ -1029,8 +1032,8 @@ template <int MODEL, int W>
 static int bdf_precond_launch_w(occm_bdf* h, const double* src, int from_col_j, double* dst, const int* mask, cudaStream_t st) {
     const occm_system* sys = h->sys;
     const size_t smem = sys->smem_tables;
-    static size_t lim = 48 * 1024;
-    if (smem > lim) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(bdf_precond_warp<MODEL, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); lim = smem; }
+    static OccmLaunchCache cache;
+    if (int rc = occm_kernel_prepare(&cache, (const void*)bdf_precond_warp<MODEL, W>, sys->device, 128, smem, nullptr)) return rc;
     const long long groups = (long long)h->M * (MODEL == 0 ? sys->dev.n_points : sys->dev.n_models);
     const int gpb = 128 / W;
     long long blocks = (groups + gpb - 1) / gpb;
@@ -1044,8 +1047,8 @@ template <int W>
 static int bdf_factor_launch_w(occm_bdf* h, cudaStream_t st) {
     const occm_system* sys = h->sys;
     const size_t smem = sys->smem_tables;
-    static size_t lim = 48 * 1024;
-    if (smem > lim) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(bdf_precond_factor<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); lim = smem; }
+    static OccmLaunchCache cache;
+    if (int rc = occm_kernel_prepare(&cache, (const void*)bdf_precond_factor<W>, sys->device, 128, smem, nullptr)) return rc;
     const long long groups = (long long)h->M * sys->dev.n_points;
     const int gpb = 128 / W;
     long long blocks = (groups + gpb - 1) / gpb;
@@ -1103,6 +1106,26 @@ static int bdf_read_counters(occm_bdf* h, cudaStream_t st) {
     return OCCM_OK;
 }
 
+// device side of occm_bdf_init: member scalars, f(t0, y0), D[0] = y0, D[1] = f h, first output row
+static int bdf_init_device(occm_bdf* h, cudaStream_t st) {
+    const occm_system* sys = h->sys;
+    const occm_bdf_problem* p = &h->prob;
+    OccmBdfDev& b = h->d;
+    const int M = h->M;
+    const int gm = (M + 63) / 64;
+    BDF_LAUNCH(bdf_ctrl_init, gm, 64, 0, b, p->t0, p->first_step, p->t_eval ? 0 : 1);
+    OCCM_CUDA_CHECK(cudaMemcpyAsync(b.y, p->y0, (size_t)M * b.ndof * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    const int rc = bdf_rhs(h, nullptr, nullptr, nullptr, b.f, st);
+    if (rc) return rc;
+    const int gv = bdf_grid(sys, (long long)M * b.nchunk);
+    BDF_LAUNCH(bdf_init_D, gv, 256, 0, b, p->y0);
+    if (!p->t_eval) {
+        const int n_save = p->save_idx ? p->n_save : (int)b.ndof;
+        BDF_LAUNCH(bdf_write_initial, 148 * 4, 256, 0, b, n_save, p->save_idx, p->n_t_eval, p->t0, p->out, p->out_t);
+    }
+    return OCCM_OK;
+}
+
 extern "C" int occm_bdf_init(occm_bdf** out, const occm_system* sys, const occm_members* mem, const occm_bdf_problem* p,
                              void* workspace, size_t workspace_bytes, void* stream) {
     if (!out || !sys || !p || !workspace || !p->y0 || !p->out || !p->tdiag) { occm_set_error("occm_bdf_init: null argument"); return OCCM_ERR_INVALID; }
@@ -1138,18 +1161,8 @@ extern "C" int occm_bdf_init(occm_bdf** out, const occm_system* sys, const occm_
     b.tdiag = p->tdiag; b.q_scale = h->mem.q_scale; b.k_scale = h->mem.k_scale;
     h->h_counters = (int*)occm_pinned_acquire();
     if (!h->h_counters) { occm_set_error("host allocation failed"); free(h); return OCCM_ERR_CUDA; }
-    const int gm = (M + 63) / 64;
-    BDF_LAUNCH(bdf_ctrl_init, gm, 64, 0, b, p->t0, p->first_step, p->t_eval ? 0 : 1);
-    // f(t0, y0) -> b.f ; D[0] = y0, D[1] = f h
-    OCCM_CUDA_CHECK(cudaMemcpyAsync(b.y, p->y0, (size_t)M * b.ndof * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    int rc = bdf_rhs(h, nullptr, nullptr, nullptr, b.f, st);
-    if (rc) { free(h); return rc; }
-    const int gv = bdf_grid(sys, (long long)M * b.nchunk);
-    BDF_LAUNCH(bdf_init_D, gv, 256, 0, b, p->y0);
-    if (!p->t_eval) {
-        const int n_save = p->save_idx ? p->n_save : (int)b.ndof;
-        BDF_LAUNCH(bdf_write_initial, 148 * 4, 256, 0, b, n_save, p->save_idx, p->n_t_eval, p->t0, p->out, p->out_t);
-    }
+    const int rc = bdf_init_device(h, st);
+    if (rc) { occm_pinned_release(h->h_counters); free(h); return rc; }        // no handle, no pinned slot left behind
     *out = h;
     return OCCM_OK;
 }

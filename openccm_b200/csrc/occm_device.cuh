@@ -15,6 +15,9 @@
 
 #define OCCM_BLOCK 256
 #define OCCM_MAX_S 64
+#ifndef OCCM_FAST_BLOCK
+#define OCCM_FAST_BLOCK 256        // threads per CTA of the fast kernels (the fix-up kernel keeps OCCM_BLOCK)
+#endif
 
 struct OccmSysDev {
     int model, S, n_models, P;

@@ -22,9 +22,6 @@
 #ifndef OCCM_FAST_CTAS
 #define OCCM_FAST_CTAS 2
 #endif
-#ifndef OCCM_FAST_BLOCK
-#define OCCM_FAST_BLOCK 256        // threads per CTA of the fast kernels (the fix-up kernel keeps OCCM_BLOCK)
-#endif
 
 struct __align__(16) OccmEllEntry { int src; int flag; double w; };
 

@@ -14,7 +14,19 @@ struct occm_system {
     int max_terms;        // most terms of any species (table header)
     int use_fast;         // 0: always run the generic kernels (OCCM_B200_NO_FAST=1, used by the tests to cover both)
     size_t smem_tables;   // bytes of the staged table blob (8-byte aligned)
+    int device;           // CUDA device the handle was created on (launch state is kept per device)
+    int use_pipe;         // 0: no TMA-pipelined kernels (OCCM_B200_NO_PIPE=1)
+    int pipe_depth;       // cap on the ring depth of the pipelined kernels (OCCM_B200_PIPE_DEPTH, 0 = as deep as shared memory allows)
+    int smem_per_block, smem_per_sm;
 };
+
+// Launch state of ONE kernel, per device: the dynamic shared-memory opt-in that has been granted and the occupancy at the
+// last shared-memory size asked for.  cudaFuncSetAttribute applies per device and systems differ in their table sizes, so
+// neither may be a process-wide scalar; guarded by one mutex (host threads driving different GPUs).
+#define OCCM_MAX_DEVICES 32
+struct OccmLaunchCache { size_t smem_limit[OCCM_MAX_DEVICES]; size_t occ_smem[OCCM_MAX_DEVICES]; int occ[OCCM_MAX_DEVICES]; int occ_block[OCCM_MAX_DEVICES]; };
+// opt in to `smem` bytes of dynamic shared memory if needed; *ctas_per_sm (may be NULL) receives the occupancy
+int occm_kernel_prepare(OccmLaunchCache* cache, const void* kernel, int device, int block, size_t smem, int* ctas_per_sm);
 
 void occm_set_error(const char* fmt, ...);
 void occm_count_launch(int n = 1);
@@ -60,6 +72,18 @@ static inline OccmMemDev occm_mem_dev(const occm_members* mem, int fallback_M) {
 static inline size_t occm_elem_smem(const occm_system* sys, int E) {
     const size_t tile = (size_t)E * (sys->dev.tc + 1) * (sys->dev.S + 1);     // [halo row | tc rows] x (S + 1) per sub-chunk
     return sys->smem_tables + sizeof(double) * (tile + sys->dev.n_rxn + (size_t)sys->dev.S * 4 + 44);
+}
+
+// Error partial sums per member that the stage-7 kernels may write (the workspace is carved for this many; every launcher
+// checks its own count against it).  One partial per warp and chunk; the smallest chunk any variant uses is the warp mapping
+// with one species per thread: (OCCM_FAST_BLOCK / 32) * (32 / S) points (odd S; the dense mapping holds OCCM_BLOCK / S >= that).
+static inline size_t occm_err_capacity(const occm_system* sys) {
+    const int S = sys->dev.S, nwarp = OCCM_FAST_BLOCK / 32;
+    long long min_pts = OCCM_FAST_BLOCK / S < OCCM_BLOCK / S ? OCCM_FAST_BLOCK / S : OCCM_BLOCK / S;
+    if (S <= 32 && (long long)nwarp * (32 / S) < min_pts) min_pts = (long long)nwarp * (32 / S);
+    if (min_pts < 1) min_pts = 1;
+    const long long chunks = (sys->dev.n_points + min_pts - 1) / min_pts + 2;
+    return (size_t)(chunks * nwarp + sys->desc.n_flagged + 8);
 }
 
 // persistent grid: a multiple of the SM count, capped by the amount of work

@@ -60,6 +60,25 @@ void occm_pinned_release(void* p) {
     else free(p);
 }
 
+static std::mutex g_launch_mutex;
+int occm_kernel_prepare(OccmLaunchCache* c, const void* kernel, int device, int block, size_t smem, int* ctas_per_sm) {
+    std::lock_guard<std::mutex> lock(g_launch_mutex);
+    const int d = device >= 0 && device < OCCM_MAX_DEVICES ? device : 0;
+    if (smem > 48 * 1024 && smem > c->smem_limit[d]) {      // 48 KB is available without opting in
+        OCCM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->smem_limit[d] = smem;
+    }
+    if (ctas_per_sm) {
+        if (c->occ[d] == 0 || c->occ_smem[d] != smem || c->occ_block[d] != block) {
+            int n = 0;
+            OCCM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, block, smem));
+            c->occ[d] = n < 1 ? 1 : n; c->occ_smem[d] = smem; c->occ_block[d] = block;
+        }
+        *ctas_per_sm = c->occ[d];
+    }
+    return OCCM_OK;
+}
+
 extern "C" const char* occm_last_error(void) { return g_err; }
 extern "C" int occm_abi_version(void) { return OCCM_ABI_VERSION; }
 extern "C" int64_t occm_launch_count(void) { return g_launches.load(); }
@@ -100,6 +119,8 @@ extern "C" int occm_system_create(occm_system** out, const occm_system_desc* d) 
     v.ell_src = d->ell_src; v.ell_w = d->ell_w;
     v.point_flags = d->point_flags;
     s->use_fast = getenv("OCCM_B200_NO_FAST") ? 0 : 1;
+    s->use_pipe = getenv("OCCM_B200_NO_PIPE") ? 0 : 1;          // tests / A-B measurements: register-prefetching fast kernels instead
+    s->pipe_depth = getenv("OCCM_B200_PIPE_DEPTH") ? atoi(getenv("OCCM_B200_PIPE_DEPTH")) : 0;
     s->force_wide = getenv("OCCM_B200_FORCE_WIDE") ? 1 : 0;      // tests: run the shared-memory term-list variant on any mechanism
     s->max_terms = hdr[OCCM_H_MAX_TERMS];
     v.fast_ok = hdr[OCCM_H_MAX_TERMS] <= OCCM_NT && hdr[OCCM_H_MAX_SLOTS] <= OCCM_NF && !hdr[OCCM_H_ANY_PROG] && hdr[OCCM_H_NRXN] <= 255;
@@ -111,9 +132,12 @@ extern "C" int occm_system_create(occm_system** out, const occm_system_desc* d) 
     s->smem_tables = (size_t)d->tables_bytes;
     int dev = 0;
     OCCM_CUDA_CHECK(cudaGetDevice(&dev));
+    s->device = dev;
     OCCM_CUDA_CHECK(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev));
     int max_smem = 0;
     OCCM_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    s->smem_per_block = max_smem;
+    OCCM_CUDA_CHECK(cudaDeviceGetAttribute(&s->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
     if (occm_elem_smem(s, OCCM_EMAX) > (size_t)max_smem) {
         occm_set_error("mechanism tables (%d B) do not fit in shared memory (%d B)", d->tables_bytes, max_smem);
         free(s);
@@ -366,7 +390,8 @@ occm_stage(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmM
                 }
             }
         }
-        if (mem.k_scale && coeff_m != m && tid < sys.n_rxn) ksc_s[tid] = __ldg(mem.k_scale + (long long)m * sys.n_rxn + tid);
+        if (mem.k_scale && coeff_m != m)                 // any number of reactions (mechanisms with > 255 always run this kernel)
+            for (int r = tid; r < sys.n_rxn; r += OCCM_BLOCK) ksc_s[r] = __ldg(mem.k_scale + (long long)m * sys.n_rxn + r);
         if (MODEL == 1 && tid < S) {           // upwind neighbour point of each sub-chunk's first point
 #pragma unroll
             for (int i = 0; i < E; ++i) {
@@ -436,6 +461,7 @@ occm_stage(const __grid_constant__ OccmSysDev sys, const __grid_constant__ OccmM
 }
 
 #include "occm_fast.cuh"
+#include "occm_pipe.cuh"
 
 #ifndef OCCM_STAGE_TU
 // ------------------------------------------------------------------------------------------------ controller
@@ -620,16 +646,12 @@ __global__ void occm_rk45_write_initial(const double* __restrict__ y0, int M, lo
 template <int MODEL, int STAGE>
 static int occm_launch_stage_m(const occm_system* sys, const OccmMemDev& mem, const OccmRkDev& rk, const double* t_dev,
                                double t_scalar, const double* y_in, double* dy_out, cudaStream_t st) {
-    static size_t smem_limit = 48 * 1024;   // the default opt-out limit; raise it only when needed
-    static int ctas_per_sm = 0;
+    static OccmLaunchCache cache;
+    int ctas_per_sm = 1;
     constexpr int E = STAGE <= 1 ? OCCM_E0 : OCCM_E;
     const size_t smem = occm_elem_smem(sys, E);
     auto kern = occm_stage<MODEL, STAGE, E>;
-    if (smem > smem_limit) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_limit = smem; }
-    if (ctas_per_sm == 0) {
-        OCCM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, OCCM_BLOCK, smem));
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-    }
+    if (int rc = occm_kernel_prepare(&cache, (const void*)kern, sys->device, OCCM_BLOCK, smem, &ctas_per_sm)) return rc;
     OccmSysDev dev = sys->dev;
     dev.chunks_per_member = (int)((dev.n_points + (long long)E * dev.tc - 1) / ((long long)E * dev.tc));
     const long long chunks = (long long)mem.M * dev.chunks_per_member;
@@ -648,12 +670,29 @@ static occm_fast_fn occm_fast_kernel() {
     else return occm_fast_pfr<STAGE, WIDE, V>;
 }
 
+// Flagged points of the fast / pipelined path (occm_fixup): launched right after the hot kernel of the same stage
+template <int MODEL, int STAGE>
+static int occm_launch_fixup(const occm_system* sys, const OccmMemDev& mem, const OccmRkDev& rk, const double* t_dev, double t_scalar,
+                             const double* y_in, double* dy_out, cudaStream_t st, int err_stride, int err_offset) {
+    static OccmLaunchCache fix_cache;
+    const int S = sys->dev.S, n_flagged = sys->desc.n_flagged;
+    const int tcf = OCCM_BLOCK / S;
+    const int nfix = n_flagged > 0 ? (n_flagged + tcf - 1) / tcf : 0;
+    if (nfix == 0) return OCCM_OK;
+    const size_t fsmem = (size_t)sys->dev.tables_bytes + sizeof(double) * ((size_t)(MODEL == 1 ? 2 : 1) * tcf * (S + 1) + 8);
+    if (int rc = occm_kernel_prepare(&fix_cache, (const void*)occm_fixup<MODEL, STAGE>, sys->device, OCCM_BLOCK, fsmem, nullptr)) return rc;
+    occm_fixup<MODEL, STAGE><<<dim3(nfix, mem.M), OCCM_BLOCK, fsmem, st>>>(sys->dev, mem, rk, t_dev, t_scalar, y_in, dy_out, sys->desc.flagged_points,
+                                                                      n_flagged, err_stride, err_offset);
+    OCCM_LAUNCH_CHECK("occm_fixup");
+    return OCCM_OK;
+}
+
 // V = values per thread: 2 (even species counts, 128-bit accesses) or 1 (odd species counts, 64-bit accesses)
 template <int MODEL, int STAGE, int K, int WIDE, int V>
 static int occm_launch_fast(const occm_system* sys, const OccmMemDev& mem, const OccmRkDev& rk, const double* t_dev,
                             double t_scalar, const double* y_in, double* dy_out, cudaStream_t st, int* cpm_out) {
-    static size_t smem_limit = 48 * 1024;
-    static int ctas_per_sm = 0;
+    static OccmLaunchCache cache;
+    int ctas_per_sm = 1;
     const int S = sys->dev.S;
     const int H = S / V;                                                                                // threads per point
     const int tcv = (OccmWarpMap<STAGE>::value && !WIDE) ? (OCCM_FAST_BLOCK / 32) * (32 / H)            // a warp owns 32 / H whole points
@@ -663,11 +702,7 @@ static int occm_launch_fast(const occm_system* sys, const OccmMemDev& mem, const
                         sizeof(double) * ((size_t)2 * (OCCM_TILE_BUF_BYTES / 8) + (WIDE ? 3 * nw + (nw + 1) / 2 : (size_t)S * OCCM_NT) + 40) +
                         (OccmOpsAsync<STAGE>::value ? (size_t)2 * OccmNops<STAGE>::value * OCCM_OPS_STRIDE : 0);
     auto kern = occm_fast_kernel<MODEL, STAGE, K, WIDE, V>();
-    if (smem > smem_limit) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_limit = smem; }
-    if (ctas_per_sm == 0) {
-        OCCM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, OCCM_FAST_BLOCK, smem));
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-    }
+    if (int rc = occm_kernel_prepare(&cache, (const void*)kern, sys->device, OCCM_FAST_BLOCK, smem, &ctas_per_sm)) return rc;
     const int cpm = (int)((sys->dev.n_points + tcv - 1) / tcv);
     const long long chunks = (long long)mem.M * cpm;
     if (chunks >= (1ll << 31)) { occm_set_error("too many chunks (%lld) for one launch", chunks); return OCCM_ERR_INVALID; }
@@ -677,21 +712,89 @@ static int occm_launch_fast(const occm_system* sys, const OccmMemDev& mem, const
     const int nfix = n_flagged > 0 ? (n_flagged + tcf - 1) / tcf : 0;
     const int nwarp = OCCM_FAST_BLOCK / 32;
     const int err_stride = cpm * nwarp + nfix;            // partial sums per member: one per warp and chunk, then fix-up blocks
+    if (STAGE == 7 && (size_t)err_stride > occm_err_capacity(sys)) {
+        occm_set_error("error partials per member (%d) exceed the carved capacity (%zu)", err_stride, occm_err_capacity(sys));
+        return OCCM_ERR_WORKSPACE;
+    }
     kern<<<grid, OCCM_FAST_BLOCK, smem, st>>>(sys->dev, mem, rk, t_dev, t_scalar, y_in, dy_out, (const OccmEllEntry*)sys->desc.ell_packed, cpm, tcv, err_stride);
     OCCM_LAUNCH_CHECK("occm_fast_cstr");
-    if (nfix > 0) {
-        const size_t fsmem = (size_t)sys->dev.tables_bytes + sizeof(double) * ((size_t)(MODEL == 1 ? 2 : 1) * tcf * (S + 1) + 8);
-        static size_t fix_limit = 48 * 1024;
-        if (fsmem > fix_limit) { OCCM_CUDA_CHECK(cudaFuncSetAttribute(occm_fixup<MODEL, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); fix_limit = fsmem; }
-        occm_fixup<MODEL, STAGE><<<dim3(nfix, mem.M), OCCM_BLOCK, fsmem, st>>>(sys->dev, mem, rk, t_dev, t_scalar, y_in, dy_out, sys->desc.flagged_points,
-                                                                          n_flagged, err_stride, cpm * nwarp);
-        OCCM_LAUNCH_CHECK("occm_fixup");
-    }
+    if (int rc = occm_launch_fixup<MODEL, STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, err_stride, cpm * nwarp)) return rc;
     if (cpm_out) *cpm_out = err_stride;
     return OCCM_OK;
 }
 
 static inline bool occm_aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+// TMA-pipelined kernels (occm_pipe.cuh).  Returns 1 when the configuration does not fit them (the caller then takes the
+// register-prefetching fast kernels), 0 after a launch, < 0 on error.
+template <int MODEL, int STAGE, int K, int WIDE, int V>
+static int occm_launch_pipe(const occm_system* sys, const OccmMemDev& mem, const OccmRkDev& rk, const double* t_dev,
+                            double t_scalar, const double* y_in, double* dy_out, cudaStream_t st, int* cpm_out) {
+    static OccmLaunchCache cache;
+    constexpr int NS = OccmPipeStreams<STAGE>::value;
+    constexpr int CTAS = OccmPipeLight<STAGE>::value ? OCCM_PIPE_CTAS_LIGHT : OCCM_PIPE_CTAS;
+    const int S = sys->dev.S, H = S / V, ppw = 32 / H;
+    const long long ndof = sys->dev.ndof;
+    // bulk copies move multiples of 16 bytes from 16-byte aligned addresses: every member base and every chunk must start on one
+    if ((ndof & 1) || ((sys->dev.n_points * S) & 1)) return 1;
+    if (STAGE <= 1 && (!occm_aligned16(y_in) || !occm_aligned16(dy_out) || (STAGE == 1 && !occm_aligned16(mem.z)))) return 1;
+    OccmPipeGeom g;
+    g.pc = OCCM_PIPE_WARPS * ppw;
+    g.cpm = (int)((sys->dev.n_points + g.pc - 1) / g.pc);
+    g.ell_stride = g.pc * 16;
+    g.slot_bytes = (int)((NS * OCCM_PIPE_STREAM_BYTES + (unsigned)(K * g.ell_stride) + 127u) & ~127u);
+    const size_t nw = (size_t)S * sys->max_terms;
+    size_t o = ((size_t)sys->dev.tables_bytes + 15) & ~(size_t)15;
+    g.coef_off = (int)o;
+    g.wide_stride = (int)(8 * nw);
+    o += WIDE ? 8 * nw + 4 * (nw + (nw & 1)) + (size_t)OCCM_PIPE_WARPS * g.wide_stride : sizeof(double) * (size_t)S * OCCM_NT;
+    o = (o + 15) & ~(size_t)15;
+    g.tile_off = (int)o;
+    o += sizeof(double) * (size_t)OCCM_PIPE_WARPS * ppw * (S + 2);
+    o = (o + 15) & ~(size_t)15;
+    g.bar_off = (int)o;
+    o += 16 * OCCM_PIPE_MAX_DEPTH;
+    o = (o + 127) & ~(size_t)127;
+    g.ring_off = (int)o;
+    const size_t budget = (size_t)sys->smem_per_sm / CTAS - 1024;          // 1 KB per resident CTA is reserved by the system
+    const size_t cap = (size_t)sys->smem_per_block < budget ? (size_t)sys->smem_per_block : budget;
+    if (cap < o + 2 * (size_t)g.slot_bytes) return 1;
+    int depth = (int)((cap - o) / (size_t)g.slot_bytes);
+    if (depth > OCCM_PIPE_MAX_DEPTH) depth = OCCM_PIPE_MAX_DEPTH;
+    if (sys->pipe_depth > 0 && depth > sys->pipe_depth) depth = sys->pipe_depth < 2 ? 2 : sys->pipe_depth;
+    g.depth = depth;
+    const size_t smem = o + (size_t)depth * g.slot_bytes;
+    const long long chunks = (long long)mem.M * g.cpm;
+    if (chunks >= (1ll << 31)) { occm_set_error("too many chunks (%lld) for one launch", chunks); return OCCM_ERR_INVALID; }
+    const int n_flagged = sys->desc.n_flagged;
+    const int tcf = OCCM_BLOCK / S;
+    const int nfix = n_flagged > 0 ? (n_flagged + tcf - 1) / tcf : 0;
+    g.err_stride = g.cpm * OCCM_PIPE_WARPS + nfix;
+    if (STAGE == 7 && (size_t)g.err_stride > occm_err_capacity(sys)) {
+        occm_set_error("error partials per member (%d) exceed the carved capacity (%zu)", g.err_stride, occm_err_capacity(sys));
+        return OCCM_ERR_WORKSPACE;
+    }
+    auto kern = occm_pipe<MODEL, STAGE, K, WIDE, V>;
+    int ctas_per_sm = 1;
+    if (int rc = occm_kernel_prepare(&cache, (const void*)kern, sys->device, OCCM_PIPE_THREADS, smem, &ctas_per_sm)) return rc;
+    const int grid = occm_grid(sys, chunks, ctas_per_sm);
+    kern<<<grid, OCCM_PIPE_THREADS, smem, st>>>(sys->dev, mem, rk, y_in, dy_out, (const OccmEllEntry*)sys->desc.ell_packed, g);
+    OCCM_LAUNCH_CHECK("occm_pipe");
+    if (int rc = occm_launch_fixup<MODEL, STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, g.err_stride, g.cpm * OCCM_PIPE_WARPS)) return rc;
+    if (cpm_out) *cpm_out = g.err_stride;
+    return OCCM_OK;
+}
+
+// the pipelined kernel when it applies, else the register-prefetching one
+template <int MODEL, int STAGE, int K, int WIDE, int V>
+static int occm_launch_both(const occm_system* sys, const OccmMemDev& mem, const OccmRkDev& rk, const double* t_dev,
+                            double t_scalar, const double* y_in, double* dy_out, cudaStream_t st, int* cpm_out) {
+    if (sys->use_pipe) {
+        const int rc = occm_launch_pipe<MODEL, STAGE, K, WIDE, V>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
+        if (rc <= 0) return rc;
+    }
+    return occm_launch_fast<MODEL, STAGE, K, WIDE, V>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
+}
 
 // Every STAGE pulls in ~12 kernel instantiations; the build compiles this file once per stage with -DOCCM_STAGE_TU=<stage>
 // (explicit instantiation below) in parallel, and once without it for everything else (extern template).
@@ -705,7 +808,7 @@ int occm_launch_stage(const occm_system* sys, const OccmMemDev& mem, const OccmR
                       (sys->desc.n_flagged == 0 || sys->desc.flagged_points) && mem.M <= 65535 && d.ell_k >= 1 &&
                       d.ell_k <= 4 && d.n_points * d.S < (1ll << 31) &&
                       (!even || (occm_aligned16(y_in) && occm_aligned16(dy_out) && occm_aligned16(mem.z)));
-#define OCCM_FAST_CALL(MODEL, K, WIDE, V) occm_launch_fast<MODEL, STAGE, K, WIDE, V>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out)
+#define OCCM_FAST_CALL(MODEL, K, WIDE, V) occm_launch_both<MODEL, STAGE, K, WIDE, V>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out)
 #define OCCM_FAST_CALL_V(MODEL, K, WIDE) (even ? OCCM_FAST_CALL(MODEL, K, WIDE, 2) : OCCM_FAST_CALL(MODEL, K, WIDE, 1))
     if (fast && d.model == OCCM_MODEL_PFR && d.ell_k == 1 && sys->desc.n_flagged >= d.n_models)
         return wide ? OCCM_FAST_CALL_V(1, 1, 1) : OCCM_FAST_CALL_V(1, 1, 0);
@@ -773,7 +876,7 @@ static RkLayout rk_layout(const occm_system* sys, int M) {
     L.off_par = take(M * 4); L.off_status = take(M * 4); L.off_rej = take(M * 4); L.off_acc_now = take(M * 4);
     L.off_lo = take(M * 4); L.off_hi = take(M * 4); L.off_rows = take(M * 4);
     L.off_nacc = take(M * 8); L.off_nrej = take(M * 8); L.off_nfev = take(M * 8);
-    L.off_err = take((size_t)M * (size_t)(((sys->dev.n_points + sys->dev.tc - 1) / sys->dev.tc + 2) * (OCCM_BLOCK / 32) + sys->desc.n_flagged) * 8);   // capacity for any chunking
+    L.off_err = take((size_t)M * occm_err_capacity(sys) * 8);        // any chunking of any stage-7 variant
     L.off_running = take(256);
     L.total = o;
     return L;
@@ -782,6 +885,32 @@ static RkLayout rk_layout(const occm_system* sys, int M) {
 extern "C" size_t occm_rk45_workspace_bytes(const occm_system* sys, int32_t M) {
     if (!sys || M < 1) return 0;
     return rk_layout(sys, M).total;
+}
+
+// device side of occm_rk45_init: initial state, member scalars, K1 = f(t0, y0), first output row
+static int occm_rk45_init_device(occm_rk45* rk, cudaStream_t st) {
+    const occm_system* sys = rk->sys;
+    const occm_rk45_problem* p = &rk->prob;
+    const OccmRkDev& d = rk->d;
+    const int M = rk->M;
+    const size_t state_bytes = (size_t)M * sys->dev.ndof * sizeof(double);
+    OCCM_CUDA_CHECK(cudaMemcpyAsync(d.Y[0], p->y0, state_bytes, cudaMemcpyDeviceToDevice, st));
+    occm_rk45_init_members<<<(M + 127) / 128, 128, 0, st>>>(d, M, p->t0, p->first_step, p->t_eval ? 0 : 1, p->t_eval, p->n_t_eval);
+    OCCM_LAUNCH_CHECK("occm_rk45_init_members");
+    // K1 = f(t0, y0)   (rk.py:94)
+    const OccmMemDev md = occm_mem_dev(rk->has_mem ? &rk->mem : nullptr, 1);
+    const int rc = occm_launch_stage<0>(sys, md, d, nullptr, p->t0, d.Y[0], d.KF[0], st);
+    if (rc) return rc;
+    if (!p->t_eval) {
+        // ivp.py:653-655: ts = [t0], ys = [y0]
+        const int n_save = p->save_idx ? p->n_save : (int)sys->dev.ndof;
+        const long long total = (long long)M * n_save;
+        const int grid = (int)((total + OCCM_BLOCK - 1) / OCCM_BLOCK < 65535 ? (total + OCCM_BLOCK - 1) / OCCM_BLOCK : 65535);
+        occm_rk45_write_initial<<<grid, OCCM_BLOCK, 0, st>>>(d.Y[0], M, sys->dev.ndof, n_save, p->save_idx, p->n_t_eval, p->t0,
+                                                             p->out, p->out_t);
+        OCCM_LAUNCH_CHECK("occm_rk45_write_initial");
+    }
+    return OCCM_OK;
 }
 
 extern "C" int occm_rk45_init(occm_rk45** out, const occm_system* sys, const occm_members* mem, const occm_rk45_problem* p,
@@ -825,23 +954,8 @@ extern "C" int occm_rk45_init(occm_rk45** out, const occm_system* sys, const occ
     if (!rk->h_running) {
         occm_set_error("host allocation failed"); free(rk); return OCCM_ERR_CUDA;
     }
-    const size_t state_bytes = (size_t)M * sys->dev.ndof * sizeof(double);
-    OCCM_CUDA_CHECK(cudaMemcpyAsync(d.Y[0], p->y0, state_bytes, cudaMemcpyDeviceToDevice, st));
-    occm_rk45_init_members<<<(M + 127) / 128, 128, 0, st>>>(d, M, p->t0, p->first_step, p->t_eval ? 0 : 1, p->t_eval, p->n_t_eval);
-    OCCM_LAUNCH_CHECK("occm_rk45_init_members");
-    // K1 = f(t0, y0)   (rk.py:94)
-    const OccmMemDev md = occm_mem_dev(rk->has_mem ? &rk->mem : nullptr, 1);
-    int rc = occm_launch_stage<0>(sys, md, d, nullptr, p->t0, d.Y[0], d.KF[0], st);
-    if (rc) { free(rk); return rc; }
-    if (!p->t_eval) {
-        // ivp.py:653-655: ts = [t0], ys = [y0]
-        const int n_save = p->save_idx ? p->n_save : (int)sys->dev.ndof;
-        const long long total = (long long)M * n_save;
-        const int grid = (int)((total + OCCM_BLOCK - 1) / OCCM_BLOCK < 65535 ? (total + OCCM_BLOCK - 1) / OCCM_BLOCK : 65535);
-        occm_rk45_write_initial<<<grid, OCCM_BLOCK, 0, st>>>(d.Y[0], M, sys->dev.ndof, n_save, p->save_idx, p->n_t_eval, p->t0,
-                                                             p->out, p->out_t);
-        OCCM_LAUNCH_CHECK("occm_rk45_write_initial");
-    }
+    const int rc = occm_rk45_init_device(rk, st);
+    if (rc) { occm_pinned_release(rk->h_running); free(rk); return rc; }      // no handle, no pinned slot left behind
     rk->launched_steps = 0;
     *out = rk;
     return OCCM_OK;

@@ -24,7 +24,10 @@ struct occm_system {
 // last shared-memory size asked for.  cudaFuncSetAttribute applies per device and systems differ in their table sizes, so
 // neither may be a process-wide scalar; guarded by one mutex (host threads driving different GPUs).
 #define OCCM_MAX_DEVICES 32
-struct OccmLaunchCache { size_t smem_limit[OCCM_MAX_DEVICES]; size_t occ_smem[OCCM_MAX_DEVICES]; int occ[OCCM_MAX_DEVICES]; int occ_block[OCCM_MAX_DEVICES]; };
+struct OccmLaunchCache {
+    size_t smem_limit[OCCM_MAX_DEVICES]; size_t occ_smem[OCCM_MAX_DEVICES]; int occ[OCCM_MAX_DEVICES]; int occ_block[OCCM_MAX_DEVICES];
+    unsigned long long geom_key[OCCM_MAX_DEVICES]; int geom_depth[OCCM_MAX_DEVICES];      // pipelined kernels: ring depth chosen for a shared-memory layout
+};
 // opt in to `smem` bytes of dynamic shared memory if needed; *ctas_per_sm (may be NULL) receives the occupancy
 int occm_kernel_prepare(OccmLaunchCache* cache, const void* kernel, int device, int block, size_t smem, int* ctas_per_sm);
 

@@ -4,7 +4,7 @@
 // polynomial mechanism, flagged rows left to occm_fixup) — what changes is how the bytes reach the SM.  Every input of a
 // trip is a CONTIGUOUS range of global memory: the chunk's rows of the stage state, of y, K1..K5 (species innermost, points
 // consecutive) and of the K packed ELL columns.  A dedicated producer warp streams them into a ring of shared-memory slots
-// with 1-D bulk copies (cp.async.bulk -> UBLKCP, completion on an mbarrier) several trips ahead; eight consumer warps wait
+// with 1-D bulk copies (cp.async.bulk -> UBLKCP, completion on an mbarrier) several trips ahead; seven consumer warps wait
 // on the slot's "full" barrier, compute, and hand the slot back through its "empty" barrier.  Nothing of a future trip is
 // held in registers, so the bytes in flight per SM are set by the ring depth (tens of KB) instead of by the register file
 // (the register-prefetching fast kernels had 8-16 KB in flight and sat at 25 % occupancy: latency bound).
@@ -23,7 +23,7 @@
 #define OCCM_PIPE_CTAS 2
 #endif
 #ifndef OCCM_PIPE_CTAS_LIGHT
-#define OCCM_PIPE_CTAS_LIGHT 3                              // stages with few streams (plain RHS, J*v, 2, 7)
+#define OCCM_PIPE_CTAS_LIGHT 2                              // stages with few streams (plain RHS, J*v, 2, 7): 3 CTAs (80 registers) spilled and measured slower
 #endif
 #define OCCM_PIPE_STREAM_BYTES 4096u                        // a chunk's rows of one vector: 8 * (32 / H) points * S * 8 B <= 4096
 #define OCCM_PIPE_MAX_DEPTH 8
@@ -185,6 +185,9 @@ occm_pipe_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
 
     if (warp == OCCM_PIPE_WARPS) {
         // ================================================================ producer: one thread streams the trips into the ring
+        // (Measured and dropped: the idle lanes of this warp pulling the out-of-chunk neighbour rows into L2 ahead of the
+        //  consumers.  prefetch.global.L2 fetches whole lines for rows of which the gathers touch 2-3 sectors, and it runs ahead
+        //  of the streaming pass that would have brought half of them in anyway: DRAM traffic up, every kernel 10-90 % slower.)
         if (lane != 0) return;
         int cur_m = -1, par = 0;
         for (bool valid = skip(); valid; valid = advance()) {

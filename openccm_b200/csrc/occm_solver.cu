@@ -756,12 +756,37 @@ static int occm_launch_pipe(const occm_system* sys, const OccmMemDev& mem, const
     o += 16 * OCCM_PIPE_MAX_DEPTH;
     o = (o + 127) & ~(size_t)127;
     g.ring_off = (int)o;
-    const size_t budget = (size_t)sys->smem_per_sm / CTAS - 1024;          // 1 KB per resident CTA is reserved by the system
+    // 1 KB per resident CTA is reserved by the system.  The resident CTAs together stay inside the 196 KB shared-memory
+    // configuration: the next one (228 KB) leaves 28 KB of L1 for the row gathers and measured 18 % slower (stage 5, depth 4 vs 3)
+    const size_t smem_sm = (size_t)sys->smem_per_sm < 196 * 1024 ? (size_t)sys->smem_per_sm : 196 * 1024;
+    const size_t budget = smem_sm / CTAS - 1024;
     const size_t cap = (size_t)sys->smem_per_block < budget ? (size_t)sys->smem_per_block : budget;
     if (cap < o + 2 * (size_t)g.slot_bytes) return 1;
     int depth = (int)((cap - o) / (size_t)g.slot_bytes);
-    if (depth > OCCM_PIPE_MAX_DEPTH) depth = OCCM_PIPE_MAX_DEPTH;
-    if (sys->pipe_depth > 0 && depth > sys->pipe_depth) depth = sys->pipe_depth < 2 ? 2 : sys->pipe_depth;
+    // Ring depth, measured per stage on C4 at 512 members (profiles/r02_notes.md): the operand-heavy stages want the ring as deep
+    // as two resident CTAs allow, stage 2 and the J*v kernel (two summands per gathered row) are best at 4, stage 7 at 5.
+    int want = sys->pipe_depth > 0 ? sys->pipe_depth                         // OCCM_B200_PIPE_DEPTH overrides
+             : STAGE == 0 ? 8 : (STAGE == 1 || STAGE == 2) ? 4 : STAGE == 7 ? 5 : 6;
+    if (want < 2) want = 2;
+    if (want > OCCM_PIPE_MAX_DEPTH) want = OCCM_PIPE_MAX_DEPTH;
+    if (depth > want) depth = want;
+    auto kern = occm_pipe<MODEL, STAGE, K, WIDE, V>;
+    int ctas_per_sm = 1;
+    {   // never trade a resident CTA for a deeper ring (measured: stage 5 at one CTA per SM 6.5 ms, at two 5.5 ms)
+        const unsigned long long key = ((unsigned long long)o << 32) ^ ((unsigned long long)g.slot_bytes << 8) ^ (unsigned long long)depth;
+        const int d = sys->device >= 0 && sys->device < OCCM_MAX_DEVICES ? sys->device : 0;
+        if (cache.geom_key[d] == key && cache.geom_depth[d] > 0) depth = cache.geom_depth[d];
+        else {
+            int dd = depth;
+            for (; dd >= 2; --dd) {
+                if (int rc = occm_kernel_prepare(&cache, (const void*)kern, sys->device, OCCM_PIPE_THREADS, o + (size_t)dd * g.slot_bytes, &ctas_per_sm)) return rc;
+                if (ctas_per_sm >= CTAS) break;
+            }
+            if (dd < 2) dd = 2;
+            cache.geom_key[d] = key; cache.geom_depth[d] = dd;
+            depth = dd;
+        }
+    }
     g.depth = depth;
     const size_t smem = o + (size_t)depth * g.slot_bytes;
     const long long chunks = (long long)mem.M * g.cpm;
@@ -774,8 +799,6 @@ static int occm_launch_pipe(const occm_system* sys, const OccmMemDev& mem, const
         occm_set_error("error partials per member (%d) exceed the carved capacity (%zu)", g.err_stride, occm_err_capacity(sys));
         return OCCM_ERR_WORKSPACE;
     }
-    auto kern = occm_pipe<MODEL, STAGE, K, WIDE, V>;
-    int ctas_per_sm = 1;
     if (int rc = occm_kernel_prepare(&cache, (const void*)kern, sys->device, OCCM_PIPE_THREADS, smem, &ctas_per_sm)) return rc;
     const int grid = occm_grid(sys, chunks, ctas_per_sm);
     kern<<<grid, OCCM_PIPE_THREADS, smem, st>>>(sys->dev, mem, rk, y_in, dy_out, (const OccmEllEntry*)sys->desc.ell_packed, g);

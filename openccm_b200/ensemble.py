@@ -184,8 +184,9 @@ class EnsembleSolver:
                 res = sysd.rk45(yb, self.t_span, rtol=self.rtol, atol=self.atol, first_step=self.first_step, t_eval=te,
                                 save_idx=save_dev, members=mem)
             else:
-                from .bdf import solve_bdf
-                res = solve_bdf(sysd, yb, self.t_span, rtol=self.rtol, atol=self.atol, first_step=self.first_step,
+                from .bdf import device_tolerances, solve_bdf
+                rtol_d, atol_d = device_tolerances(self.rtol, self.atol)
+                res = solve_bdf(sysd, yb, self.t_span, rtol=rtol_d, atol=atol_d, first_step=self.first_step,
                                 t_eval=te, save_idx=save_dev, members=mem)
             y_parts.append(res.y)
             status.append(res.status); nfev.append(res.nfev); nacc.append(res.n_accepted); nrej.append(res.n_rejected)

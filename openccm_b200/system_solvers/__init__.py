@@ -6,7 +6,9 @@ Device replacement for ``openccm.system_solvers`` (/root/reference/openccm/syste
 liboccm_b200.so.  Selection is by ``[SIMULATION] solver``:
 
     B200-RK45   adaptive Dormand-Prince, step-for-step mirror of scipy's RK45
-    B200-BDF    variable-order BDF with Newton + preconditioned GMRES (stiff networks)
+    B200-BDF    variable-order BDF with Newton + preconditioned GMRES (stiff networks); integrates at 0.01 x the
+                user's (rtol, atol) so that it meets the 1e-10 + 1e-6 |c| band wherever the reference's LSODA does
+                (openccm_b200.bdf.device_tolerances)
 
 Any other solver name raises here (this package has no CPU path); ``openccm_b200.dropin.install()`` forwards
 those names to the reference's own scipy path when the reference is importable.
@@ -52,8 +54,9 @@ def solve_system(model: str, model_network, config_parser, cmesh, *, return_info
     if solver == 'B200-RK45':
         res = dev.rk45(y0, t_span, rtol=rtol, atol=atol, first_step=first_timestep, t_eval=t_eval, max_steps=max_steps)
     else:
-        from ..bdf import solve_bdf
-        res = solve_bdf(dev, y0, t_span, rtol=rtol, atol=atol, first_step=first_timestep, t_eval=t_eval, max_steps=max_steps)
+        from ..bdf import device_tolerances, solve_bdf
+        rtol_d, atol_d = device_tolerances(rtol, atol)         # tolerance-mapping policy of B200-BDF (see its docstring)
+        res = solve_bdf(dev, y0, t_span, rtol=rtol_d, atol=atol_d, first_step=first_timestep, t_eval=t_eval, max_steps=max_steps)
     status = int(res.status[0])
     message = STATUS_MESSAGES.get(status, str(status))
     if model == 'pfr':

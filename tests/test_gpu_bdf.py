@@ -1,8 +1,10 @@
-"""Device BDF (Newton + block-Jacobi GMRES) against the reference's golden solves.
+"""Device BDF (Newton + preconditioned GMRES) against tight solutions of the unmodified reference.
 
-Two adaptive integrators agree only to about their tolerance, so (SURVEY.md §7 "hard parts") the device BDF is run at
-tolerances tighter than the acceptance band and compared with the tight LSODA goldens of the unmodified reference:
-band rtol 1e-6 / atol 1e-10 is asserted wherever the golden itself is that accurate (its own rtol is 1e-8 / 1e-10)."""
+Two adaptive integrators agree only to about their tolerance (SURVEY.md §7 "hard parts"), so the yard-stick is a tight
+solution (tests/golden/tight_*.npz: the reference with LSODA at rtol 1e-13 / atol 1e-15, confirmed by DOP853 / Radau) and the
+device runs at the USER tolerance of the north star, rtol 1e-6 / atol 1e-10, through `solver = B200-BDF` — whose documented
+tolerance-mapping policy (openccm_b200.bdf.device_tolerances) is what makes it meet the band.  For context the goldens also
+hold the reference's own LSODA solve at the same user tolerance; the tests print how it fares."""
 import numpy as np
 import pytest
 
@@ -12,49 +14,46 @@ from _util import load_golden, setup_case
 pytestmark = pytest.mark.gpu
 
 CASES = ['cstr_irreversible', 'cstr_monod', 'cstr_net12_nacl', 'cstr_net20_timebc', 'pfr_single', 'pfr_net8', 'pfr_net8_nacl',
-         'cstr_net10_pointmass']
+         'cstr_net10_pointmass', 'pfr_net6_pointmass', 'cstr_net9_tracer', 'pfr_chains_tracer']
+
+
+def band_units(c, tight):
+    return np.abs(c - tight) / (1e-10 + 1e-6 * np.abs(tight))
+
+
+def solve_at_user_tolerance(name, tmp_path):
+    from openccm_b200.system_solvers import solve_system
+    cp, cmesh, net, mn = setup_case(name, 'B200-BDF', tmp_path, rtol=1e-6, atol=1e-10)
+    c, t, imap, omap, info = solve_system(C.CASES[name]['model'], mn, cp, cmesh, return_info=True)
+    assert info['status'] == 1, info
+    tg = load_golden(f'tight_{name}')
+    np.testing.assert_allclose(t, tg['t'], rtol=0, atol=1e-14)
+    e_dev, e_ref = band_units(c, tg['c_tight']), band_units(tg['c_user_LSODA'], tg['c_tight'])
+    print(f'{name}: device max {e_dev.max():.3f} band units (nfev {info["nfev"]}); reference LSODA at the same tolerance: '
+          f'max {e_ref.max():.2f}, {100 * (e_ref <= 1).mean():.1f} % of the outputs in band (nfev {int(tg["nfev_user_LSODA"])})')
+    return e_dev, e_ref, info
 
 
 @pytest.mark.parametrize('name', CASES)
-def test_bdf_matches_reference(name, tmp_path):
-    """Device BDF at rtol 1e-9 vs the oracle (restated ddt + scipy LSODA) at rtol 1e-11: north-star band at every output."""
-    from oracle import openccm_oracle as O
-    from openccm_b200.system_solvers import solve_system
-    g = load_golden(name)
-    cp, cmesh, net, mn = setup_case(name, 'B200-BDF', tmp_path, rtol=1e-9, atol=1e-12)
-    c, t, imap, omap, info = solve_system(C.CASES[name]['model'], mn, cp, cmesh, return_info=True)
-    assert info['status'] == 1, info
-    cpo, cmesho, _, mno = setup_case(name, 'LSODA', tmp_path, rtol=1e-11, atol=1e-13)
-    ref, t_ref, *_ = O.solve_system(C.CASES[name]['model'], mno, cpo, cmesho)
-    np.testing.assert_allclose(t, t_ref, rtol=0, atol=1e-14)
-    assert np.all(np.abs(c - ref) <= 1e-10 + 1e-6 * np.abs(ref)), np.abs(c - ref).max()
-    # the reference's own (looser, rtol 1e-8) golden solve agrees within its tolerance
-    assert np.all(np.abs(c - g['c_LSODA']) <= 5e-7 + 1e-6 * np.abs(g['c_LSODA']))
+def test_bdf_at_the_user_tolerance_is_inside_the_band(name, tmp_path):
+    """North-star band 1e-10 + 1e-6 |c| around the tight solution, at every output time of every DOF — not only where the
+    reference's own solver at that tolerance happens to be inside it."""
+    e_dev, e_ref, info = solve_at_user_tolerance(name, tmp_path)
+    assert e_dev.max() <= 1.0, e_dev.max()
 
 
 def test_bdf_openfoam_network(tmp_path):
-    """C2: the stiff 444-PFR network (residence times 8e-4 .. 4e3) — where scipy RK45 needs 8e5 RHS calls."""
-    from openccm_b200.system_solvers import solve_system
-    g = load_golden('openfoam_2d_pfr')
-    cp, cmesh, net, mn = setup_case('openfoam_2d_pfr', 'B200-BDF', tmp_path, rtol=1e-9, atol=1e-12)
-    c, t, imap, omap, info = solve_system('pfr', mn, cp, cmesh, return_info=True)
-    assert info['status'] == 1, info
-    ref = g['c_LSODA']                       # LSODA at rtol 1e-10 / atol 1e-12
-    assert np.all(np.abs(c - ref) <= 1e-8 + 1e-6 * np.abs(ref)), np.abs(c - ref).max()
-    assert info['nfev'] < 400_000
+    """C2: the stiff 444-PFR network (residence times 8e-4 .. 4e3) — where scipy RK45 needs 8e5 RHS calls and the
+    reference's LSODA 37 534 (36 408 of them for dense finite-difference Jacobians)."""
+    e_dev, e_ref, info = solve_at_user_tolerance('openfoam_2d_pfr', tmp_path)
+    assert e_dev.max() <= 1.0, e_dev.max()
+    assert info['nfev'] < 40_000
 
 
 def test_bdf_openfoam_cstr_nacl(tmp_path):
-    """C3 (BASELINE.json configs[2]): 76 CSTRs of the OpenFOAM example, 2NaCl + CaCO3 <-> Na2CO3 + CaCl2, against the
-    unmodified reference's LSODA solve at rtol 1e-10 / atol 1e-12."""
-    from openccm_b200.system_solvers import solve_system
-    g = load_golden('openfoam_2d_cstr_nacl')
-    cp, cmesh, net, mn = setup_case('openfoam_2d_cstr_nacl', 'B200-BDF', tmp_path, rtol=1e-9, atol=1e-12)
-    c, t, imap, omap, info = solve_system('cstr', mn, cp, cmesh, return_info=True)
-    assert info['status'] == 1, info
-    ref = g['c_LSODA']
-    np.testing.assert_allclose(t, g['t_LSODA'], rtol=0, atol=1e-14)
-    assert np.all(np.abs(c - ref) <= 1e-8 + 1e-6 * np.abs(ref)), np.abs(c - ref).max()
+    """C3 (BASELINE.json configs[2]): 76 CSTRs of the OpenFOAM example, 2NaCl + CaCO3 <-> Na2CO3 + CaCl2."""
+    e_dev, e_ref, info = solve_at_user_tolerance('openfoam_2d_cstr_nacl', tmp_path)
+    assert e_dev.max() <= 1.0, e_dev.max()
 
 
 def test_bdf_batched_members(tmp_path):
@@ -63,7 +62,7 @@ def test_bdf_batched_members(tmp_path):
     from openccm_b200.ensemble import EnsembleSolver
     import scipy.integrate
     name = 'cstr_net12_nacl'
-    cp, cmesh, net, mn = setup_case(name, 'B200-BDF', tmp_path, rtol=1e-9, atol=1e-12)
+    cp, cmesh, net, mn = setup_case(name, 'B200-BDF', tmp_path, rtol=1e-7, atol=1e-10)      # the device integrates at 1e-9 / 1e-12
     solver = EnsembleSolver('cstr', mn, cp, cmesh)
     M = 4
     rng = np.random.default_rng(3)

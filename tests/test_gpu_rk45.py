@@ -9,12 +9,23 @@ from _util import load_golden, setup_case
 
 pytestmark = pytest.mark.gpu
 
-# Linear cases that sit at steady state for most of the interval: there the RK45 error estimate is pure round-off, the
-# step sequence is governed by noise, and scipy itself moves by ~1e-8 when its RHS is perturbed by 1e-16 relative
-# (measured in the build container).  They are held to the acceptance band only.
+import os
+
+from _util import GOLDEN_DIR
+
+# Linear cases that sit at steady state for most of the interval: there the RK45 error estimate is pure round-off, the step
+# sequence is governed by noise, and two runs of the same algorithm (scipy vs scipy with its RHS perturbed by 1e-16) differ by
+# ~1e-8.  Comparing two such answers with each other needs a relaxed band; comparing EACH with a tight-tolerance solution of
+# the unmodified reference (tests/golden/tight_*.npz: LSODA at rtol 1e-13, confirmed by DOP853) does not.
 ROUNDOFF_LIMITED = {'cstr_net9_tracer', 'cstr_reversible', 'pfr_chains_tracer'}
 
 RK_CASES = [n for n in sorted(C.CASES) if 'RK45' in C.CASES[n].get('solvers', ('RK45', 'LSODA'))]
+TIGHT_RK_CASES = [n for n in RK_CASES if os.path.exists(os.path.join(GOLDEN_DIR, f'tight_{n}.npz'))]
+
+
+def band_units(c, tight):
+    """|c - tight| in units of the north-star acceptance band 1e-10 + 1e-6 |tight|."""
+    return np.abs(c - tight) / (1e-10 + 1e-6 * np.abs(tight))
 
 
 @pytest.mark.parametrize('name', RK_CASES)
@@ -28,13 +39,40 @@ def test_solve_system_matches_reference_rk45(name, tmp_path):
     np.testing.assert_allclose(t, g['t_RK45'], rtol=0, atol=1e-14)
     ref = g['c_RK45']
     if name in ROUNDOFF_LIMITED:
-        # scipy-vs-perturbed-scipy moves by up to ~1e-8 here (see above): rtol 1e-6 with the atol that noise floor allows
-        assert np.all(np.abs(c - ref) <= 2e-7 + 1e-6 * np.abs(ref))
+        # both the reference's solve and the device's sit inside the acceptance band around the tight solution, at every output
+        tight = load_golden(f'tight_{name}')['c_tight']
+        assert band_units(ref, tight).max() <= 1.0
+        assert band_units(c, tight).max() <= 1.0, band_units(c, tight).max()
+        assert abs(info['nfev'] - int(g['nfev_RK45'])) <= 0.05 * int(g['nfev_RK45'])      # step sequence governed by round-off
     else:
         # north-star acceptance band at every output time, and the much tighter band a step-exact mirror reaches
         assert np.all(np.abs(c - ref) <= 1e-10 + 1e-6 * np.abs(ref))
         np.testing.assert_allclose(c, ref, rtol=1e-9, atol=2e-12)
-    assert abs(info['nfev'] - int(g['nfev_RK45'])) <= (60 if name in ROUNDOFF_LIMITED else 12)
+        assert abs(info['nfev'] - int(g['nfev_RK45'])) <= 12
+
+
+@pytest.mark.parametrize('name', TIGHT_RK_CASES)
+def test_rk45_at_the_user_tolerance_is_in_band_wherever_scipy_is(name, tmp_path):
+    """rtol 1e-6 / atol 1e-10 (the north star's numbers).  At that tolerance the reference's own RK45 is up to 250 bands away
+    from the tight solution on some cases (tests/golden/make_golden.py --tight prints them), so the assertion is: the device
+    is inside the band wherever scipy is, never further out than scipy, and spends the same number of RHS calls."""
+    from openccm_b200.system_solvers import solve_system
+    tg = load_golden(f'tight_{name}')
+    cp, cmesh, net, mn = setup_case(name, 'B200-RK45', tmp_path, rtol=1e-6, atol=1e-10)
+    c, t, imap, omap, info = solve_system(C.CASES[name]['model'], mn, cp, cmesh, return_info=True)
+    assert info['status'] == 1
+    np.testing.assert_allclose(t, tg['t'], rtol=0, atol=1e-14)
+    e_dev, e_ref = band_units(c, tg['c_tight']), band_units(tg['c_user_RK45'], tg['c_tight'])
+    if name in ROUNDOFF_LIMITED:
+        # accepted steps are decided by round-off in the error estimate: WHICH outputs land inside the band differs between two
+        # runs of the same algorithm, so the statement is about the distribution — as many outputs in band as scipy, none further out
+        assert (e_dev <= 1.0).mean() >= (e_ref <= 1.0).mean() - 0.02, ((e_dev <= 1.0).mean(), (e_ref <= 1.0).mean())
+        slack = 0.05
+    else:
+        assert np.all(e_dev[e_ref <= 0.98] <= 1.0), e_dev[e_ref <= 0.98].max()
+        slack = 0.02
+    assert e_dev.max() <= (1 + slack) * e_ref.max() + 0.02, (e_dev.max(), e_ref.max())
+    assert abs(info['nfev'] - int(tg['nfev_user_RK45'])) <= slack * int(tg['nfev_user_RK45'])
 
 
 @pytest.mark.parametrize('name', ['cstr_irreversible', 'cstr_net12_nacl', 'pfr_net8', 'cstr_net20_timebc'])

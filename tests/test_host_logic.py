@@ -163,11 +163,19 @@ def test_dropin_install_rebinds_both_names():
         from openccm_b200 import dropin
         original = ss.solve_system
         assert run_mod.solve_system is original
+        pp = importlib.import_module('openccm.postprocessing')
+        ana = importlib.import_module('openccm.postprocessing.analysis')
+        original_rtd = ana.network_to_rtd
+        assert run_mod.network_to_rtd is original_rtd and pp.network_to_rtd is original_rtd
         dropin.install()
         assert ss.solve_system is not original and run_mod.solve_system is ss.solve_system
         assert ss.solve_system.__doc__ == original.__doc__
+        # the RTD post-processing is rebound wherever the reference holds the name (run.py:32-33, :205)
+        assert run_mod.network_to_rtd is not original_rtd
+        assert run_mod.network_to_rtd is pp.network_to_rtd is ana.network_to_rtd
         dropin.uninstall()
         assert ss.solve_system is original and run_mod.solve_system is original
+        assert run_mod.network_to_rtd is original_rtd and pp.network_to_rtd is original_rtd and ana.network_to_rtd is original_rtd
     finally:
         sys.path.remove('/root/reference')
 

@@ -14,8 +14,13 @@ configuration); a "step" is one complete ensemble solve of the rank's members.
            (sum over members of nfev * N * S, divided by the max-over-ranks device time), inputs resident in HBM.
   e2e    : the same metric through the public host API (EnsembleSolver.solve with HOST numpy arrays: upload of the
            network tables, parameters and initial state, solve, download of the recorded outlet concentrations).
-  roofline: the dominant kernel = the fused Dormand-Prince stage kernel (stage 5: reads the stage state, y, K1..K4,
-           writes K5 and the next stage state), timed live with CUDA events on the launching stream.
+  roofline: the dominant kernel = the fused Dormand-Prince stage-6 kernel (largest share of the step: reads the stage state,
+           y, K1, K3..K5, writes K6, y_new and the partial error combination), timed live with CUDA events on the launching
+           stream; every stage and the plain fused RHS are reported beside it.
+  strong : the north-star configuration on THIS many GPUs: 4096 members in total, batched by free HBM on a rank.
+  bdf    : (N = 1) C5 — 1e4 PFRs x 200 points x 12 species, stiff 20-reaction mechanism — solved by the device BDF + GMRES;
+           live kernel times of the fused RHS / J*v / preconditioner inside Newton; scipy BDF + jac_sparsity on a reduced
+           instance of the same workload as its CPU baseline.
   cpu_baseline / --impl reference: the oracle port of the reference's CPU path (numpy/scipy.sparse restatement of
            cstr_system.ddt + scipy.integrate.solve_ivp RK45) on a bounded member sample, all host cores.
 """
@@ -50,6 +55,9 @@ def parse_args():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-sample-members', type=int, default=0, help='members of the CPU baseline sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-strong', action='store_true', help='skip the 4096-member strong-scaling solve')
+    ap.add_argument('--no-bdf', action='store_true', help='skip the C5 BDF block (N = 1)')
+    ap.add_argument('--strong-members', type=int, default=4096)
     return ap.parse_args()
 
 
@@ -244,6 +252,86 @@ def run_reference_arm(args):
     _emit(line)
 
 
+
+# ------------------------------------------------------------------------------------------------ BDF block (C5)
+def _bdf_cpu_job(payload):
+    """scipy BDF + jac_sparsity (openccm_b200.system_solvers.jacobian) around the oracle's restated pfr ddt, reduced C5."""
+    n_chains, chain_len, P, t_end = payload
+    import tempfile
+    import scipy.integrate
+    from oracle import openccm_oracle as O
+    from openccm_b200.system_solvers.export import export_system
+    from openccm_b200.system_solvers.jacobian import jacobian_sparsity
+    from openccm_b200.workloads import pfr_stiff_workload
+    model, net, cp, cmesh = pfr_stiff_workload(n_chains=n_chains, chain_len=chain_len, P=P, t_end=t_end, n_out=11, workdir=tempfile.mkdtemp())
+    host = export_system(model, net, cp, cmesh)
+    ora = O.build_pfr(net.to_model_network(), cp, cmesh)
+    J = jacobian_sparsity(host)
+    np.seterr(all='warn', under='ignore')
+    t0 = time.perf_counter()
+    r = scipy.integrate.solve_ivp(ora.fun, (0.0, t_end), ora.y0, method='BDF', rtol=1e-6, atol=1e-10, first_step=1e-4,
+                                  t_eval=np.linspace(0.0, t_end, 11), jac_sparsity=J)
+    return host.ndof, time.perf_counter() - t0, int(r.nfev), int(r.njev), int(r.nlu), int(r.status)
+
+
+def bdf_block(args, peak):
+    """C5: Np = 1e4 PFRs x 200 points x 12 species = 2.4e7 DOF, 20-reaction mechanism with k from 1e-3 to 1e4, t in [0, 20]."""
+    import torch
+    from openccm_b200.bdf import BdfRun, device_tolerances
+    from openccm_b200.device import DeviceSystem
+    from openccm_b200.system_solvers.export import export_system
+    from openccm_b200.workloads import pfr_stiff_workload
+    t_end = 20.0
+    model, net, cp, cmesh = pfr_stiff_workload(n_chains=500, chain_len=20, P=200, t_end=t_end)
+    host = export_system(model, net, cp, cmesh)
+    dev = DeviceSystem(host)
+    y0 = torch.as_tensor(host.to_device_layout(host.c0.reshape(-1)), device='cuda')[None].contiguous()
+    te = np.linspace(0.0, t_end, 41)
+    save = torch.arange(0, host.ndof, max(1, host.ndof // 1000), dtype=torch.int32, device='cuda')
+    rtol, atol = 1e-6, 1e-10                     # the integrator's own tolerances (C5 as measured in round 1); the B200-BDF solver
+    kw = dict(rtol=rtol, atol=atol, first_step=1e-4, t_eval=te, save_idx=save)     # name would map them through device_tolerances
+    with BdfRun(dev, y0, (0.0, t_end), **kw) as run:                                # warm-up slice
+        run.run(max_attempts=30)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with BdfRun(dev, y0, (0.0, t_end), **kw) as run:
+        ev0.record()
+        run.run()
+        ev1.record(); torch.cuda.synchronize()
+        run.stats()
+        solve_s = ev0.elapsed_time(ev1) * 1e-3
+        attempts = int(run.n_acc[0] + run.n_rej[0])
+        kern = {name: run.time_kernel(which, 10) for which, name in ((0, 'rhs'), (1, 'jv'), (2, 'precond_apply'))}
+        status, nfev, n_gmres = int(run.status[0]), int(run.nfev[0]), int(run.n_gmres[0])
+        n_factor, n_apply, n_fail = int(run.n_precond_factor[0]), int(run.n_precond_apply[0]), int(run.n_newton_fail[0])
+        mode = run.precond_mode
+    ndof, S = host.ndof, host.S
+    newton_its = nfev - n_gmres - 1                 # RHS calls that are Newton residuals (the others are Jacobian actions)
+    alg = {'rhs': 16.0 * ndof, 'jv': 24.0 * ndof, 'precond_apply': (32.0 + 8.0 * S) * ndof}      # bytes per launch (DESIGN.md §3)
+    roof = {k: {"ms_per_launch": v, "achieved_gbs": alg[k] / (v * 1e-3) / 1e9, "frac": alg[k] / (v * 1e-3) / 1e9 / peak} for k, v in kern.items()}
+    out = {"workload": "C5: 1e4 PFRs (500 recycle chains of 20) x 200 points x 12 species = 2.4e7 DOF, 20 reactions with k in [1e-3, 1e4], "
+                       "t in [0, 20], rtol 1e-6 atol 1e-10, BDF + block-preconditioned GMRES(30), one member",
+           "status": status, "solve_s": solve_s, "solves_per_s": 1.0 / solve_s, "attempts": attempts, "ms_per_attempt": 1e3 * solve_s / max(attempts, 1),
+           "accepted": int(run.n_acc[0]), "newton_failures": n_fail, "rhs_calls": nfev, "gmres_iterations": n_gmres,
+           "gmres_per_newton": n_gmres / max(newton_its, 1), "newton_per_attempt": newton_its / max(attempts, 1),
+           "precond": {"mode": mode, "applications": n_apply, "rebuilds": n_factor},
+           "dof_steps_per_s": ndof * float(run.n_acc[0]) / solve_s,
+           "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s", "kernels": roof}}
+    del dev, y0
+    torch.cuda.empty_cache()
+    if not args.no_cpu_baseline:
+        try:
+            import multiprocessing as mp
+            with mp.get_context('spawn').Pool(1) as pool:
+                nd, sec, nf, nj, nl, st = pool.map(_bdf_cpu_job, [(5, 10, 20, 5.0)])[0]
+            out["cpu_baseline"] = {"kind": "port", "cores": 1, "ndof": nd, "seconds": sec, "nfev": nf, "njev": nj, "nlu": nl, "status": st,
+                                   "sample": "reduced C5 (5 chains x 10 PFRs x 20 points x 12 species, t in [0, 5]): scipy BDF with "
+                                             "jac_sparsity around the oracle's restated pfr ddt, rtol 1e-6 atol 1e-10, one core"}
+        except Exception as exc:
+            out["cpu_baseline"] = {"failed": repr(exc)}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ device arm
 _REAL_STDOUT = None
 
@@ -298,8 +386,10 @@ def main():
     M_loc = args.members_per_gpu
     M_glob = M_loc * world_size
     ks_all, qs_all, ics_all = syn.ensemble_sweeps(M_glob, host.tables.n_rxn)
-    lo, hi = rank * M_loc, (rank + 1) * M_loc
-    ks, qs, ics = ks_all[lo:hi], qs_all[lo:hi], ics_all[lo:hi]
+    # members are dealt to the ranks by a stiffness estimate (boustrophedon over the sorted list): every rank gets the same mix
+    from openccm_b200.ensemble import balanced_order, stiffness_estimate
+    mine = balanced_order(stiffness_estimate(host, M_glob, ks_all, qs_all), world_size)[rank * M_loc:(rank + 1) * M_loc]
+    ks, qs, ics = ks_all[mine], qs_all[mine], ics_all[mine]
     save_idx = solver.outlet_save_idx()
     te = np.asarray(solver.t_eval)
     dev = solver.upload()
@@ -367,60 +457,71 @@ def main():
     def e2e_step():
         solver_e2e.dev = None                      # re-upload tables every step
         # global host arrays in; the solver takes this rank's contiguous member block (no collective on the data path)
-        r = solver_e2e.solve(M_glob, k_scale=ks_all, q_scale=qs_all, ic_scale=ics_all, save=save_idx, gather=False)
+        # (the NCCL all_gather of the recorded outlet concentrations + RTD arrays and the all_reduce of the RTD moment statistics
+        #  — the only collectives of the path — are inside the timed region)
+        r = solver_e2e.solve(M_glob, k_scale=ks_all, q_scale=qs_all, ic_scale=ics_all, save=save_idx, gather=True, rtd=True)
         return r
     for _ in range(min(args.warmup, 1)):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
     nfev_e2e = 0
+    gather_ms, reduce_ms = [], []
     for _ in range(args.steps):
         r = e2e_step()
-        nfev_e2e += int(r.nfev.sum())
+        nfev_e2e += int(r.nfev.sum())            # gathered: every rank holds the counters of ALL members
+        gather_ms.append(1e3 * r.timing.get('gather_s', 0.0)); reduce_ms.append(1e3 * r.timing.get('reduce_s', 0.0))
     barrier()
     e2e_s = time.perf_counter() - t0
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-    w_e = torch.tensor([float(nfev_e2e)], dtype=torch.float64, device=device)
     if world_size > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX); dist.all_reduce(w_e, op=dist.ReduceOp.SUM)
-    e2e_value = float(w_e.item()) * N * S / float(t_e.item())
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = float(nfev_e2e) * N * S / float(t_e.item())
     blob_bytes = host.tables.pack().nbytes
     h2d = (host.row_ptr.nbytes + host.row_src.nbytes + host.row_w.nbytes) * 2 + blob_bytes + host.c0.nbytes + \
         ks.nbytes + qs.nbytes + ics.nbytes + save_idx.nbytes + te.nbytes
-    d2h = M_loc * len(te) * len(save_idx) * 8 + M_loc * (4 + 3 * 8)
+    # every rank downloads the gathered members: recorded outlets [M, T, n_save], RTD [M, S, T, 3], moments, counters
+    d2h = M_glob * (len(te) * len(save_idx) * 8 + S * len(te) * 3 * 8 + S * 3 * 8 + 4 + 3 * 8)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- roofline of the dominant kernel (rank 0): fused stage-5 kernel, live CUDA-event timing
+    # ---- roofline of the dominant kernel (rank 0): fused stage-6 kernel (largest share of the step), live CUDA-event timing
     roof = None
     plain = None
+    STAGE_BYTES = {2: 32, 3: 48, 4: 56, 5: 64, 6: 72, 7: 32}       # algorithmic bytes per element
     if rank == 0:
         with dev.open_rk45(y0, solver.t_span, rtol=solver.rtol, atol=solver.atol, first_step=solver.first_step,
                            t_eval=te, save_idx=save_dev, members=mem) as run:
             run.run(max_launch_steps=2)            # buffers hold a genuine mid-solve state
-            run.time_stage(5, 3)
-            ms5 = run.time_stage(5, 10)
-            stage_ms = {s: run.time_stage(s, 5) for s in (2, 3, 4, 5, 6, 7)}
+            run.time_stage(6, 3)
+            ms6 = run.time_stage(6, 10)
+            stage_ms = {}
+            for s_ in (2, 3, 4, 5, 6, 7):
+                run.time_stage(s_, 2)              # two untimed launches of the stage, then five timed ones
+                stage_ms[s_] = run.time_stage(s_, 5)
         nnz = len(host.row_src)
         csr_bytes = 12 * nnz + 4 * (N + 1)
-        alg5 = M_loc * ndof * 8 * 8 + csr_bytes          # 6 vector reads + 2 vector writes per element, CSR once
+        alg6 = M_loc * ndof * STAGE_BYTES[6] + csr_bytes          # 6 vector reads + 3 vector writes per element, CSR once
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))
         except Exception:
             pass
         peak = float(peaks.get('hbm_gbs', 6650.0))
-        ach = alg5 / (ms5 * 1e-3) / 1e9
+        ach = alg6 / (ms6 * 1e-3) / 1e9
         traffic = None          # dram__bytes_read + dram__bytes_write of this kernel from the committed ncu capture (same workload)
         try:
-            tr = json.load(open(os.path.join(REPO, 'profiles', 'traffic_r01.json')))
+            tr = json.load(open(os.path.join(REPO, 'profiles', 'traffic_r02.json')))
             if tr.get('members_per_gpu') == M_loc and tr.get('n_cstr') == N:
                 traffic = tr['traffic_bytes_per_launch']
         except Exception:
             pass
-        roof = {"bound": "hbm", "kernel": "occm_fast_cstr<stage 5, K> (fused Dormand-Prince stage: RHS + next stage state)", "achieved": ach, "peak": peak, "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": "occm_pipe<CSTR, stage 6, K> (fused Dormand-Prince stage: RHS of the stage state + K6, y_new and the "
+                                          "partial error combination; TMA bulk-copy ring)",
+                "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
-                "ms_per_launch": ms5, "alg_bytes_per_launch": alg5,
+                "ms_per_launch": ms6, "alg_bytes_per_launch": alg6,
                 "stage_ms": stage_ms,
+                "stage_frac": {s: (M_loc * ndof * STAGE_BYTES[s] + csr_bytes) / (v * 1e-3) / 1e9 / peak for s, v in stage_ms.items()},
                 # all six stage kernels of a step attempt together: 304 B per element over their summed time
                 "all_stages_frac": (M_loc * ndof * 304.0 + 6 * csr_bytes) / (sum(stage_ms.values()) * 1e-3) / 1e9 / peak}
         # plain fused RHS (16 B per compartment-species eval)
@@ -438,6 +539,42 @@ def main():
                  "frac": alg_r / (ms_r * 1e-3) / 1e9 / peak}
         del dy
 
+    # ---- strong scaling: the north-star ensemble (4096 members in total) on this many GPUs, batched by free HBM per rank
+    strong = None
+    del y0, mem
+    torch.cuda.empty_cache()
+    if not args.no_strong:
+        M_s = args.strong_members
+        ks_s, qs_s, ics_s = syn.ensemble_sweeps(M_s, host.tables.n_rxn)
+        solver_s = EnsembleSolver(model, net, cp, cmesh, host=host)
+        solver_s.dev = dev
+        bpr = -(-(M_s // world_size) // solver_s.members_per_batch(len(save_idx), len(te)))
+        barrier()
+        t0 = time.perf_counter()
+        r_s = solver_s.solve(M_s, k_scale=ks_s, q_scale=qs_s, ic_scale=ics_s, save=save_idx, gather=True, rtd=True)
+        barrier()
+        t_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        if world_size > 1:
+            dist.all_reduce(t_s, op=dist.ReduceOp.MAX)
+        assert np.all(r_s.status == 1)
+        lo_s, hi_s = r_s.local_range
+        strong = {"scaling": "strong", "members_total": M_s, "members_per_rank": hi_s - lo_s, "seconds": float(t_s.item()),
+                  "ode_solves_per_s": M_s / float(t_s.item()), "evals_per_s": float(r_s.nfev.sum()) * N * S / float(t_s.item()),
+                  "batches_per_rank": bpr,
+                  "gather_ms": 1e3 * r_s.timing.get('gather_s', 0.0), "reduce_ms": 1e3 * r_s.timing.get('reduce_s', 0.0),
+                  "note": "host API (EnsembleSolver.solve): host arrays in, gathered outlets + RTD out, one timed solve"}
+        del r_s
+
+    # ---- BDF + GMRES on C5 (N = 1 only: a single network does not shard)
+    bdf = None
+    if rank == 0 and world_size == 1 and not args.no_bdf:
+        del solver_e2e, solver, dev
+        torch.cuda.empty_cache()
+        try:
+            bdf = bdf_block(args, peak if rank == 0 else 6650.0)
+        except Exception as exc:           # never take the headline down
+            bdf = {"failed": repr(exc)}
+
     cpu = None
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
         try:
@@ -452,11 +589,14 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "members_per_gpu": M_loc, "members_total": M_glob, "n_cstr": N, "n_species": S,
                            "l2": f"inputs larger than L2: {11 * M_loc * ndof * 8 / 2**30:.1f} GiB of state vectors per GPU",
-                           "parallelism": f"members sharded over {world_size} GPU(s), no data-path collective"},
+                           "parallelism": f"members dealt to {world_size} GPU(s) by a stiffness estimate, no data-path collective"},
                 "ode_solves_per_s": solves_per_s, "rhs_evals_total": evals, "step_ms": step_ms,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "solves_per_s": M_glob * args.steps / float(t_e.item())},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "plain_rhs": plain, "cpu_baseline": cpu}
+                        "solves_per_s": M_glob * args.steps / float(t_e.item()),
+                        "collectives": "all_gather(outlets, RTD, counters) + all_reduce(RTD moment statistics) inside the timed region",
+                        "gather_ms": float(np.mean(gather_ms)), "reduce_ms": float(np.mean(reduce_ms))},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "plain_rhs": plain, "cpu_baseline": cpu,
+                "strong": strong, "bdf": bdf}
         _emit(line)
     if world_size > 1:
         dist.destroy_process_group()

@@ -230,6 +230,18 @@ int occm_rtd(const double* out, int32_t n_members, int32_t n_times, int32_t n_sa
              double q_in_total, double* rtd, double* moments, void* stream);
 
 /*
+ * The same from a PULSE experiment (north star item 4; the reference's precedent is the point-mass initial condition turned
+ * into a short smoothed rectangular source, system_solvers/boundary_and_initial_conditions.py:174-180, used by
+ * examples/OpenCMP/closed_box/CONFIG:20-27): the recorded outlet concentrations are the response to an inlet pulse u(t) of
+ * known area / mean / variance, so E(t) = sum_k out * w / q_in_total / pulse_area with no differentiation, F = its running
+ * trapezoid integral, and the moments are those of the response minus the pulse's own (moments of a convolution add).
+ */
+int occm_rtd_pulse(const double* out, int32_t n_members, int32_t n_times, int32_t n_save, const double* t, int32_t t_per_member,
+                   const int32_t* sel_idx, const double* sel_w, const int32_t* sel_species, int32_t n_sel, int32_t n_species,
+                   double q_in_total, double pulse_area, double pulse_mean, double pulse_variance, double* rtd, double* moments,
+                   void* stream);
+
+/*
  * Recorded solution -> mesh elements.  Replaces the time x species x dof loops of `export_to_vtu_openfoam`
  * (postprocessing/vtu_output.py:311-322) over `create_dof_to_element_map` (mesh/__init__.py:142-198):
  *   out[t][s][element] = y[t][el_dof*S + s] * el_w + y[t][el_other*S + s] * (1 - el_w);  -1 where el_dof[element] < 0.
@@ -242,6 +254,10 @@ int occm_dofs_to_elements(const double* y, int32_t n_times, int32_t n_species, i
 /* Development/measurement aid: launch Dormand-Prince stage kernel `stage` (2..7) `reps` times back to back on the
  * handle's current buffers and return the mean duration (CUDA events on `stream`). Leaves y, t, h untouched. */
 int occm_rk45_time_stage(occm_rk45* rk, int32_t stage, int32_t reps, float* ms_per_launch, void* stream);
+
+/* The same for the kernels of the BDF Newton / GMRES loop, on the handle's current buffers (run a few attempts first):
+ * which = 0 fused RHS at the predictor, 1 matrix-free Jacobian action (RHS of y + eps z), 2 preconditioner application. */
+int occm_bdf_time_kernel(occm_bdf* bdf, int32_t which, int32_t reps, float* ms_per_launch, void* stream);
 
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t occm_launch_count(void);

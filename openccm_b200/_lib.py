@@ -75,8 +75,11 @@ SIGNATURES = {
     'occm_bdf_stats': (C.c_int, [C.c_void_p] * 11),
     'occm_bdf_get_state': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'occm_bdf_free': (C.c_int, [C.c_void_p]),
+    'occm_bdf_time_kernel': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_void_p]),
     'occm_dofs_to_elements': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),
+    'occm_rtd_pulse': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     'occm_rtd': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                            C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

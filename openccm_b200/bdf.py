@@ -62,82 +62,125 @@ def transport_diagonal(system: DeviceSystem) -> torch.Tensor:
     return torch.as_tensor(np.ascontiguousarray(d), device=system.dev)
 
 
-def solve_bdf(system: DeviceSystem, y0: torch.Tensor, t_span: Sequence[float], *, rtol: float, atol: float, first_step: float,
-              t_eval: Optional[Sequence[float]] = None, save_idx: Optional[torch.Tensor] = None,
-              members: Optional[MemberParams] = None, max_steps: int = 0, gmres_restart: int = 30, lin_tol_factor: float = 0.0,
-              all_capacity: int = 4096, return_final: bool = False, precond_mode: Optional[int] = None) -> BdfResult:
+class BdfRun:
+    """One batched BDF integration: owns the workspace / output tensors and the C handle (context manager)."""
+
+    def __init__(self, system: DeviceSystem, y0: torch.Tensor, t_span: Sequence[float], *, rtol: float, atol: float, first_step: float,
+                 t_eval: Optional[Sequence[float]] = None, save_idx: Optional[torch.Tensor] = None,
+                 members: Optional[MemberParams] = None, max_steps: int = 0, gmres_restart: int = 30, lin_tol_factor: float = 0.0,
+                 all_capacity: int = 4096, precond_mode: Optional[int] = None):
+        auto_mode = precond_mode is None and 'OCCM_B200_BDF_PRECOND' not in os.environ
+        if precond_mode is None:
+            precond_mode = int(os.environ.get('OCCM_B200_BDF_PRECOND', '0'))
+        assert y0.is_cuda and y0.dtype == torch.float64 and y0.is_contiguous()
+        self.sys = system
+        lib = self.lib = system.lib
+        M = self.M = 1 if y0.dim() == 1 else y0.shape[0]
+        assert y0.numel() == M * system.ndof
+        self.members = members if members is not None else MemberParams(M)
+        self.n_save = system.ndof if save_idx is None else int(save_idx.numel())
+        self.all_mode = t_eval is None
+        if self.all_mode:
+            T, self.te, self.te_np = int(all_capacity), None, None
+        else:
+            te_np = np.ascontiguousarray(np.asarray(t_eval, dtype=np.float64))
+            if np.any(te_np < min(t_span)) or np.any(te_np > max(t_span)):
+                raise ValueError("Values in `t_eval` are not within `t_span`.")
+            if np.any(np.diff(te_np) <= 0):
+                raise ValueError("Values in `t_eval` are not properly sorted.")
+            T = te_np.size
+            self.te_np = te_np
+            self.te = torch.as_tensor(te_np, device=system.dev)
+        self.out = torch.empty((M, T, self.n_save), dtype=torch.float64, device=system.dev)
+        self.out_t = torch.empty((M, T), dtype=torch.float64, device=system.dev)
+        self.tdiag = transport_diagonal(system)
+        ws_bytes = lib.occm_bdf_workspace_bytes(system.handle, M, gmres_restart, int(precond_mode))
+        if auto_mode and precond_mode == 0:
+            # the stored block inverses are optional: drop them when they would not fit next to the Krylov vectors
+            free_bytes = torch.cuda.mem_get_info(system.dev)[0]
+            if ws_bytes > 0.9 * free_bytes:
+                precond_mode = 1
+                ws_bytes = lib.occm_bdf_workspace_bytes(system.handle, M, gmres_restart, 1)
+        self.precond_mode = int(precond_mode)
+        self.ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=system.dev)
+        ws_ptr = (self.ws.data_ptr() + 255) & ~255
+        self.save_idx = save_idx
+        prob = _lib.BdfProblem(float(t_span[0]), float(t_span[1]), float(first_step), float(rtol), float(atol), y0.data_ptr(),
+                               _ptr(self.te), T, _ptr(save_idx), self.n_save, self.out.data_ptr(), self.out_t.data_ptr(), int(max_steps),
+                               self.tdiag.data_ptr(), int(gmres_restart), float(lin_tol_factor), int(precond_mode))
+        self._ms = self.members.c_struct()
+        self.handle = C.c_void_p()
+        _lib.check(lib.occm_bdf_init(C.byref(self.handle), system.handle, C.byref(self._ms), C.byref(prob), ws_ptr, ws_bytes, _stream()))
+        i64 = lambda: np.zeros(M, dtype=np.int64)
+        self.status = np.zeros(M, dtype=np.int32); self.order = np.zeros(M, dtype=np.int32); self.n_rows = np.zeros(M, dtype=np.int32)
+        self.n_acc, self.n_rej, self.nfev, self.n_gmres, self.n_newton_fail = i64(), i64(), i64(), i64(), i64()
+        self.n_precond_apply, self.n_precond_factor = i64(), i64()
+        self.t_now = np.zeros(M)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def close(self):
+        if self.handle:
+            self.lib.occm_bdf_free(self.handle)
+            self.handle = C.c_void_p()
+        self.ws = None
+
+    def run(self, max_attempts: int = 0) -> int:
+        """Advance until every member is finished / failed / paused, or for at most ``max_attempts`` step attempts."""
+        running = C.c_int32(0)
+        _lib.check(self.lib.occm_bdf_run(self.handle, int(max_attempts), C.byref(running), _stream()))
+        return running.value
+
+    def stats(self):
+        _lib.check(self.lib.occm_bdf_stats(self.handle, self.status.ctypes.data, self.n_acc.ctypes.data, self.n_rej.ctypes.data,
+                                           self.nfev.ctypes.data, self.n_gmres.ctypes.data, self.n_newton_fail.ctypes.data,
+                                           self.t_now.ctypes.data, self.n_rows.ctypes.data, self.order.ctypes.data, _stream()))
+        _lib.check(self.lib.occm_bdf_precond_stats(self.handle, self.n_precond_apply.ctypes.data, self.n_precond_factor.ctypes.data, _stream()))
+
+    def resume(self):
+        _lib.check(self.lib.occm_bdf_resume(self.handle, _stream()))
+
+    def time_kernel(self, which: int, reps: int = 10) -> float:
+        """Mean duration (ms, CUDA events) of one kernel of the Newton / GMRES loop on the handle's current buffers:
+        0 = fused RHS at the predictor, 1 = matrix-free J*v (RHS of y + eps z), 2 = preconditioner application."""
+        ms = C.c_float(0.0)
+        _lib.check(self.lib.occm_bdf_time_kernel(self.handle, int(which), int(reps), C.byref(ms), _stream()))
+        return float(ms.value)
+
+    def final_state(self) -> torch.Tensor:
+        y = torch.empty((self.M, self.sys.ndof), dtype=torch.float64, device=self.sys.dev)
+        _lib.check(self.lib.occm_bdf_get_state(self.handle, y.data_ptr(), _stream()))
+        torch.cuda.current_stream().synchronize()
+        return y
+
+
+def solve_bdf(system: DeviceSystem, y0: torch.Tensor, t_span: Sequence[float], *, return_final: bool = False, **kw) -> BdfResult:
     """``precond_mode``: 0 keeps the block inverses of the preconditioner in HBM (ndof * S doubles per member, rebuilt by
     CVODE's setup policy), 1 rebuilds and solves the blocks on every application; None = ``OCCM_B200_BDF_PRECOND`` or 0."""
-    auto_mode = precond_mode is None and 'OCCM_B200_BDF_PRECOND' not in os.environ
-    if precond_mode is None:
-        precond_mode = int(os.environ.get('OCCM_B200_BDF_PRECOND', '0'))
-    assert y0.is_cuda and y0.dtype == torch.float64 and y0.is_contiguous()
-    lib = system.lib
-    M = 1 if y0.dim() == 1 else y0.shape[0]
-    assert y0.numel() == M * system.ndof
-    mem = members if members is not None else MemberParams(M)
-    n_save = system.ndof if save_idx is None else int(save_idx.numel())
-    all_mode = t_eval is None
-    if all_mode:
-        T, te, te_np = int(all_capacity), None, None
-    else:
-        te_np = np.ascontiguousarray(np.asarray(t_eval, dtype=np.float64))
-        if np.any(te_np < min(t_span)) or np.any(te_np > max(t_span)):
-            raise ValueError("Values in `t_eval` are not within `t_span`.")
-        if np.any(np.diff(te_np) <= 0):
-            raise ValueError("Values in `t_eval` are not properly sorted.")
-        T = te_np.size
-        te = torch.as_tensor(te_np, device=system.dev)
-    out = torch.empty((M, T, n_save), dtype=torch.float64, device=system.dev)
-    out_t = torch.empty((M, T), dtype=torch.float64, device=system.dev)
-    tdiag = transport_diagonal(system)
-    ws_bytes = lib.occm_bdf_workspace_bytes(system.handle, M, gmres_restart, int(precond_mode))
-    if auto_mode and precond_mode == 0:
-        # the stored block inverses are optional: drop them when they would not fit next to the Krylov vectors
-        free_bytes = torch.cuda.mem_get_info(system.dev)[0]
-        if ws_bytes > 0.9 * free_bytes:
-            precond_mode = 1
-            ws_bytes = lib.occm_bdf_workspace_bytes(system.handle, M, gmres_restart, 1)
-    ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=system.dev)
-    ws_ptr = (ws.data_ptr() + 255) & ~255
-    prob = _lib.BdfProblem(float(t_span[0]), float(t_span[1]), float(first_step), float(rtol), float(atol), y0.data_ptr(),
-                           _ptr(te), T, _ptr(save_idx), n_save, out.data_ptr(), out_t.data_ptr(), int(max_steps),
-                           tdiag.data_ptr(), int(gmres_restart), float(lin_tol_factor), int(precond_mode))
-    ms = mem.c_struct()
-    handle = C.c_void_p()
-    _lib.check(lib.occm_bdf_init(C.byref(handle), system.handle, C.byref(ms), C.byref(prob), ws_ptr, ws_bytes, _stream()))
-    try:
-        status = np.zeros(M, dtype=np.int32); order = np.zeros(M, dtype=np.int32); n_rows = np.zeros(M, dtype=np.int32)
-        i64 = lambda: np.zeros(M, dtype=np.int64)
-        n_acc, n_rej, nfev, n_gm, n_nf = i64(), i64(), i64(), i64(), i64()
-        t_now = np.zeros(M)
-        running = C.c_int32(0)
+    with BdfRun(system, y0, t_span, **kw) as run:
+        M = run.M
         ts_all = [[] for _ in range(M)]; ys_all = [[] for _ in range(M)]
         while True:
-            _lib.check(lib.occm_bdf_run(handle, 0, C.byref(running), _stream()))
-            _lib.check(lib.occm_bdf_stats(handle, status.ctypes.data, n_acc.ctypes.data, n_rej.ctypes.data, nfev.ctypes.data,
-                                          n_gm.ctypes.data, n_nf.ctypes.data, t_now.ctypes.data, n_rows.ctypes.data,
-                                          order.ctypes.data, _stream()))
-            if not all_mode:
+            run.run()
+            run.stats()
+            if not run.all_mode:
                 break
             for m in range(M):
-                r = int(n_rows[m])
+                r = int(run.n_rows[m])
                 if r:
-                    ts_all[m].append(out_t[m, :r].cpu().numpy()); ys_all[m].append(out[m, :r].clone())
-            if not np.any(status == 2):
+                    ts_all[m].append(run.out_t[m, :r].cpu().numpy()); ys_all[m].append(run.out[m, :r].clone())
+            if not np.any(run.status == 2):
                 break
-            _lib.check(lib.occm_bdf_resume(handle, _stream()))
-        n_pa, n_pf = i64(), i64()
-        _lib.check(lib.occm_bdf_precond_stats(handle, n_pa.ctypes.data, n_pf.ctypes.data, _stream()))
-        y_final = None
-        if return_final:
-            y_final = torch.empty((M, system.ndof), dtype=torch.float64, device=system.dev)
-            _lib.check(lib.occm_bdf_get_state(handle, y_final.data_ptr(), _stream()))
-            torch.cuda.current_stream().synchronize()
-    finally:
-        lib.occm_bdf_free(handle)
-    if all_mode:
-        t_res = [np.concatenate(x) if x else np.zeros(0) for x in ts_all]
-        y_res = [torch.cat(x) if x else out[m, :0] for m, x in enumerate(ys_all)]
-        return BdfResult(t_res, y_res, status, n_acc, n_rej, nfev, n_gm, n_nf, y_final, None, n_pa, n_pf)
-    return BdfResult(te_np, out, status, n_acc, n_rej, nfev, n_gm, n_nf, y_final, n_rows, n_pa, n_pf)
+            run.resume()
+        y_final = run.final_state() if return_final else None
+        st = (run.status.copy(), run.n_acc.copy(), run.n_rej.copy(), run.nfev.copy(), run.n_gmres.copy(), run.n_newton_fail.copy())
+        pa, pf = run.n_precond_apply.copy(), run.n_precond_factor.copy()
+        if run.all_mode:
+            t_res = [np.concatenate(x) if x else np.zeros(0) for x in ts_all]
+            y_res = [torch.cat(x) if x else run.out[m, :0] for m, x in enumerate(ys_all)]
+            return BdfResult(t_res, y_res, *st, y_final, None, pa, pf)
+        return BdfResult(run.te_np, run.out, *st, y_final, run.n_rows.copy(), pa, pf)

@@ -33,6 +33,48 @@ def shard_bounds(n_members: int, rank: int, world_size: int) -> Tuple[int, int]:
     return n_members * rank // world_size, n_members * (rank + 1) // world_size
 
 
+def stiffness_estimate(host: HostSystem, n_members: int, k_scale: Optional[np.ndarray] = None,
+                       q_scale: Optional[np.ndarray] = None) -> np.ndarray:
+    """Fastest rate of each member, up to a constant: |transport diagonal|_max * q_scale + max_r |k_r| * k_scale[m, r]
+    (adaptive step counts differ per member; members are ordered by this before they are dealt to ranks)."""
+    rows = np.repeat(np.arange(len(host.row_ptr) - 1), np.diff(host.row_ptr))
+    if host.model == 'pfr':
+        tmax = float(np.max(np.abs(host.a))) if host.a is not None and len(host.a) else 0.0
+    else:
+        on_diag = host.row_src == rows
+        tmax = float(np.max(np.abs(host.row_w[on_diag]))) if on_diag.any() else 0.0
+    est = tmax * (np.ones(n_members) if q_scale is None else np.asarray(q_scale, dtype=np.float64)[:n_members])
+    terms = host.tables.terms
+    if terms:
+        coeff = np.array([abs(t.coeff) for t in terms]); rxn = np.array([t.rxn for t in terms])
+        if k_scale is None:
+            est = est + coeff.max()
+        else:
+            est = est + (np.asarray(k_scale, dtype=np.float64)[:n_members][:, rxn] * coeff[None, :]).max(axis=1)
+    return est
+
+
+def balanced_order(estimate: np.ndarray, world_size: int) -> np.ndarray:
+    """Permutation of the members such that rank r owns ``perm[shard_bounds(n, r, world_size)]``: members sorted by decreasing
+    stiffness estimate and dealt to the ranks in boustrophedon order (0..w-1, w-1..0, ...), so every rank gets the same mix
+    and, inside a rank, neighbours in the batch have similar step counts.  Deterministic: every rank computes the same order."""
+    n = len(estimate)
+    order = np.argsort(-np.asarray(estimate, dtype=np.float64), kind='stable')
+    cap = [shard_bounds(n, r, world_size)[1] - shard_bounds(n, r, world_size)[0] for r in range(world_size)]
+    buckets = [[] for _ in range(world_size)]
+    r, step = 0, 1
+    for mbr in order.tolist():
+        while len(buckets[r]) >= cap[r]:                      # (sizes differ by at most one)
+            r += step
+            if r == world_size or r < 0:
+                step = -step; r += step
+        buckets[r].append(mbr)
+        r += step
+        if r == world_size or r < 0:
+            step = -step; r += step
+    return np.concatenate([np.asarray(b, dtype=np.int64) for b in buckets]) if n else np.zeros(0, dtype=np.int64)
+
+
 def gather_members(local: torch.Tensor, n_members: int) -> torch.Tensor:
     """All-gather per-member rows (axis 0) from every rank, in member order. Works on CUDA (NCCL) and CPU (gloo)."""
     rank, ws = world()
@@ -77,6 +119,7 @@ class EnsembleResult:
     moment_stats: Optional[Dict[str, np.ndarray]] = None
     timing: Dict[str, float] = field(default_factory=dict)
     local_range: Tuple[int, int] = (0, 0)
+    member_ids: Optional[np.ndarray] = None     # global member id of every row of y / status / ... (identity after a gather)
 
 
 class EnsembleSolver:
@@ -121,11 +164,14 @@ class EnsembleSolver:
     def solve(self, n_members: int, *, k_scale: Optional[np.ndarray] = None, q_scale: Optional[np.ndarray] = None,
               bc_scale: Optional[np.ndarray] = None, ic_scale: Optional[np.ndarray] = None,
               y0: Optional[Union[np.ndarray, torch.Tensor]] = None, save: Union[str, np.ndarray] = 'outlets',
-              rtd: bool = False, batch: Optional[int] = None, gather: bool = True, to_host: bool = True) -> EnsembleResult:
+              rtd: bool = False, batch: Optional[int] = None, gather: bool = True, to_host: bool = True,
+              balance: bool = True) -> EnsembleResult:
         """Solve ``n_members`` systems that share the network but differ in the given per-member scales.
 
-        All array arguments are HOST arrays indexed by the global member id (each rank reads its own block).
-        ``y0`` ([M, ndof], reference layout per member) overrides ``ic_scale * c0``."""
+        All array arguments are HOST arrays indexed by the global member id (each rank reads its own members).
+        ``y0`` ([M, ndof], reference layout per member) overrides ``ic_scale * c0``.
+        ``balance``: deal the members to ranks (and to batches inside a rank) by a stiffness estimate instead of in contiguous
+        blocks; gathered results are returned in member order either way."""
         from .device import MemberParams
         from .postprocessing.analysis import outlet_selection, rtd_on_device
         tm: Dict[str, float] = {}
@@ -136,6 +182,8 @@ class EnsembleSolver:
         rank, ws = world()
         lo, hi = shard_bounds(n_members, rank, ws)
         M_loc = hi - lo
+        perm = balanced_order(stiffness_estimate(host, n_members, k_scale, q_scale), ws) if balance else np.arange(n_members, dtype=np.int64)
+        ids = perm[lo:hi]                                   # global ids of this rank's members, stiffest first
         if isinstance(save, str):
             save_idx = None if save == 'all' else self.outlet_save_idx()
         else:
@@ -155,7 +203,7 @@ class EnsembleSolver:
             if a is None:
                 return None
             a = np.asarray(a, dtype=np.float64)
-            return torch.as_tensor(np.ascontiguousarray(a[b_lo:b_hi]), device=device)
+            return torch.as_tensor(np.ascontiguousarray(a[ids[b_lo - lo:b_hi - lo]]), device=device)
 
         y_parts, status, nfev, nacc, nrej, rtd_parts, mom_parts = [], [], [], [], [], [], []
         if self.solver != 'B200-RK45' and self.solver != 'B200-BDF':
@@ -165,11 +213,11 @@ class EnsembleSolver:
             mb = b_hi - b_lo
             mem = MemberParams(mb, dev_slice(k_scale, b_lo, b_hi), dev_slice(q_scale, b_lo, b_hi), dev_slice(bc_scale, b_lo, b_hi))
             if y0 is not None:
-                yb = y0[b_lo:b_hi]
-                if isinstance(yb, torch.Tensor):
-                    yb = yb.to(device)
+                sel = ids[b_lo - lo:b_hi - lo]
+                if isinstance(y0, torch.Tensor):
+                    yb = y0[torch.as_tensor(sel, device=y0.device)].to(device)
                 else:
-                    yb = torch.as_tensor(np.ascontiguousarray(yb), device=device)
+                    yb = torch.as_tensor(np.ascontiguousarray(np.asarray(y0)[sel]), device=device)
                 # reference layout [S, n_points] -> device layout [n_points, S]
                 yb = yb.reshape(mb, host.S, host.n_points).transpose(1, 2).contiguous().reshape(mb, -1)
             else:
@@ -213,20 +261,29 @@ class EnsembleSolver:
         rtd_loc = cat(rtd_parts, (0, host.S, T, 3)) if rtd else None
         mom_loc = cat(mom_parts, (0, host.S, 3)) if rtd else None
         stats = None
+        member_ids = ids
         if rtd:
+            torch.cuda.synchronize(device); t_r = time.perf_counter()
             stats = {k: v.cpu().numpy() for k, v in reduce_statistics(mom_loc, n_members).items()}
-        if gather and ws > 1:
-            y_loc = gather_members(y_loc, n_members)
-            st_loc = gather_members(st_loc, n_members)
-            cnt_loc = gather_members(cnt_loc, n_members)
+            tm['reduce_s'] = time.perf_counter() - t_r            # all_reduce(SUM, SUM, MIN, MAX) of the RTD moments + download
+        if gather:
+            torch.cuda.synchronize(device); t_g = time.perf_counter()
+            inv = torch.as_tensor(np.argsort(perm), device=device)        # gathered rows arrive in dealing order
+            def collect(x):
+                return gather_members(x, n_members)[inv] if (ws > 1 or balance) else x
+            y_loc, st_loc, cnt_loc = collect(y_loc), collect(st_loc), collect(cnt_loc)
             if rtd:
-                rtd_loc = gather_members(rtd_loc, n_members); mom_loc = gather_members(mom_loc, n_members)
+                rtd_loc, mom_loc = collect(rtd_loc), collect(mom_loc)
+            torch.cuda.synchronize(device)
+            tm['gather_s'] = time.perf_counter() - t_g              # all_gather of the recorded observables (NCCL on GPUs)
+            if ws > 1 or balance:
+                member_ids = np.arange(n_members, dtype=np.int64)
         tm['total_s'] = time.perf_counter() - t_start
         cnt = cnt_loc.cpu().numpy()
         to_np = (lambda x: None if x is None else x.cpu().numpy()) if to_host else (lambda x: x)
         return EnsembleResult(te, to_np(y_loc), np.arange(host.ndof, dtype=np.int32) if save_idx is None else save_idx,
                               st_loc.cpu().numpy(), cnt[:, 0], cnt[:, 1], cnt[:, 2], to_np(rtd_loc), to_np(mom_loc), stats, tm,
-                              (lo, hi))
+                              (lo, hi), member_ids)
 
 
 def solve_ensemble(model: str, model_network, config_parser, cmesh, n_members: int, **kw) -> EnsembleResult:

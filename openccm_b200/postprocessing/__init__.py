@@ -1,1 +1,1 @@
-from .analysis import network_to_rtd, rtd_on_device  # noqa: F401
+from .analysis import network_to_rtd, pulse_moments, pulse_to_rtd, rtd_on_device  # noqa: F401

@@ -92,6 +92,11 @@ CASES: Dict[str, dict] = {
         '0, 10', '0.25, linear', 'second_order')),
     'cstr_net9_tracer': dict(net=lambda: syn.random_network(9, n_io=2, seed=11), **_cfg(
         'cstr', 'a', ['a -> 0'], ['a: inlet -> 1'], '0, 40', '0.5, linear', None, rtd=True)),
+    # N = 2000: the largest size at which the reference's dense N x N operator is still cheap; pins the oracle's sparse
+    # ("reference-sparse") assembly against the unmodified reference, odd species count
+    'cstr_net2000': dict(net=lambda: syn.random_network(2000, n_io=4, seed=23), **_cfg(
+        'cstr', 'a, b, c', ['a -> 1', 'b -> 0.5', 'c -> 0'], ['a: inlet -> 1', 'b: inlet -> 2', 'c: inlet -> 0'],
+        '0, 2', '0.5, linear', 'second_order', rtol=1e-6), solvers=('RK45',)),
     'cstr_net10_pointmass': dict(net=lambda: syn.random_network(10, n_io=1, seed=13), **_cfg(
         'cstr', 'a', ['a -> 2.0 @ point(0.3, 0.4)'], [], '0, 5', '0.1, linear', None, first=1e-6)),
     # ---- C1 / C2-like: PFRs

@@ -23,7 +23,13 @@ def _worker(rank, world_size, port, n_members, q):
         local = glob[lo:hi].clone()
         full = gather_members(local, n_members)
         stats = reduce_statistics(local, n_members)
-        ok = torch.equal(full, glob) and torch.allclose(stats['mean'], glob.mean(0)) \
+        # members dealt by a stiffness estimate (boustrophedon) instead of contiguous blocks: gather + inverse permutation
+        from openccm_b200.ensemble import balanced_order
+        est = np.random.default_rng(5).uniform(0.0, 1.0, n_members)
+        perm = balanced_order(est, world_size)
+        dealt = glob[torch.as_tensor(perm[lo:hi])].clone()
+        back = gather_members(dealt, n_members)[torch.as_tensor(np.argsort(perm))]
+        ok = torch.equal(back, glob) and torch.equal(full, glob) and torch.allclose(stats['mean'], glob.mean(0)) \
             and torch.equal(stats['min'], glob.min(0).values) and torch.equal(stats['max'], glob.max(0).values) \
             and torch.allclose(stats['var'], glob.var(0, unbiased=False))
         q.put((rank, bool(ok), (lo, hi)))
@@ -54,3 +60,20 @@ def test_shard_bounds_cover_all_members():
             assert all(b[i][1] == b[i + 1][0] for i in range(ws - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_balanced_order_deals_every_rank_the_same_mix():
+    from openccm_b200.ensemble import balanced_order, shard_bounds
+    rng = np.random.default_rng(0)
+    for n, ws in ((7, 2), (4096, 8), (513, 4), (5, 8), (64, 1)):
+        est = rng.lognormal(0.0, 1.0, n)
+        perm = balanced_order(est, ws)
+        assert sorted(perm.tolist()) == list(range(n))                     # a permutation
+        sums = []
+        for r in range(ws):
+            lo, hi = shard_bounds(n, r, ws)
+            mine = est[perm[lo:hi]]
+            assert np.all(np.diff(mine) <= 0)                              # stiffest first inside a rank
+            sums.append(mine.sum())
+        if n >= 8 * ws:                                                    # every rank carries the same share of the work
+            assert max(sums) / min(sums) < 1.05, sums

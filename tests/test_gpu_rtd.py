@@ -50,3 +50,63 @@ def test_rtd_openfoam_golden_concentrations(tmp_path):
     host = export_system('pfr', mn, cp, cmesh)
     rtd = network_to_rtd((g['c_LSODA'], g['t_LSODA'], host.inlet_map, host.outlet_map), cmesh, cp, mn)
     np.testing.assert_allclose(rtd, g['rtd_LSODA'], rtol=1e-11, atol=1e-13)
+
+
+def _smooth_step(x):
+    """helper_functions.H (helper_functions.py:33-53): half-cosine ramp over [0, 0.01]."""
+    return 0.0 if x <= 0 else (1.0 if x >= 0.01 else 0.5 * (1.0 - np.cos(np.pi * x / 0.01)))
+
+
+def test_pulse_tracer_rtd_matches_step_route_and_oracle(tmp_path):
+    """North star item 4: E(t) straight from an inlet-PULSE solve on the same kernels (no differentiation of F).
+    (a) the device pulse route equals the oracle's numpy restatement of it on the oracle's own solve of the same CONFIG;
+    (b) its moments equal those of the reference's step-tracer route (F -> E = dF/dt, analysis.py:77-100) to 1e-6 once both
+        are sampled finely enough (the step route's finite differences need it: at dt = 0.01 it is 5e-6 off, the pulse route 2e-7)."""
+    from oracle import openccm_oracle as O
+    from openccm_b200.postprocessing import network_to_rtd, pulse_moments, pulse_to_rtd
+    from openccm_b200.system_solvers import solve_system
+    name, w = 'cstr_net9_tracer', 0.05
+    pulse = pulse_moments(lambda x: (_smooth_step(x) - _smooth_step(x - w)) / w, -0.01, w + 0.02)
+    assert abs(pulse[0] - 1.0) < 1e-12
+    over = dict(t_span='0, 150', t_eval='0.002, linear', rtol=1e-10, atol=1e-13)
+    bc = f'a: inlet -> (H(t) - H(t - {w}))/{w}'
+    cp, cmesh, net, mn = setup_case(name, 'B200-RK45', tmp_path, boundary_conditions=bc, **over)
+    res = solve_system('cstr', mn, cp, cmesh)
+    rtd, mom = pulse_to_rtd(res, cmesh, cp, mn, pulse)
+    # (a) oracle: scipy RK45 on the restated ddt + the numpy pulse route
+    cpo, cmesho, _, mno = setup_case(name, 'RK45', tmp_path, boundary_conditions=bc, **over)
+    rtd_o, mom_o = O.pulse_to_rtd(O.solve_system('cstr', mno, cpo, cmesho), cmesho, cpo, mno, pulse)
+    np.testing.assert_allclose(rtd[:, :, 1], rtd_o[:, :, 1], rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(rtd[:, :, 2], rtd_o[:, :, 2], rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(mom, mom_o, rtol=1e-8)
+    # (b) step-tracer route on the device, same output grid
+    cps, cmeshs, _, mns = setup_case(name, 'B200-RK45', tmp_path, **over)
+    rtd_s, mom_s = network_to_rtd(solve_system('cstr', mns, cps, cmeshs), cmeshs, cps, mns, return_moments=True)
+    np.testing.assert_allclose(mom[:, :2], mom_s[:, :2], rtol=1e-6)            # m0, mean residence time
+    # variance: the pulse route is the accurate one (it agrees with the oracle's to 1e-8 above).  The step route differentiates F
+    # numerically and weights the result with (t - mean)^2 up to 150^2: its own variance moves by 1.4e-6 between two RK45 solves
+    # at rtol 1e-10 (device vs oracle), so it can only confirm the pulse route to that noise.
+    np.testing.assert_allclose(mom[:, 2], mom_s[:, 2], rtol=5e-6)
+    # E of both routes: the pulse response is E smeared over the pulse width w, i.e. E shifted by the pulse mean to first order
+    shift = int(round(pulse[1] / 0.002))
+    assert np.max(np.abs(rtd[0, shift:, 1] - rtd_s[0, :-shift, 1])) < 2e-4 * rtd_s[0, :, 1].max()
+
+
+def test_point_mass_pulse_rtd_matches_oracle(tmp_path):
+    """The reference's own pulse precedent: a point-mass initial condition becomes a smoothed rectangular source of width 0.02
+    on the nearest model (boundary_and_initial_conditions.py:174-180).  Device solve + device pulse route vs the oracle."""
+    from oracle import openccm_oracle as O
+    from openccm_b200.postprocessing import pulse_moments, pulse_to_rtd
+    from openccm_b200.system_solvers import solve_system
+    name = 'cstr_net10_pointmass'
+    # m / (0.01 V) H(t) H(-(t - 0.02)): in time a pulse of area 0.01 (the mass enters through the source term, not through a flow)
+    pulse = pulse_moments(lambda x: _smooth_step(x) * _smooth_step(-(x - 0.02)), -0.01, 0.03)
+    over = dict(t_span='0, 5', t_eval='0.01, linear', rtol=1e-9, atol=1e-12)
+    cp, cmesh, net, mn = setup_case(name, 'B200-RK45', tmp_path, **over)
+    flow = 2.0 / pulse[0]               # injected mass (2.0, cases.py) = source_flow x pulse area: E integrates to the fraction that has left
+    rtd, mom = pulse_to_rtd(solve_system('cstr', mn, cp, cmesh), cmesh, cp, mn, pulse, source_flow=flow)
+    cpo, cmesho, _, mno = setup_case(name, 'RK45', tmp_path, **over)
+    rtd_o, mom_o = O.pulse_to_rtd(O.solve_system('cstr', mno, cpo, cmesho), cmesho, cpo, mno, pulse, source_flow=flow)
+    assert 0.0 < mom[0, 0] < 1.0
+    np.testing.assert_allclose(rtd[:, :, 1:], rtd_o[:, :, 1:], rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(mom, mom_o, rtol=1e-6)

@@ -118,3 +118,22 @@ def test_paper_equilibrium(tmp_path):
     d = np.zeros_like(C_eq)
     rx(C_eq, d)
     assert np.all(np.abs(d) < 2e-4)
+
+
+def test_sparse_cstr_assembly_is_pinned(tmp_path):
+    """The oracle's sparse CSTR path (`build_cstr(sparse=True)`: the CPU arm of bench.py and the yard-stick of the full-size GPU
+    tests, where the reference's dense N x N operator does not fit) against the UNMODIFIED reference's raw ddt at N = 2000 and
+    against the oracle's own verbatim dense path."""
+    g = load_golden('cstr_net2000')
+    cp, cmesh, net, mn = setup_case('cstr_net2000', 'RK45', tmp_path)
+    sparse = O.build_cstr(mn, cp, cmesh, sparse=True)
+    dense = O.build_cstr(mn, cp, cmesh, sparse=False)
+    import scipy.sparse
+    assert scipy.sparse.issparse(sparse.extra['A']) and isinstance(dense.extra['A'], np.ndarray)
+    np.testing.assert_allclose(sparse.extra['A'].toarray(), dense.extra['A'].T, rtol=1e-15, atol=0)      # A_sparse = Q_div_v^T
+    np.testing.assert_allclose(sparse.y0, g['c0'], rtol=1e-14, atol=1e-15)
+    for y, t, ref in zip(g['ddt_y'], g['ddt_t'], g['ddt_out']):
+        out_s, out_d = sparse.fun(float(t), y.copy()), dense.fun(float(t), y.copy())
+        scale = max(1.0, np.abs(ref).max())
+        np.testing.assert_allclose(out_s, ref, rtol=1e-12, atol=1e-13 * scale)
+        np.testing.assert_allclose(out_s, out_d, rtol=1e-13, atol=1e-13 * scale)

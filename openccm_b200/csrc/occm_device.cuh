@@ -235,11 +235,17 @@ __device__ __forceinline__ double occm_reaction_fast(const double (&coeffm)[OCCM
     return acc;
 }
 
+// operator arrays: read-only global memory (ld.global.nc), or — SHARED_SYS, the persistent small-network kernel — a copy in
+// shared memory reached through the same struct
+template <bool SHARED_SYS, class T_>
+__device__ __forceinline__ T_ occm_sys_ld(const T_* p) { if (SHARED_SYS) return *p; return __ldg(p); }
+
+template <bool SHARED_SYS = false>
 __device__ __forceinline__ double occm_pulses(const OccmSysDev& sys, const OccmTab& T, int model, int s, double t) {
     double acc = 0.0;
     if (sys.pulse_ptr) {
-        for (int k = __ldg(sys.pulse_ptr + model); k < __ldg(sys.pulse_ptr + model + 1); ++k)
-            acc += __ldg(sys.pulse_w + k) * occm_bc_value(T, __ldg(sys.pulse_fn + k), s, t);
+        for (int k = occm_sys_ld<SHARED_SYS>(sys.pulse_ptr + model); k < occm_sys_ld<SHARED_SYS>(sys.pulse_ptr + model + 1); ++k)
+            acc += occm_sys_ld<SHARED_SYS>(sys.pulse_w + k) * occm_bc_value(T, occm_sys_ld<SHARED_SYS>(sys.pulse_fn + k), s, t);
     }
     return acc;
 }
@@ -251,7 +257,7 @@ __device__ __forceinline__ double occm_pulses(const OccmSysDev& sys, const OccmT
 //   in(e)  : stage state at flat element e of this member (global memory)
 //   myrow  : staged concentrations of point p (shared memory), prevrow: those of point p - 1 (PFR upwind neighbour)
 // CSTR: cstr_system.py:194-203.   PFR: pfr_system.py:290-316.
-template <int MODEL, class In>
+template <int MODEL, class In, bool SHARED_SYS = false>
 __device__ __noinline__ double occm_point_generic(const OccmSysDev& sys, const int* tab_smem, const In& in,
                                                   const double* myrow, const double* prevrow, int p, int s, double t,
                                                   double qs, double bs, const double* ksc) {
@@ -260,32 +266,32 @@ __device__ __noinline__ double occm_point_generic(const OccmSysDev& sys, const i
     auto row = [myrow](int sp) { return myrow[sp]; };
     if (MODEL == 0) {
         double acc = 0.0;
-        const int kb = __ldg(sys.row_ptr + p), ke = __ldg(sys.row_ptr + p + 1);
+        const int kb = occm_sys_ld<SHARED_SYS>(sys.row_ptr + p), ke = occm_sys_ld<SHARED_SYS>(sys.row_ptr + p + 1);
         for (int k = kb; k < ke; ++k) {
-            const int src = __ldg(sys.row_src + k);
-            const double w = __ldg(sys.row_w + k);
+            const int src = occm_sys_ld<SHARED_SYS>(sys.row_src + k);
+            const double w = occm_sys_ld<SHARED_SYS>(sys.row_w + k);
             if (src >= 0) acc += w * (src == p ? myrow[s] : in(src * S + s));
             else          acc += w * (bs * occm_bc_value(T, -1 - src, s, t));
         }
-        return __dadd_rn(__dadd_rn(__dmul_rn(qs, acc), occm_pulses(sys, T, p, s, t)), occm_reaction_tables(T, s, row, ksc, t, p, sys));
+        return __dadd_rn(__dadd_rn(__dmul_rn(qs, acc), occm_pulses<SHARED_SYS>(sys, T, p, s, t)), occm_reaction_tables(T, s, row, ksc, t, p, sys));
     } else {
         const int P = sys.P;
         const int k = p / P;
         const int node = p - k * P;
         if (node > 0) {
-            const double conv = __dmul_rn(-(qs * __ldg(sys.a + k)), myrow[s] - prevrow[s]);
-            return __dadd_rn(__dadd_rn(conv, occm_pulses(sys, T, k, s, t)), occm_reaction_tables(T, s, row, ksc, t, p, sys));
+            const double conv = __dmul_rn(-(qs * occm_sys_ld<SHARED_SYS>(sys.a + k)), myrow[s] - prevrow[s]);
+            return __dadd_rn(__dadd_rn(conv, occm_pulses<SHARED_SYS>(sys, T, k, s, t)), occm_reaction_tables(T, s, row, ksc, t, p, sys));
         }
         double acc = 0.0;
-        const int eb = __ldg(sys.row_ptr + k), ee = __ldg(sys.row_ptr + k + 1);
+        const int eb = occm_sys_ld<SHARED_SYS>(sys.row_ptr + k), ee = occm_sys_ld<SHARED_SYS>(sys.row_ptr + k + 1);
         for (int e = eb; e < ee; ++e) {
-            const int src = __ldg(sys.row_src + e);
-            const double w = __ldg(sys.row_w + e);
+            const int src = occm_sys_ld<SHARED_SYS>(sys.row_src + e);
+            const double w = occm_sys_ld<SHARED_SYS>(sys.row_w + e);
             if (src >= 0) {
                 const int o = P * (src + 1) - 1;                 // outlet node of the upstream PFR
                 auto orow = [&in, o, S](int sp) { return in(o * S + sp); };
-                double d = -(qs * __ldg(sys.a + src)) * (in(o * S + s) - in((o - 1) * S + s));
-                d += occm_pulses(sys, T, src, s, t);
+                double d = -(qs * occm_sys_ld<SHARED_SYS>(sys.a + src)) * (in(o * S + s) - in((o - 1) * S + s));
+                d += occm_pulses<SHARED_SYS>(sys, T, src, s, t);
                 d += occm_reaction_tables(T, s, orow, ksc, t, o, sys);
                 acc += w * d;
             } else {

@@ -16,8 +16,10 @@ struct occm_system {
     size_t smem_tables;   // bytes of the staged table blob (8-byte aligned)
     int device;           // CUDA device the handle was created on (launch state is kept per device)
     int use_pipe;         // 0: no TMA-pipelined kernels (OCCM_B200_NO_PIPE=1)
+    int use_small;        // 0: no persistent one-CTA-per-member RK45 for networks that fit in shared memory (OCCM_B200_NO_SMALL=1)
     int pipe_depth;       // cap on the ring depth of the pipelined kernels (OCCM_B200_PIPE_DEPTH, 0 = as deep as shared memory allows)
     int smem_per_block, smem_per_sm;
+    int nnz, pulse_nnz;   // entries of row_src / row_w and of pulse_fn / pulse_w
 };
 
 // Launch state of ONE kernel, per device: the dynamic shared-memory opt-in that has been granted and the occupancy at the

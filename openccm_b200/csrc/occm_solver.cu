@@ -119,6 +119,7 @@ extern "C" int occm_system_create(occm_system** out, const occm_system_desc* d) 
     v.ell_src = d->ell_src; v.ell_w = d->ell_w;
     v.point_flags = d->point_flags;
     s->use_fast = getenv("OCCM_B200_NO_FAST") ? 0 : 1;
+    s->use_small = getenv("OCCM_B200_NO_SMALL") ? 0 : 1;        // tests / A-B: batched kernels also for networks that fit in shared memory
     s->use_pipe = getenv("OCCM_B200_NO_PIPE") ? 0 : 1;          // tests / A-B measurements: register-prefetching fast kernels instead
     s->pipe_depth = getenv("OCCM_B200_PIPE_DEPTH") ? atoi(getenv("OCCM_B200_PIPE_DEPTH")) : 0;
     s->force_wide = getenv("OCCM_B200_FORCE_WIDE") ? 1 : 0;      // tests: run the shared-memory term-list variant on any mechanism
@@ -130,6 +131,13 @@ extern "C" int occm_system_create(occm_system** out, const occm_system_desc* d) 
     if (v.ell_k < 0 || v.ell_k > OCCM_KREG || (d->model == OCCM_MODEL_CSTR && v.ell_k > 0 && (!d->ell_src || !d->ell_w))) { occm_set_error("bad ELL description"); free(s); return OCCM_ERR_INVALID; }
     if (ndof >= (1ll << 31)) { occm_set_error("ndof per member must fit in int32"); free(s); return OCCM_ERR_INVALID; }
     s->smem_tables = (size_t)d->tables_bytes;
+    {   // entries of the operator and of the pulse lists (the persistent small-network kernel stages them in shared memory)
+        int last = 0;
+        OCCM_CUDA_CHECK(cudaMemcpy(&last, d->row_ptr + d->n_models, sizeof(int), cudaMemcpyDeviceToHost));
+        s->nnz = last;
+        s->pulse_nnz = 0;
+        if (d->pulse_ptr) { OCCM_CUDA_CHECK(cudaMemcpy(&last, d->pulse_ptr + d->n_models, sizeof(int), cudaMemcpyDeviceToHost)); s->pulse_nnz = last; }
+    }
     int dev = 0;
     OCCM_CUDA_CHECK(cudaGetDevice(&dev));
     s->device = dev;
@@ -640,6 +648,8 @@ __global__ void occm_rk45_write_initial(const double* __restrict__ y0, int M, lo
     }
 }
 
+#include "occm_small.cuh"
+
 #endif  // !OCCM_STAGE_TU
 
 // ------------------------------------------------------------------------------------------------ launch helpers
@@ -1039,9 +1049,54 @@ struct OccmSlowCall {
     }
 };
 
+// Networks that fit in shared memory: one persistent CTA per member (occm_small.cuh).  Returns 1 when the problem does not
+// qualify (all-steps mode, too many DOF, tables too large), 0 after running, < 0 on error.
+static int occm_rk45_run_small(occm_rk45* rk, int64_t max_launch_steps, int32_t* n_running, cudaStream_t st) {
+    static OccmLaunchCache cache[2];
+    const occm_system* sys = rk->sys;
+    const long long ndof = sys->dev.ndof;
+    if (!sys->use_small || !rk->prob.t_eval || ndof > OCCM_SMALL_MAX_NDOF || rk->M > 65535) return 1;
+    const int nm = sys->dev.n_models, nnz = sys->nnz, pnnz = sys->pulse_nnz;
+    const size_t smem = (size_t)sys->dev.tables_bytes + sizeof(double) * (10 * (size_t)ndof + nnz + nm + pnnz) +
+                        sizeof(int) * (2 * (size_t)(nm + 1) + nnz + pnnz) + 16;
+    if (smem > (size_t)sys->smem_per_block) return 1;
+    int block = (int)((ndof + 31) / 32 * 32);
+    block = block < 64 ? 64 : block > 512 ? 512 : block;          // (1024 threads = 64 registers: the generic RHS spilled)
+    const bool pfr = sys->dev.model == OCCM_MODEL_PFR;
+    const void* kern = pfr ? (const void*)occm_rk45_small<1> : (const void*)occm_rk45_small<0>;
+    if (int rc = occm_kernel_prepare(&cache[pfr ? 1 : 0], kern, sys->device, block, smem, nullptr)) return rc;
+    const OccmMemDev md = occm_mem_dev(rk->has_mem ? &rk->mem : nullptr, 1);
+    const int n_save = rk->prob.save_idx ? rk->prob.n_save : (int)ndof;
+    long long done = 0;
+    int running = rk->M;
+    while (true) {
+        long long todo = 1ll << 18;                          // attempts per launch (a launch of a few seconds at most)
+        if (max_launch_steps > 0 && done + todo > max_launch_steps) todo = max_launch_steps - done;
+        if (pfr) occm_rk45_small<1><<<rk->M, block, smem, st>>>(sys->dev, md, rk->d, rk->prob.t_eval, rk->prob.n_t_eval, rk->prob.save_idx, n_save,
+                                                                rk->prob.out, rk->prob.out_t, todo, nnz, pnnz);
+        else     occm_rk45_small<0><<<rk->M, block, smem, st>>>(sys->dev, md, rk->d, rk->prob.t_eval, rk->prob.n_t_eval, rk->prob.save_idx, n_save,
+                                                                rk->prob.out, rk->prob.out_t, todo, nnz, pnnz);
+        OCCM_LAUNCH_CHECK("occm_rk45_small");
+        done += todo;
+        occm_count_running<<<1, 256, 0, st>>>(rk->d.status, rk->M, rk->d.n_running);
+        OCCM_LAUNCH_CHECK("occm_count_running");
+        OCCM_CUDA_CHECK(cudaMemcpyAsync(rk->h_running, rk->d.n_running, sizeof(int), cudaMemcpyDeviceToHost, st));
+        OCCM_CUDA_CHECK(cudaStreamSynchronize(st));
+        running = *rk->h_running;
+        if (running == 0 || (max_launch_steps > 0 && done >= max_launch_steps)) break;
+    }
+    rk->launched_steps += done;
+    if (n_running) *n_running = running;
+    return OCCM_OK;
+}
+
 extern "C" int occm_rk45_run(occm_rk45* rk, int64_t max_launch_steps, int32_t* n_running, void* stream) {
     if (!rk) { occm_set_error("occm_rk45_run: null handle"); return OCCM_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        const int rc = occm_rk45_run_small(rk, max_launch_steps, n_running, st);
+        if (rc <= 0) return rc;
+    }
     long long launched = 0;
     int batch = 4;
     int running = rk->M;

@@ -250,6 +250,51 @@ def openfoam_cstr_fixture() -> None:
     shutil.rmtree(tmp, ignore_errors=True)
 
 
+def cstr_builder_golden() -> None:
+    """f-2: inputs and outputs of the UNMODIFIED `create_cstr_network` (compartment_models/cstr.py:138-251) on the OpenFOAM 2-D
+    example compartmentalised with model = CSTR.  Inputs are stored flattened (no reference classes needed to load them)."""
+    import openccm
+    from openccm.compartment_models.cstr import create_cstr_network
+    tmp = tempfile.mkdtemp(prefix='golden_cstr_builder_')
+    dst = os.path.join(tmp, 'case')
+    shutil.copytree('/root/reference/examples/OpenFOAM/pipe_with_recirc', dst)
+    old = os.getcwd(); os.chdir(dst)
+    try:
+        cp = ConfigParser('CONFIG')
+        cp['COMPARTMENT MODELLING']['model'] = 'cstr'
+        cp['SIMULATION']['points_per_pfr'] = '1'
+        cp['SIMULATION']['run'] = 'False'
+        cp['POST-PROCESSING']['calculate_rtd'] = 'False'
+        openccm.run(cp)
+        load = lambda n: pickle.load(open(f'cache/{n}.pickle', 'rb'))
+        cn, comp, cmesh = load('cstr_compartment_network'), load('cstr_compartments_post'), load('cmesh')
+        fu = np.load('cache/flows_and_upwind.npy', allow_pickle=True)
+        connections, volumes, flows, c2m, m2e = create_cstr_network(comp, cn, cmesh, fu, None, cp)
+    finally:
+        os.chdir(old)
+    g_comp, g_nb, g_len, facets, elems = [], [], [], [], []
+    for c, nbs in cn.items():
+        for nb, fd in nbs.items():
+            g_comp.append(c); g_nb.append(nb); g_len.append(len(fd)); facets.extend(fd.keys()); elems.extend(fd.values())
+    facets = np.asarray(facets, dtype=np.int64)
+    comp_ptr = np.concatenate([[0], np.cumsum([len(comp[c]) for c in sorted(comp)])])
+    comp_el = np.concatenate([np.fromiter(comp[c], dtype=np.int64, count=len(comp[c])) for c in sorted(comp)])
+    from openccm_b200.network import NetworkArrays
+    na = NetworkArrays.from_model_network((connections, volumes, flows, c2m, m2e))
+    np.savez_compressed(os.path.join(HERE, 'openfoam_2d_cstr_builder.npz'),
+                        g_comp=np.asarray(g_comp), g_nb=np.asarray(g_nb), g_len=np.asarray(g_len), facets=facets, elems=np.asarray(elems, dtype=np.int64),
+                        facet_el=np.asarray([(tuple(cmesh.facet_elements[f]) + (-1, -1))[:2] for f in facets.tolist()], dtype=np.int64),   # boundary facets: one element
+                        facet_flow=fu[facets, 0].astype(np.float64), facet_flag=fu[facets, 1].astype(np.int64),
+                        comp_ptr=comp_ptr, comp_el=comp_el, element_sizes=np.asarray(cmesh.element_sizes, dtype=np.float64),
+                        domain_inlets=np.asarray(cmesh.grouped_bcs.domain_inlets), domain_outlets=np.asarray(cmesh.grouped_bcs.domain_outlets),
+                        flow_threshold=cp.get_item(['COMPARTMENT MODELLING', 'flow_threshold'], float),
+                        atol_opt=cp.get_item(['COMPARTMENT MODELLING', 'atol_opt'], float),
+                        volumes=volumes, flows=flows, in_model=na.in_model, in_conn=na.in_conn, in_other=na.in_other,
+                        out_model=na.out_model, out_conn=na.out_conn, out_other=na.out_other)
+    print(f'[golden] openfoam_2d_cstr_builder: {len(g_comp)} compartment pairs, {len(facets)} facets -> {len(volumes)} CSTRs, {len(flows)} connections')
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
 def openfoam_fixture() -> None:
     """Run the reference's own pipeline on examples/OpenFOAM/pipe_with_recirc (a writable copy) and freeze the
     444-PFR model network + element geometry as a fixture (inputs only)."""
@@ -342,6 +387,11 @@ if __name__ == '__main__':
     if '--openfoam-cstr-fixture' in argv:
         argv.remove('--openfoam-cstr-fixture')
         openfoam_cstr_fixture()
+    if '--cstr-builder' in argv:
+        argv.remove('--cstr-builder')
+        cstr_builder_golden()
+        if not argv:
+            sys.exit(0)
     if '--flows' in argv:
         argv.remove('--flows')
         flows_golden()

@@ -86,7 +86,7 @@ occm_rk45_small(const __grid_constant__ OccmSysDev sys_g, const __grid_constant_
     int i1 = 0, i7 = 6;
     const long long base = (long long)m * ndof;
     const double qs = mem.q_scale ? mem.q_scale[m] : 1.0, bs = mem.bc_scale ? mem.bc_scale[m] : 1.0;
-    const double* ksc = mem.k_scale ? mem.k_scale + (long long)m * sys.n_rxn : nullptr;
+    const double* ksc = mem.k_scale ? mem.k_scale + (long long)m * sys_g.n_rxn : nullptr;     // (sys_sh is not complete before the barrier below)
     {
         const int par = rk.parity[m];
         for (int e = tid; e < ndof; e += nthr) { y[e] = rk.Y[par][base + e]; Kb[e] = rk.KF[par][base + e]; }

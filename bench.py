@@ -459,7 +459,7 @@ def main():
         # global host arrays in; the solver takes this rank's contiguous member block (no collective on the data path)
         # (the NCCL all_gather of the recorded outlet concentrations + RTD arrays and the all_reduce of the RTD moment statistics
         #  — the only collectives of the path — are inside the timed region)
-        r = solver_e2e.solve(M_glob, k_scale=ks_all, q_scale=qs_all, ic_scale=ics_all, save=save_idx, gather=True, rtd=True)
+        r = solver_e2e.solve(M_glob, k_scale=ks_all, q_scale=qs_all, ic_scale=ics_all, save=save_idx, gather='root', rtd=True)
         return r
     for _ in range(min(args.warmup, 1)):
         e2e_step()
@@ -469,18 +469,19 @@ def main():
     gather_ms, reduce_ms = [], []
     for _ in range(args.steps):
         r = e2e_step()
-        nfev_e2e += int(r.nfev.sum())            # gathered: every rank holds the counters of ALL members
+        nfev_e2e += int(r.nfev.sum())            # rank 0: the counters of ALL members (gathered); other ranks: their own
         gather_ms.append(1e3 * r.timing.get('gather_s', 0.0)); reduce_ms.append(1e3 * r.timing.get('reduce_s', 0.0))
     barrier()
     e2e_s = time.perf_counter() - t0
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device=device)
     if world_size > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = float(nfev_e2e) * N * S / float(t_e.item())
+    e2e_value = float(nfev_e2e) * N * S / float(t_e.item())      # used on rank 0 only, where nfev_e2e covers every member
     blob_bytes = host.tables.pack().nbytes
     h2d = (host.row_ptr.nbytes + host.row_src.nbytes + host.row_w.nbytes) * 2 + blob_bytes + host.c0.nbytes + \
         ks.nbytes + qs.nbytes + ics.nbytes + save_idx.nbytes + te.nbytes
-    # every rank downloads the gathered members: recorded outlets [M, T, n_save], RTD [M, S, T, 3], moments, counters
+    # rank 0 downloads the gathered members: recorded outlets [M, T, n_save], RTD [M, S, T, 3], moments, counters (the other ranks
+    # their own 1 / N of it)
     d2h = M_glob * (len(te) * len(save_idx) * 8 + S * len(te) * 3 * 8 + S * 3 * 8 + 4 + 3 * 8)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -551,7 +552,7 @@ def main():
         bpr = -(-(M_s // world_size) // solver_s.members_per_batch(len(save_idx), len(te)))
         barrier()
         t0 = time.perf_counter()
-        r_s = solver_s.solve(M_s, k_scale=ks_s, q_scale=qs_s, ic_scale=ics_s, save=save_idx, gather=True, rtd=True)
+        r_s = solver_s.solve(M_s, k_scale=ks_s, q_scale=qs_s, ic_scale=ics_s, save=save_idx, gather='root', rtd=True)
         barrier()
         t_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
         if world_size > 1:
@@ -593,7 +594,7 @@ def main():
                 "ode_solves_per_s": solves_per_s, "rhs_evals_total": evals, "step_ms": step_ms,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "solves_per_s": M_glob * args.steps / float(t_e.item()),
-                        "collectives": "all_gather(outlets, RTD, counters) + all_reduce(RTD moment statistics) inside the timed region",
+                        "collectives": "gather to rank 0 (outlets, RTD, counters) + all_reduce(RTD moment statistics) inside the timed region",
                         "gather_ms": float(np.mean(gather_ms)), "reduce_ms": float(np.mean(reduce_ms))},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "plain_rhs": plain, "cpu_baseline": cpu,
                 "strong": strong, "bdf": bdf}

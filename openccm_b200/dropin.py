@@ -12,7 +12,7 @@ Drop-in installation behind OpenCCM's own entry point.
 
 Every other solver name is forwarded untouched to the reference's scipy path (this package itself never integrates on
 the CPU).  With ``route_scipy_names=True`` the scipy method names are mapped too: RK45/RK23/DOP853 -> B200-RK45,
-LSODA/BDF/Radau -> B200-BDF.
+LSODA -> B200-LSODA (RK45 probe, then BDF if the step is stability limited), BDF/Radau -> B200-BDF.
 """
 from __future__ import annotations
 
@@ -21,7 +21,7 @@ from typing import Callable, Optional
 from .system_solvers import is_device_solver, solve_system as _device_solve_system
 
 _SCIPY_TO_DEVICE = {'RK45': 'B200-RK45', 'RK23': 'B200-RK45', 'DOP853': 'B200-RK45',
-                    'LSODA': 'B200-BDF', 'BDF': 'B200-BDF', 'RADAU': 'B200-BDF'}
+                    'LSODA': 'B200-LSODA', 'BDF': 'B200-BDF', 'RADAU': 'B200-BDF'}
 _original: Optional[Callable] = None
 _original_rtd: Optional[Callable] = None
 # every name `network_to_rtd` is bound to inside the reference (run.py:32-33 imports it from the package, which imports it

@@ -75,8 +75,9 @@ def balanced_order(estimate: np.ndarray, world_size: int) -> np.ndarray:
     return np.concatenate([np.asarray(b, dtype=np.int64) for b in buckets]) if n else np.zeros(0, dtype=np.int64)
 
 
-def gather_members(local: torch.Tensor, n_members: int) -> torch.Tensor:
-    """All-gather per-member rows (axis 0) from every rank, in member order. Works on CUDA (NCCL) and CPU (gloo)."""
+def gather_members(local: torch.Tensor, n_members: int, root: Optional[int] = None) -> Optional[torch.Tensor]:
+    """Gather per-member rows (axis 0) from every rank, in rank order. ``root=None``: all_gather, every rank gets all rows;
+    ``root=r``: gather to rank r only (the others return None).  Works on CUDA (NCCL) and CPU (gloo)."""
     rank, ws = world()
     if ws == 1:
         return local
@@ -84,9 +85,27 @@ def gather_members(local: torch.Tensor, n_members: int) -> torch.Tensor:
     n_max = max(hi - lo for lo, hi in per_rank)
     pad = torch.zeros((n_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[:local.shape[0]] = local
-    parts = [torch.empty_like(pad) for _ in range(ws)]
-    dist.all_gather(parts, pad)
+    if root is None:
+        parts = [torch.empty_like(pad) for _ in range(ws)]
+        dist.all_gather(parts, pad)
+    else:
+        parts = [torch.empty_like(pad) for _ in range(ws)] if rank == root else None
+        dist.gather(pad, parts, dst=root)
+        if rank != root:
+            return None
     return torch.cat([parts[r][:hi - lo] for r, (lo, hi) in enumerate(per_rank)], dim=0)
+
+
+def to_host_pinned(x: Optional[torch.Tensor]) -> Optional[np.ndarray]:
+    """Device -> host through a pinned staging buffer (a pageable .cpu() of the gathered outputs ran at a quarter of the PCIe rate)."""
+    if x is None:
+        return None
+    if not x.is_cuda or x.numel() == 0:
+        return x.cpu().numpy()
+    buf = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+    buf.copy_(x, non_blocking=True)
+    torch.cuda.current_stream(x.device).synchronize()
+    return buf.numpy()
 
 
 def reduce_statistics(local: torch.Tensor, n_members: int) -> Dict[str, torch.Tensor]:
@@ -164,12 +183,14 @@ class EnsembleSolver:
     def solve(self, n_members: int, *, k_scale: Optional[np.ndarray] = None, q_scale: Optional[np.ndarray] = None,
               bc_scale: Optional[np.ndarray] = None, ic_scale: Optional[np.ndarray] = None,
               y0: Optional[Union[np.ndarray, torch.Tensor]] = None, save: Union[str, np.ndarray] = 'outlets',
-              rtd: bool = False, batch: Optional[int] = None, gather: bool = True, to_host: bool = True,
+              rtd: bool = False, batch: Optional[int] = None, gather: Union[bool, str] = True, to_host: bool = True,
               balance: bool = True) -> EnsembleResult:
         """Solve ``n_members`` systems that share the network but differ in the given per-member scales.
 
         All array arguments are HOST arrays indexed by the global member id (each rank reads its own members).
         ``y0`` ([M, ndof], reference layout per member) overrides ``ic_scale * c0``.
+        ``gather``: True / 'all' = every rank receives all members (all_gather); 'root' = rank 0 only (the other ranks keep their
+        own members: at 8 GPUs every rank downloading all 4096 members cost a third of the end-to-end time); False = no collective.
         ``balance``: deal the members to ranks (and to batches inside a rank) by a stiffness estimate instead of in contiguous
         blocks; gathered results are returned in member order either way."""
         from .device import MemberParams
@@ -266,21 +287,32 @@ class EnsembleSolver:
             torch.cuda.synchronize(device); t_r = time.perf_counter()
             stats = {k: v.cpu().numpy() for k, v in reduce_statistics(mom_loc, n_members).items()}
             tm['reduce_s'] = time.perf_counter() - t_r            # all_reduce(SUM, SUM, MIN, MAX) of the RTD moments + download
-        if gather:
+        root = 0 if gather == 'root' else None
+        if gather and (root is None or ws > 1):
             torch.cuda.synchronize(device); t_g = time.perf_counter()
             inv = torch.as_tensor(np.argsort(perm), device=device)        # gathered rows arrive in dealing order
+            have_all = root is None or rank == root
             def collect(x):
-                return gather_members(x, n_members)[inv] if (ws > 1 or balance) else x
+                if not (ws > 1 or balance):
+                    return x
+                g = gather_members(x, n_members, root)
+                return g[inv] if g is not None else x               # non-root ranks of a rooted gather keep their own rows
             y_loc, st_loc, cnt_loc = collect(y_loc), collect(st_loc), collect(cnt_loc)
             if rtd:
                 rtd_loc, mom_loc = collect(rtd_loc), collect(mom_loc)
             torch.cuda.synchronize(device)
-            tm['gather_s'] = time.perf_counter() - t_g              # all_gather of the recorded observables (NCCL on GPUs)
-            if ws > 1 or balance:
+            tm['gather_s'] = time.perf_counter() - t_g              # (all_)gather of the recorded observables (NCCL on GPUs)
+            if have_all and (ws > 1 or balance):
                 member_ids = np.arange(n_members, dtype=np.int64)
+        elif gather and balance:                                    # rooted gather on one rank: only the permutation is undone
+            inv = torch.as_tensor(np.argsort(perm), device=device)
+            y_loc, st_loc, cnt_loc = y_loc[inv], st_loc[inv], cnt_loc[inv]
+            if rtd:
+                rtd_loc, mom_loc = rtd_loc[inv], mom_loc[inv]
+            member_ids = np.arange(n_members, dtype=np.int64)
         tm['total_s'] = time.perf_counter() - t_start
         cnt = cnt_loc.cpu().numpy()
-        to_np = (lambda x: None if x is None else x.cpu().numpy()) if to_host else (lambda x: x)
+        to_np = to_host_pinned if to_host else (lambda x: x)
         return EnsembleResult(te, to_np(y_loc), np.arange(host.ndof, dtype=np.int32) if save_idx is None else save_idx,
                               st_loc.cpu().numpy(), cnt[:, 0], cnt[:, 1], cnt[:, 2], to_np(rtd_loc), to_np(mom_loc), stats, tm,
                               (lo, hi), member_ids)

@@ -6,6 +6,7 @@ Device replacement for ``openccm.system_solvers`` (/root/reference/openccm/syste
 liboccm_b200.so.  Selection is by ``[SIMULATION] solver``:
 
     B200-RK45   adaptive Dormand-Prince, step-for-step mirror of scipy's RK45
+    B200-LSODA  automatic choice: an RK45 probe, then BDF from the probe's state if the step size is stability limited
     B200-BDF    variable-order BDF with Newton + preconditioned GMRES (stiff networks); integrates at 0.01 x the
                 user's (rtol, atol) so that it meets the 1e-10 + 1e-6 |c| band wherever the reference's LSODA does
                 (openccm_b200.bdf.device_tolerances)
@@ -22,7 +23,16 @@ import numpy as np
 from .export import HostSystem, export_system
 from .helper_functions import generate_t_eval
 
-DEVICE_SOLVERS = ('B200-RK45', 'B200-BDF')
+DEVICE_SOLVERS = ('B200-RK45', 'B200-BDF', 'B200-LSODA')
+
+# B200-LSODA: automatic method selection in the spirit of LSODA (the reference's default solver, expanded_config_parser.py:55;
+# scipy/integrate/_ivp/lsoda.py:120-197 wraps ODEPACK, which starts non-stiff and switches when the problem turns stiff).
+# Here: a probe of explicit RK45 steps; when it has not finished and the step size it settled at projects to more than
+# LSODA_SWITCH_STEPS further steps — on these networks that means the step is limited by the fastest compartment
+# (h <~ 3.3 tau_min), not by accuracy — the integration continues from the probe's state with the device BDF.
+# One-way (non-stiff -> stiff), decided once.
+LSODA_PROBE_STEPS = 400
+LSODA_SWITCH_STEPS = 4000
 
 
 def is_device_solver(name: str) -> bool:
@@ -51,8 +61,11 @@ def solve_system(model: str, model_network, config_parser, cmesh, *, return_info
     dev = DeviceSystem(host)
     y0 = torch.as_tensor(host.to_device_layout(host.c0.reshape(-1)), device=dev.dev).reshape(1, -1)
 
+    switched = None
     if solver == 'B200-RK45':
         res = dev.rk45(y0, t_span, rtol=rtol, atol=atol, first_step=first_timestep, t_eval=t_eval, max_steps=max_steps)
+    elif solver == 'B200-LSODA' and t_eval is not None:
+        res, switched = _solve_auto(dev, y0, t_span, rtol, atol, first_timestep, t_eval)
     else:
         from ..bdf import device_tolerances, solve_bdf
         rtol_d, atol_d = device_tolerances(rtol, atol)         # tolerance-mapping policy of B200-BDF (see its docstring)
@@ -76,8 +89,39 @@ def solve_system(model: str, model_network, config_parser, cmesh, *, return_info
     out = (c, ts, dict(host.inlet_map), dict(host.outlet_map))
     if return_info:
         return out + (dict(status=status, message=message, nfev=int(res.nfev[0]), n_accepted=int(res.n_accepted[0]),
-                           n_rejected=int(res.n_rejected[0])),)
+                           n_rejected=int(res.n_rejected[0]), switched_at=switched),)
     return out
+
+
+def _solve_auto(dev, y0, t_span, rtol, atol, first_step, t_eval):
+    """B200-LSODA: RK45 probe, then (if the projected number of steps says the step is stability limited) BDF from the probe's
+    state.  Returns (result with the rows of both phases, switch time or None)."""
+    import torch
+    from ..bdf import device_tolerances, solve_bdf
+    from ..device import Rk45Result
+    te = np.asarray(t_eval, dtype=np.float64)
+    with dev.open_rk45(y0, t_span, rtol=rtol, atol=atol, first_step=first_step, t_eval=te, save_idx=None, members=None,
+                       max_steps=LSODA_PROBE_STEPS, all_capacity=0) as run:
+        run.run()
+        run.stats()
+        probe = Rk45Result(te, run.out, run.status.copy(), run.n_acc.copy(), run.n_rej.copy(), run.nfev.copy(), None, run.n_rows.copy())
+        if int(run.status[0]) != -3:                           # finished (or failed) inside the probe: a plain RK45 solve
+            return probe, None
+        t_now, rows, n_acc = float(run.t_now[0]), int(run.n_rows[0]), int(run.n_acc[0])
+        if rows >= len(te):                                    # every requested output is already written
+            probe.status[:] = 1
+            return probe, None
+        y_now = run.final_state()
+    h_avg = (t_now - float(t_span[0])) / max(n_acc, 1)
+    if (float(t_span[1]) - t_now) / h_avg <= LSODA_SWITCH_STEPS:            # accuracy limited: stay explicit
+        return dev.rk45(y0, t_span, rtol=rtol, atol=atol, first_step=first_step, t_eval=te), None
+    rtol_d, atol_d = device_tolerances(rtol, atol)
+    rest = solve_bdf(dev, y_now, (t_now, float(t_span[1])), rtol=rtol_d, atol=atol_d, first_step=min(h_avg, float(t_span[1]) - t_now),
+                     t_eval=te[rows:])
+    y = torch.cat([probe.y[:, :rows], rest.y], dim=1)
+    n_rows = np.array([rows + (len(te) - rows if int(rest.status[0]) == 1 else int(rest.n_rows[0]))], dtype=np.int32)
+    return Rk45Result(te, y, rest.status, probe.n_accepted + rest.n_accepted, probe.n_rejected + rest.n_rejected,
+                      probe.nfev + rest.nfev, None, n_rows), t_now
 
 
 def _dae_residual_warning(c: np.ndarray, host: HostSystem, atol: float) -> None:

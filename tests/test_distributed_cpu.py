@@ -29,7 +29,10 @@ def _worker(rank, world_size, port, n_members, q):
         perm = balanced_order(est, world_size)
         dealt = glob[torch.as_tensor(perm[lo:hi])].clone()
         back = gather_members(dealt, n_members)[torch.as_tensor(np.argsort(perm))]
-        ok = torch.equal(back, glob) and torch.equal(full, glob) and torch.allclose(stats['mean'], glob.mean(0)) \
+        # rooted gather: rank 0 receives every member, the others nothing
+        rooted = gather_members(local, n_members, root=0)
+        ok_root = torch.equal(rooted, glob) if rank == 0 else rooted is None
+        ok = ok_root and torch.equal(back, glob) and torch.equal(full, glob) and torch.allclose(stats['mean'], glob.mean(0)) \
             and torch.equal(stats['min'], glob.min(0).values) and torch.equal(stats['max'], glob.max(0).values) \
             and torch.allclose(stats['var'], glob.var(0, unbiased=False))
         q.put((rank, bool(ok), (lo, hi)))

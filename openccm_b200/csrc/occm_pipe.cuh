@@ -25,15 +25,25 @@
 #ifndef OCCM_PIPE_CTAS_LIGHT
 #define OCCM_PIPE_CTAS_LIGHT 2                              // stages with few streams (plain RHS, J*v, 2, 7): 3 CTAs (80 registers) spilled and measured slower
 #endif
-#define OCCM_PIPE_STREAM_BYTES 4096u                        // a chunk's rows of one vector: 8 * (32 / H) points * S * 8 B <= 4096
+#define OCCM_PIPE_SUB_BYTES 4096u                           // a sub-chunk's rows of one vector: 7 * (32 / H) points * S * 8 B <= 4096
 #define OCCM_PIPE_MAX_DEPTH 8
+#ifndef OCCM_PIPE_E_LIGHT
+#define OCCM_PIPE_E_LIGHT 1                                 // sub-chunks per trip in the light stages (see OccmPipeE)
+#endif
 
 // input streams of a stage: 0 = the stage state (stages 1 / 2: its two summands), then the epilogue operands
 template <int STAGE> struct OccmPipeStreams { static constexpr int value = STAGE == 0 ? 1 : STAGE == 1 ? 2 : STAGE == 2 ? 2 : STAGE == 3 ? 4 : STAGE == 4 ? 5 : STAGE == 7 ? 3 : 6; };
 template <int STAGE> struct OccmPipeLight { static constexpr bool value = STAGE <= 2 || STAGE == 7; };
+// Sub-chunks per trip: a consumer thread works on E points of a trip (one per sub-chunk), issues the loads of all of them —
+// among them the out-of-chunk row gathers, whose latency is the top stall of the light stages — and only then computes.
+// Measured on C4 (512 members, profiles/r02_notes.md): E = 2 made the plain RHS 13 % and stage 2 34 % SLOWER (stage 7 4 % faster),
+// E = 3 worse still — so E = 1 everywhere; the code path stays for the experiment (-DOCCM_PIPE_E_LIGHT=2).
+template <int STAGE> struct OccmPipeE { static constexpr int value = OccmPipeLight<STAGE>::value ? OCCM_PIPE_E_LIGHT : 1; };
+template <int STAGE> struct OccmPipeStreamBytes { static constexpr unsigned value = OccmPipeE<STAGE>::value * OCCM_PIPE_SUB_BYTES; };
 
 struct OccmPipeGeom {
-    int pc;            // points per chunk
+    int pc;            // points per chunk (E sub-chunks of psub points)
+    int psub;          // points per sub-chunk = consumer warps * (32 / H)
     int cpm;           // chunks per member
     int depth;         // ring slots
     int slot_bytes;    // bytes of one slot: streams, then the ELL columns
@@ -99,9 +109,10 @@ __device__ __forceinline__ double2 occm_lds2(unsigned sa) {
 // roundings as occm_fast_in)
 template <int STAGE, int V>
 __device__ __forceinline__ double2 occm_pipe_state(unsigned slot_sa, unsigned off, double hb) {
+    constexpr unsigned SB = OccmPipeStreamBytes<STAGE>::value;
     const double2 a = occm_lds2<V>(slot_sa + off);
-    if (STAGE == 2) { const double2 b = occm_lds2<V>(slot_sa + OCCM_PIPE_STREAM_BYTES + off); return make_double2(a.x + (dp::A21 * b.x) * hb, a.y + (dp::A21 * b.y) * hb); }
-    if (STAGE == 1) { const double2 b = occm_lds2<V>(slot_sa + OCCM_PIPE_STREAM_BYTES + off); return make_double2(a.x + b.x * hb, a.y + b.y * hb); }
+    if (STAGE == 2) { const double2 b = occm_lds2<V>(slot_sa + SB + off); return make_double2(a.x + (dp::A21 * b.x) * hb, a.y + (dp::A21 * b.y) * hb); }
+    if (STAGE == 1) { const double2 b = occm_lds2<V>(slot_sa + SB + off); return make_double2(a.x + b.x * hb, a.y + b.y * hb); }
     return a;
 }
 
@@ -110,14 +121,15 @@ __device__ __forceinline__ OccmOps2 occm_pipe_read_ops(unsigned sa) {      // sa
     OccmOps2 o;
     const double2 z = make_double2(0.0, 0.0);
     o.ye = o.k1 = o.ka = o.kb = o.kc = o.kd = z;
+    constexpr unsigned SB = OccmPipeStreamBytes<STAGE>::value;
     if (STAGE <= 1) return o;
-    if (STAGE == 2) { o.ye = occm_lds2_at<0u, V>(sa); o.k1 = occm_lds2_at<OCCM_PIPE_STREAM_BYTES, V>(sa); return o; }
-    o.ye = occm_lds2_at<OCCM_PIPE_STREAM_BYTES, V>(sa);
-    if (STAGE == 7) { o.ka = occm_lds2_at<2 * OCCM_PIPE_STREAM_BYTES, V>(sa); return o; }
-    o.k1 = occm_lds2_at<2 * OCCM_PIPE_STREAM_BYTES, V>(sa);
-    o.ka = occm_lds2_at<3 * OCCM_PIPE_STREAM_BYTES, V>(sa);
-    if (STAGE >= 4) o.kb = occm_lds2_at<4 * OCCM_PIPE_STREAM_BYTES, V>(sa);
-    if (STAGE >= 5) o.kc = occm_lds2_at<5 * OCCM_PIPE_STREAM_BYTES, V>(sa);
+    if (STAGE == 2) { o.ye = occm_lds2_at<0u, V>(sa); o.k1 = occm_lds2_at<SB, V>(sa); return o; }
+    o.ye = occm_lds2_at<SB, V>(sa);
+    if (STAGE == 7) { o.ka = occm_lds2_at<2 * SB, V>(sa); return o; }
+    o.k1 = occm_lds2_at<2 * SB, V>(sa);
+    o.ka = occm_lds2_at<3 * SB, V>(sa);
+    if (STAGE >= 4) o.kb = occm_lds2_at<4 * SB, V>(sa);
+    if (STAGE >= 5) o.kc = occm_lds2_at<5 * SB, V>(sa);
     return o;
 }
 
@@ -129,12 +141,14 @@ occm_pipe_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
     int* tab_s = reinterpret_cast<int*>(smem_p);
     occm_load_tables(sys.tables, sys.tables_bytes, tab_s);               // ends with __syncthreads (all 9 warps)
     constexpr int NS = OccmPipeStreams<STAGE>::value;
+    constexpr int E = OccmPipeE<STAGE>::value;
+    constexpr unsigned SB = OccmPipeStreamBytes<STAGE>::value;
     const int S = sys.S, H = S / V, RS = S + 2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ppw = 32 / H;                                                // points per warp and trip
     const int n_points = (int)sys.n_points;
     double* rxc_s = reinterpret_cast<double*>(smem_p + g.coef_off);      // unscaled coefficients [S][OCCM_NT]  (WIDE: [S][nt_u])
-    double* tile = reinterpret_cast<double*>(smem_p + g.tile_off);       // [OCCM_PIPE_WARPS][ppw][RS]
+    double* tile = reinterpret_cast<double*>(smem_p + g.tile_off);       // [E][OCCM_PIPE_WARPS][ppw][RS]
     const unsigned smem_sa = (unsigned)__cvta_generic_to_shared(smem_p);
     const unsigned bar_sa = smem_sa + (unsigned)g.bar_off;                // full[depth], empty[depth]
     const unsigned ring_sa = smem_sa + (unsigned)g.ring_off;
@@ -164,7 +178,7 @@ occm_pipe_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
             }
         }
     }
-    for (int r = tid; r < OCCM_PIPE_WARPS * ppw; r += OCCM_PIPE_THREADS) { tile[r * RS + S] = 1.0; tile[r * RS + S + 1] = 1.0; }
+    for (int r = tid; r < E * OCCM_PIPE_WARPS * ppw; r += OCCM_PIPE_THREADS) { tile[r * RS + S] = 1.0; tile[r * RS + S + 1] = 1.0; }
     __syncthreads();
 
     // ---- cursor over this CTA's (member, chunk) trips, skipping members that are not running (identical in every warp)
@@ -202,10 +216,10 @@ occm_pipe_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
             const long long e0 = (long long)m * sys.ndof + (long long)p0 * S;
 #pragma unroll
             for (int j = 0; j < NS; ++j)
-                occm_bulk_g2s(dst + j * OCCM_PIPE_STREAM_BYTES, occm_pipe_src<STAGE>(mem, rk, y_in, par, j) + e0, vbytes, full);
+                occm_bulk_g2s(dst + j * SB, occm_pipe_src<STAGE>(mem, rk, y_in, par, j) + e0, vbytes, full);
 #pragma unroll
             for (int k = 0; k < K; ++k)
-                occm_bulk_g2s(dst + NS * OCCM_PIPE_STREAM_BYTES + (unsigned)(k * g.ell_stride), ell + (size_t)k * n_points + p0, ebytes, full);
+                occm_bulk_g2s(dst + NS * SB + (unsigned)(k * g.ell_stride), ell + (size_t)k * n_points + p0, ebytes, full);
             if (++slot == g.depth) { slot = 0; phase ^= 1u; }
         }
         return;
@@ -214,10 +228,12 @@ occm_pipe_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
     // ==================================================================== consumers
     const int pw = lane / H;
     const bool lane_on = pw < ppw;
-    const int pl = warp * ppw + pw;                                        // point of the chunk this thread works on
+    const int pl = warp * ppw + pw;                                        // point of a sub-chunk this thread works on
     const int sp = V * (lane - pw * H);                                    // its first species
-    const unsigned eo = 8u * (unsigned)(pl * S + sp);                      // byte offset of its element inside a staged stream
+    const unsigned eo = 8u * (unsigned)(pl * S + sp);                      // byte offset of its element inside a staged sub-chunk
+    const unsigned sub_bytes = 8u * (unsigned)(g.psub * S);                // bytes between the sub-chunks of a staged stream
     const unsigned row_sa = occm_opaque_u32((unsigned)__cvta_generic_to_shared(tile) + 8u * (unsigned)((warp * ppw + pw) * RS));
+    const unsigned tile_sub = 8u * (unsigned)(OCCM_PIPE_WARPS * ppw * RS); // bytes between the tiles of two sub-chunks
     const unsigned cmw_sa = WIDE ? occm_opaque_u32((unsigned)__cvta_generic_to_shared(mtw_s) + 4u * (unsigned)(NW + (NW & 1)) + (unsigned)(warp * g.wide_stride)) : 0u;
     const unsigned mtw_sa = WIDE ? occm_opaque_u32((unsigned)__cvta_generic_to_shared(mtw_s)) : 0u;
     unsigned meta0[OCCM_NT], meta1[OCCM_NT];
@@ -251,62 +267,82 @@ occm_pipe_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
             }
         }
         const int p0 = ci * g.pc;
-        const int pt = (lane_on && p0 + pl < n_points) ? p0 + pl : -1;
         const int npts = min(g.pc, n_points - p0);
         const unsigned slot_sa = ring_sa + (unsigned)slot * (unsigned)g.slot_bytes;
+        const unsigned ell_sa = slot_sa + NS * SB;
         const double* ga = occm_fast_in_a<STAGE>(sys, rk, y_in, cc);
         const double* gb = occm_fast_in_b<STAGE>(sys, mem, rk, cc);
         occm_mbar_wait(bar_sa + 8u * slot, phase);                         // the trip's bytes have landed
-        double err2 = 0.0;
-        double2 own = make_double2(0.0, 0.0);
-        int4 e4[K];
-        if (pt >= 0) {
-            own = occm_pipe_state<STAGE, V>(slot_sa, eo, cc.h);
-            occm_sts2_at<0u, V>(row_sa + 8u * sp, own);
+        // ---- phase 1, all E points of this thread: own stage state into the warp's tile, ELL sources, neighbour rows — from the
+        //      staged chunk when the source point is inside it, else a gather (L2); every gather of the trip is in flight together
+        int pt[E];
+        double2 own[E], gv[E][K];
+        unsigned skipmask = 0;                   // bit i: point i is flagged (left to occm_fixup) or past the end
 #pragma unroll
-            for (int k = 0; k < K; ++k)
-                asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(e4[k].x), "=r"(e4[k].y), "=r"(e4[k].z), "=r"(e4[k].w)
-                             : "r"(slot_sa + NS * OCCM_PIPE_STREAM_BYTES + (unsigned)(k * g.ell_stride) + 16u * (unsigned)pl));
+        for (int i = 0; i < E; ++i) {
+            const int pli = i * g.psub + pl;
+            pt[i] = (lane_on && p0 + pli < n_points) ? p0 + pli : -1;
+            own[i] = make_double2(0.0, 0.0);
+            if (pt[i] >= 0) {
+                own[i] = occm_pipe_state<STAGE, V>(slot_sa, eo + i * sub_bytes, cc.h);
+                occm_sts2_at<0u, V>(row_sa + i * tile_sub + 8u * sp, own[i]);
+            }
         }
-        __syncwarp();                            // the staged rows of a warp's points are written and read by that warp only
-        if (pt >= 0 && !e4[0].y) {
-            // ---- neighbour rows: from the staged chunk when the source point is inside it, else a gather (L2)
-            double2 gv[K];
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) gv[i][k] = make_double2(0.0, 0.0);
+            if (pt[i] < 0) { skipmask |= 1u << i; continue; }
+            const unsigned esa = ell_sa + 16u * (unsigned)(i * g.psub + pl);
+            int src0, flag;
+            asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(src0), "=r"(flag) : "r"(esa));
+            if (flag) { skipmask |= 1u << i; continue; }
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const unsigned rel = (unsigned)(e4[k].x - p0);
-                if (rel < (unsigned)npts) gv[k] = occm_pipe_state<STAGE, V>(slot_sa, 8u * (rel * (unsigned)S + (unsigned)sp), cc.h);
-                else gv[k] = occm_fast_in<STAGE, V>(ga, gb, cc.h, e4[k].x * S + sp);
+                int src = src0;
+                if (k > 0) asm volatile("ld.shared.s32 %0, [%1];" : "=r"(src) : "r"(esa + (unsigned)(k * g.ell_stride)));
+                const unsigned rel = (unsigned)(src - p0);
+                if (rel < (unsigned)npts) gv[i][k] = occm_pipe_state<STAGE, V>(slot_sa, 8u * (rel * (unsigned)S + (unsigned)sp), cc.h);
+                else gv[i][k] = occm_fast_in<STAGE, V>(ga, gb, cc.h, src * S + sp);
             }
+        }
+        __syncwarp();                            // the staged rows of a warp's points are written and read by that warp only
+        // ---- phase 2: reactions (tile), transport (weights re-read from the staged ELL columns), epilogue
+        double err2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            if (skipmask >> i & 1u) continue;
+            const unsigned rsa = row_sa + i * tile_sub;
             double r0, r1;
             if (WIDE) {
                 const unsigned c0 = cmw_sa + 8u * (unsigned)(sp * nt_u), m0 = mtw_sa + 4u * (unsigned)(sp * nt_u);
                 if (nf_u <= 2) {
-                    r0 = occm_reaction_wide_sa<2, 0u>(c0, m0, row_sa, nt_u);
-                    r1 = V == 2 ? occm_reaction_wide_sa<2, 0u>(c0 + 8u * nt_u, m0 + 4u * nt_u, row_sa, nt_u) : 0.0;
+                    r0 = occm_reaction_wide_sa<2, 0u>(c0, m0, rsa, nt_u);
+                    r1 = V == 2 ? occm_reaction_wide_sa<2, 0u>(c0 + 8u * nt_u, m0 + 4u * nt_u, rsa, nt_u) : 0.0;
                 } else {
-                    r0 = occm_reaction_wide_sa<3, 0u>(c0, m0, row_sa, nt_u);
-                    r1 = V == 2 ? occm_reaction_wide_sa<3, 0u>(c0 + 8u * nt_u, m0 + 4u * nt_u, row_sa, nt_u) : 0.0;
+                    r0 = occm_reaction_wide_sa<3, 0u>(c0, m0, rsa, nt_u);
+                    r1 = V == 2 ? occm_reaction_wide_sa<3, 0u>(c0 + 8u * nt_u, m0 + 4u * nt_u, rsa, nt_u) : 0.0;
                 }
             } else if (nf_u <= 2) {                 // uniform: one of four straight-line variants
-                if (nt_u <= 2) { r0 = occm_reaction_sa<2, 2, 0u>(cm0, meta0, row_sa); r1 = V == 2 ? occm_reaction_sa<2, 2, 0u>(cm1, meta1, row_sa) : 0.0; }
-                else           { r0 = occm_reaction_sa<4, 2, 0u>(cm0, meta0, row_sa); r1 = V == 2 ? occm_reaction_sa<4, 2, 0u>(cm1, meta1, row_sa) : 0.0; }
+                if (nt_u <= 2) { r0 = occm_reaction_sa<2, 2, 0u>(cm0, meta0, rsa); r1 = V == 2 ? occm_reaction_sa<2, 2, 0u>(cm1, meta1, rsa) : 0.0; }
+                else           { r0 = occm_reaction_sa<4, 2, 0u>(cm0, meta0, rsa); r1 = V == 2 ? occm_reaction_sa<4, 2, 0u>(cm1, meta1, rsa) : 0.0; }
             } else {
-                if (nt_u <= 2) { r0 = occm_reaction_sa<2, 3, 0u>(cm0, meta0, row_sa); r1 = V == 2 ? occm_reaction_sa<2, 3, 0u>(cm1, meta1, row_sa) : 0.0; }
-                else           { r0 = occm_reaction_sa<4, 3, 0u>(cm0, meta0, row_sa); r1 = V == 2 ? occm_reaction_sa<4, 3, 0u>(cm1, meta1, row_sa) : 0.0; }
+                if (nt_u <= 2) { r0 = occm_reaction_sa<2, 3, 0u>(cm0, meta0, rsa); r1 = V == 2 ? occm_reaction_sa<2, 3, 0u>(cm1, meta1, rsa) : 0.0; }
+                else           { r0 = occm_reaction_sa<4, 3, 0u>(cm0, meta0, rsa); r1 = V == 2 ? occm_reaction_sa<4, 3, 0u>(cm1, meta1, rsa) : 0.0; }
             }
+            const unsigned esa = ell_sa + 16u * (unsigned)(i * g.psub + pl) + 8u;       // the weights of this point's ELL entries
             double2 f;
             if (MODEL == 0) {
                 double2 acc = make_double2(0.0, 0.0);
 #pragma unroll
-                for (int k = 0; k < K; ++k) acc = occm_fma2(__hiloint2double(e4[k].w, e4[k].z), gv[k], acc);
+                for (int k = 0; k < K; ++k) acc = occm_fma2(occm_lds_f64(esa + (unsigned)(k * g.ell_stride)), gv[i][k], acc);
                 f = make_double2(__dadd_rn(__dmul_rn(cc.qs, acc.x), r0), __dadd_rn(__dmul_rn(cc.qs, acc.y), r1));
             } else {                     // first-order upwind difference along the PFR
-                const double na = -(cc.qs * __hiloint2double(e4[0].w, e4[0].z));
-                f = make_double2(__dadd_rn(__dmul_rn(na, own.x - gv[0].x), r0), __dadd_rn(__dmul_rn(na, own.y - gv[0].y), r1));
+                const double na = -(cc.qs * occm_lds_f64(esa));
+                f = make_double2(__dadd_rn(__dmul_rn(na, own[i].x - gv[i][0].x), r0), __dadd_rn(__dmul_rn(na, own[i].y - gv[i][0].y), r1));
             }
-            const OccmOps2 ops = occm_pipe_read_ops<STAGE, V>(slot_sa + eo);
-            err2 = occm_fast_finish<STAGE, V>(sys, rk, cc, ops, f, own, pt * S + sp, dy_out);
+            const OccmOps2 ops = occm_pipe_read_ops<STAGE, V>(slot_sa + eo + i * sub_bytes);
+            err2 += occm_fast_finish<STAGE, V>(sys, rk, cc, ops, f, own[i], pt[i] * S + sp, dy_out);
         }   // flagged rows (boundary / pulse / overflow entries, PFR inlet nodes) are left to occm_fixup, launched right after
         if (STAGE == 7) {          // one partial per warp, summed in fixed order by the controller
             double v = err2;

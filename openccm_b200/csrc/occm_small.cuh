@@ -26,16 +26,20 @@ struct OccmSmallCtl {       // per-member controller state (shared memory copy o
     int status, rejected, out_lo, out_hi, accepted;
 };
 
-// f = ddt(t_stage, ys) for every element of the member (block-wide); all threads must call it
-template <int MODEL>
-__device__ __forceinline__ void occm_small_rhs(const OccmSysDev& sys, const int* tab_s, const double* ys, double* f, double t_stage,
-                                               double qs, double bs, const double* ksc) {
+// f = ddt(t_stage, ys) for every element of the member (block-wide), followed by `post(e, f)` on the same element — the
+// combination that only needs the element's own values (next stage state, y_new, error term) rides in the same pass, so a stage
+// is ONE pass and ONE barrier.  `post` must not write anything another thread reads during this pass (the stage states ping-pong).
+template <int MODEL, class Post>
+__device__ __forceinline__ void occm_small_stage(const OccmSysDev& sys, const int* tab_s, const double* ys, double* f, double t_stage,
+                                                 double qs, double bs, const double* ksc, const Post& post) {
     const int S = sys.S, ndof = (int)sys.ndof;
     OccmSmallIn in; in.a = ys;
     for (int e = threadIdx.x; e < ndof; e += blockDim.x) {
         const int p = e / S, s = e - p * S;
         const double* myrow = ys + p * S;
-        f[e] = occm_point_generic<MODEL, OccmSmallIn, true>(sys, tab_s, in, myrow, myrow - S, p, s, t_stage, qs, bs, ksc);
+        const double v = occm_point_generic<MODEL, OccmSmallIn, true>(sys, tab_s, in, myrow, myrow - S, p, s, t_stage, qs, bs, ksc);
+        f[e] = v;
+        post(e, v);
     }
     __syncthreads();
 }
@@ -54,9 +58,10 @@ occm_rk45_small(const __grid_constant__ OccmSysDev sys_g, const __grid_constant_
     occm_load_tables(sys_g.tables, sys_g.tables_bytes, tab_s);
     const int ndof = (int)sys_g.ndof, tid = threadIdx.x, nthr = blockDim.x;
     double* y = smem_d + (sys_g.tables_bytes >> 3);
-    double* yn = y + ndof;            // y_new (stage-7 state)
-    double* ys = yn + ndof;           // stage state
-    double* Kb = ys + ndof;           // K1..K7: slot i at Kb + i * ndof; K1 and K7 swap roles on an accepted step (FSAL)
+    double* yn = y + ndof;            // y_new (stage-7 state); swaps with y on an accepted step
+    double* ysA = yn + ndof;          // stage states ping-pong: a stage reads one while its pass writes the next into the other
+    double* ysB = ysA + ndof;
+    double* Kb = ysB + ndof;          // K1..K7: slot i at Kb + i * ndof; K1 and K7 swap roles on an accepted step (FSAL)
     // ---- the operator itself (CSR rows, Q/dV per PFR, pulse lists) also lives in shared memory: the generic row walk is a
     //      chain of dependent index / weight loads, 300+ cycles each from L2 (29 us per step on the 444-PFR network before)
     __shared__ OccmSysDev sys_sh;                                    // (a local copy would live in local memory: it is passed by reference)
@@ -103,36 +108,27 @@ occm_rk45_small(const __grid_constant__ OccmSysDev sys_g, const __grid_constant_
         const double t = ctl.t, h = ctl.h;
         double* K1 = Kb + i1 * ndof; double* K2 = Kb + 1 * ndof; double* K3 = Kb + 2 * ndof; double* K4 = Kb + 3 * ndof;
         double* K5 = Kb + 4 * ndof; double* K6 = Kb + 5 * ndof; double* K7 = Kb + i7 * ndof;
-        // ---- stages 2..6 (rk.py:14-71): stage state, then its slope
-        for (int e = tid; e < ndof; e += nthr) ys[e] = y[e] + (dp::A21 * K1[e]) * h;
+        // ---- stages 2..7 (rk.py:14-71, 64-69, 157-162): each pass evaluates a slope and forms what the next pass differentiates
+        for (int e = tid; e < ndof; e += nthr) ysA[e] = y[e] + (dp::A21 * K1[e]) * h;
         __syncthreads();
-        occm_small_rhs<MODEL>(sys, tab_s, ys, K2, t + dp::C2 * h, qs, bs, ksc);
-        for (int e = tid; e < ndof; e += nthr) ys[e] = y[e] + (dp::A31 * K1[e] + dp::A32 * K2[e]) * h;
-        __syncthreads();
-        occm_small_rhs<MODEL>(sys, tab_s, ys, K3, t + dp::C3 * h, qs, bs, ksc);
-        for (int e = tid; e < ndof; e += nthr) ys[e] = y[e] + (dp::A41 * K1[e] + dp::A42 * K2[e] + dp::A43 * K3[e]) * h;
-        __syncthreads();
-        occm_small_rhs<MODEL>(sys, tab_s, ys, K4, t + dp::C4 * h, qs, bs, ksc);
-        for (int e = tid; e < ndof; e += nthr) ys[e] = y[e] + (dp::A51 * K1[e] + dp::A52 * K2[e] + dp::A53 * K3[e] + dp::A54 * K4[e]) * h;
-        __syncthreads();
-        occm_small_rhs<MODEL>(sys, tab_s, ys, K5, t + dp::C5 * h, qs, bs, ksc);
-        for (int e = tid; e < ndof; e += nthr)
-            ys[e] = y[e] + (dp::A61 * K1[e] + dp::A62 * K2[e] + dp::A63 * K3[e] + dp::A64 * K4[e] + dp::A65 * K5[e]) * h;
-        __syncthreads();
-        occm_small_rhs<MODEL>(sys, tab_s, ys, K6, t + h, qs, bs, ksc);
-        // ---- y_new, f_new = K7, error estimate (rk.py:64-69, 157-162)
-        for (int e = tid; e < ndof; e += nthr)
-            yn[e] = y[e] + h * (dp::B1 * K1[e] + dp::B3 * K3[e] + dp::B4 * K4[e] + dp::B5 * K5[e] + dp::B6 * K6[e]);
-        __syncthreads();
-        occm_small_rhs<MODEL>(sys, tab_s, yn, K7, t + h, qs, bs, ksc);
+        occm_small_stage<MODEL>(sys, tab_s, ysA, K2, t + dp::C2 * h, qs, bs, ksc,
+                                [&](int e, double f) { ysB[e] = y[e] + (dp::A31 * K1[e] + dp::A32 * f) * h; });
+        occm_small_stage<MODEL>(sys, tab_s, ysB, K3, t + dp::C3 * h, qs, bs, ksc,
+                                [&](int e, double f) { ysA[e] = y[e] + (dp::A41 * K1[e] + dp::A42 * K2[e] + dp::A43 * f) * h; });
+        occm_small_stage<MODEL>(sys, tab_s, ysA, K4, t + dp::C4 * h, qs, bs, ksc,
+                                [&](int e, double f) { ysB[e] = y[e] + (dp::A51 * K1[e] + dp::A52 * K2[e] + dp::A53 * K3[e] + dp::A54 * f) * h; });
+        occm_small_stage<MODEL>(sys, tab_s, ysB, K5, t + dp::C5 * h, qs, bs, ksc,
+                                [&](int e, double f) { ysA[e] = y[e] + (dp::A61 * K1[e] + dp::A62 * K2[e] + dp::A63 * K3[e] + dp::A64 * K4[e] + dp::A65 * f) * h; });
+        occm_small_stage<MODEL>(sys, tab_s, ysA, K6, t + h, qs, bs, ksc,
+                                [&](int e, double f) { yn[e] = y[e] + h * (dp::B1 * K1[e] + dp::B3 * K3[e] + dp::B4 * K4[e] + dp::B5 * K5[e] + dp::B6 * f); });
         double e2 = 0.0;
-        for (int e = tid; e < ndof; e += nthr) {
+        occm_small_stage<MODEL>(sys, tab_s, yn, K7, t + h, qs, bs, ksc, [&](int e, double f) {
             const double part = dp::E1 * K1[e] + dp::E3 * K3[e] + dp::E4 * K4[e] + dp::E5 * K5[e] + dp::E6 * K6[e];
-            const double err = (part + dp::E7 * K7[e]) * h;
+            const double err = (part + dp::E7 * f) * h;
             const double scale = rk.atol + fmax(fabs(y[e]), fabs(yn[e])) * rk.rtol;
             const double q = err / scale;
             e2 += q * q;
-        }
+        });
         const double sum = occm_block_sum(e2, scratch);       // valid in thread 0; contains the barriers
         // ---- controller (rk.py:111-167; same statements as occm_rk45_control)
         if (tid == 0) {
@@ -205,9 +201,8 @@ occm_rk45_small(const __grid_constant__ OccmSysDev sys_g, const __grid_constant_
                 }
                 __syncthreads();
             }
-            for (int e = tid; e < ndof; e += nthr) y[e] = yn[e];
+            { double* sw = y; y = yn; yn = sw; }            // accepted: y_new is the state (no copy pass)
             const int sw = i1; i1 = i7; i7 = sw;             // first same as last: K7 is the next step's K1
-            __syncthreads();
         }
     }
     // ---- back to the workspace: slot 0 of the ping-pong pairs holds the state

@@ -748,11 +748,13 @@ static int occm_launch_pipe(const occm_system* sys, const OccmMemDev& mem, const
     // bulk copies move multiples of 16 bytes from 16-byte aligned addresses: every member base and every chunk must start on one
     if ((ndof & 1) || ((sys->dev.n_points * S) & 1)) return 1;
     if (STAGE <= 1 && (!occm_aligned16(y_in) || !occm_aligned16(dy_out) || (STAGE == 1 && !occm_aligned16(mem.z)))) return 1;
+    constexpr int E = OccmPipeE<STAGE>::value;
     OccmPipeGeom g;
-    g.pc = OCCM_PIPE_WARPS * ppw;
+    g.psub = OCCM_PIPE_WARPS * ppw;
+    g.pc = E * g.psub;
     g.cpm = (int)((sys->dev.n_points + g.pc - 1) / g.pc);
     g.ell_stride = g.pc * 16;
-    g.slot_bytes = (int)((NS * OCCM_PIPE_STREAM_BYTES + (unsigned)(K * g.ell_stride) + 127u) & ~127u);
+    g.slot_bytes = (int)((NS * OccmPipeStreamBytes<STAGE>::value + (unsigned)(K * g.ell_stride) + 127u) & ~127u);
     const size_t nw = (size_t)S * sys->max_terms;
     size_t o = ((size_t)sys->dev.tables_bytes + 15) & ~(size_t)15;
     g.coef_off = (int)o;
@@ -760,7 +762,7 @@ static int occm_launch_pipe(const occm_system* sys, const OccmMemDev& mem, const
     o += WIDE ? 8 * nw + 4 * (nw + (nw & 1)) + (size_t)OCCM_PIPE_WARPS * g.wide_stride : sizeof(double) * (size_t)S * OCCM_NT;
     o = (o + 15) & ~(size_t)15;
     g.tile_off = (int)o;
-    o += sizeof(double) * (size_t)OCCM_PIPE_WARPS * ppw * (S + 2);
+    o += sizeof(double) * (size_t)E * OCCM_PIPE_WARPS * ppw * (S + 2);
     o = (o + 15) & ~(size_t)15;
     g.bar_off = (int)o;
     o += 16 * OCCM_PIPE_MAX_DEPTH;
@@ -1057,7 +1059,7 @@ static int occm_rk45_run_small(occm_rk45* rk, int64_t max_launch_steps, int32_t*
     const long long ndof = sys->dev.ndof;
     if (!sys->use_small || !rk->prob.t_eval || ndof > OCCM_SMALL_MAX_NDOF || rk->M > 65535) return 1;
     const int nm = sys->dev.n_models, nnz = sys->nnz, pnnz = sys->pulse_nnz;
-    const size_t smem = (size_t)sys->dev.tables_bytes + sizeof(double) * (10 * (size_t)ndof + nnz + nm + pnnz) +
+    const size_t smem = (size_t)sys->dev.tables_bytes + sizeof(double) * (11 * (size_t)ndof + nnz + nm + pnnz) +
                         sizeof(int) * (2 * (size_t)(nm + 1) + nnz + pnnz) + 16;
     if (smem > (size_t)sys->smem_per_block) return 1;
     int block = (int)((ndof + 31) / 32 * 32);

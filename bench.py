@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-strong', action='store_true', help='skip the 4096-member strong-scaling solve')
     ap.add_argument('--no-bdf', action='store_true', help='skip the C5 BDF block (N = 1)')
+    ap.add_argument('--no-small', action='store_true', help='skip the block of the reference-sized networks C1-C3 (N = 1)')
     ap.add_argument('--strong-members', type=int, default=4096)
     return ap.parse_args()
 
@@ -252,6 +253,60 @@ def run_reference_arm(args):
     _emit(line)
 
 
+
+
+# ------------------------------------------------------------------------------------------------ reference-sized networks (C1-C3)
+def small_block(args):
+    """BASELINE configs[0..2] — one CSTR (A -> B -> C), the 444-PFR and the 76-CSTR networks of examples/OpenFOAM/pipe_with_recirc
+    (inputs: tests/golden fixtures made from the unmodified reference) — single solves through the drop-in `solve_system` and
+    4096-member ensembles.  These networks fit in shared memory: RK45 runs as one persistent CTA per member (occm_small.cuh)."""
+    import contextlib
+    import io
+    import tempfile
+    import torch
+    for p in (os.path.join(REPO, 'tests'), os.path.join(REPO, 'tests', 'golden')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import cases as C
+    from _util import setup_case
+    from openccm_b200.ensemble import EnsembleSolver
+    from openccm_b200.system_solvers import solve_system
+    out = {}
+
+    def single(name, solver, **kw):
+        cp, cmesh, net, mn = setup_case(name, solver, tempfile.mkdtemp(), **kw)
+        for _ in range(2):                                   # second call: tables uploaded, kernels loaded
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            with contextlib.redirect_stdout(io.StringIO()):
+                c, t, im, om, info = solve_system(C.CASES[name]['model'], mn, cp, cmesh, return_info=True)
+            torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        steps = info['n_accepted'] + info['n_rejected']
+        return {"seconds": dt, "steps": steps, "nfev": info['nfev'], "us_per_step": 1e6 * dt / max(steps, 1), "status": info['status']}
+
+    def ensemble(name, model, solver, M, rtd=False, **kw):
+        cp, cmesh, net, mn = setup_case(name, solver, tempfile.mkdtemp(), **kw)
+        es = EnsembleSolver(model, mn, cp, cmesh)
+        rng = np.random.default_rng(0)
+        qs = rng.uniform(0.5, 2.0, M)
+        ks = 10.0 ** rng.uniform(-0.5, 0.5, (M, es.host.tables.n_rxn)) if es.host.tables.n_rxn else None
+        for _ in range(2):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            r = es.solve(M, q_scale=qs, k_scale=ks, save='outlets', rtd=rtd)
+            torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        return {"members": M, "seconds": dt, "ode_solves_per_s": M / dt, "evals_per_s": float(r.nfev.sum()) * es.host.ndof / dt,
+                "steps_per_member": float((r.n_accepted + r.n_rejected).mean()), "ok": bool(np.all(r.status == 1))}
+
+    user = dict(rtol=1e-6, atol=1e-10)
+    out["C1_single_cstr_ensemble_rk45"] = ensemble('cstr_irreversible', 'cstr', 'B200-RK45', 4096, **user)
+    out["C2_444pfr_rk45"] = single('openfoam_2d_pfr', 'B200-RK45', **user)
+    out["C2_444pfr_bdf"] = single('openfoam_2d_pfr', 'B200-BDF', **user)
+    out["C2_444pfr_lsoda"] = single('openfoam_2d_pfr', 'B200-LSODA', **user)
+    out["C2_444pfr_bdf_ensemble_rtd"] = ensemble('openfoam_2d_pfr', 'pfr', 'B200-BDF', 256, rtd=True, **user)
+    out["C3_76cstr_nacl_rk45"] = single('openfoam_2d_cstr_nacl', 'B200-RK45', **user)
+    out["C3_76cstr_nacl_ensemble_rk45"] = ensemble('openfoam_2d_cstr_nacl', 'cstr', 'B200-RK45', 4096, **user)
+    out["reference"] = ("measured with the unmodified reference in the build container (BASELINE.md, SURVEY 3.5): C2 LSODA 12.9 s "
+                        "(5.9 s on the GPU box's host, tests/test_gpu_dropin.py), RK45 96.6 s; C3 LSODA 12.9 s incl. numba JIT")
+    return out
 
 # ------------------------------------------------------------------------------------------------ BDF block (C5)
 def _bdf_cpu_job(payload):
@@ -576,6 +631,13 @@ def main():
         except Exception as exc:           # never take the headline down
             bdf = {"failed": repr(exc)}
 
+    small = None
+    if rank == 0 and world_size == 1 and not args.no_small:
+        try:
+            small = small_block(args)
+        except Exception as exc:
+            small = {"failed": repr(exc)}
+
     cpu = None
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
         try:
@@ -597,7 +659,7 @@ def main():
                         "collectives": "gather to rank 0 (outlets, RTD, counters) + all_reduce(RTD moment statistics) inside the timed region",
                         "gather_ms": float(np.mean(gather_ms)), "reduce_ms": float(np.mean(reduce_ms))},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "plain_rhs": plain, "cpu_baseline": cpu,
-                "strong": strong, "bdf": bdf}
+                "strong": strong, "bdf": bdf, "small_networks": small}
         _emit(line)
     if world_size > 1:
         dist.destroy_process_group()

@@ -65,3 +65,16 @@ for name, model, t_end in (('openfoam_2d_cstr_nacl', 'cstr', 300.0), ('openfoam_
     evals = float(r.nfev.sum()) * solver.host.ndof
     print(f'{name:22s} ensemble M={M} t_end={t_end:g}: {dt:7.3f} s  {M / dt:9.1f} solves/s  {evals / dt / 1e9:7.2f} G evals/s  '
           f'steps/member {int((r.n_accepted + r.n_rejected).mean())}  status {np.unique(r.status)}', flush=True)
+
+# ---- the stiff real network as an ensemble through the batched BDF (all members advance in lock step, per-member order / step)
+tmp = tempfile.mkdtemp()
+cp, cmesh, net, mn = setup_case('openfoam_2d_pfr', 'B200-BDF', tmp, rtol=1e-6, atol=1e-10)
+solver = EnsembleSolver('pfr', mn, cp, cmesh)
+for M in (64, 1024):
+    qs = np.random.default_rng(0).uniform(0.5, 2.0, M)
+    for rep in range(2):
+        torch.cuda.synchronize(); t0 = time.time()
+        r = solver.solve(M, q_scale=qs, save='outlets', rtd=True)
+        torch.cuda.synchronize(); dt = time.time() - t0
+    print(f'openfoam_2d_pfr        BDF ensemble M={M} t in [0, 300], 61 outputs + RTD: {dt:7.3f} s  {M / dt:9.1f} solves/s  '
+          f'steps/member {int((r.n_accepted + r.n_rejected).mean())}  status {np.unique(r.status)}', flush=True)

@@ -65,16 +65,26 @@ def export_to_vtu_openfoam(concentrations_all_time: np.ndarray, ts: np.ndarray,
     t_span = config_parser.get_list(['SIMULATION', 't_span'], float)
     num_elements = len(cmesh.element_sizes)
     assert len(model_to_element_map) * points_per_model == np.shape(concentrations_all_time)[1]
-    fields = element_fields(concentrations_all_time, model_to_element_map, points_per_model, num_elements)
+    # all (time, species) element buffers in one kernel launch; they leave the device one output time at a time through the
+    # asynchronous writer, so the (slow, text) file formatting of time i overlaps the download of time i + 1
+    from .writer import AsyncResultWriter
+    fields = element_fields(concentrations_all_time, model_to_element_map, points_per_model, num_elements, as_numpy=False)
 
     t0_path = os.path.join(output_folder_path + vtu_folder_path + str(t_span[0]))
     contents_of_t0 = [(name, os.path.abspath(os.path.join(t0_path, name))) for name in os.listdir(t0_path)]
-    for i_t, t in enumerate(ts):
-        output_folder = output_folder_path + vtu_folder_path + str(t)
-        Path(output_folder).mkdir(parents=True, exist_ok=(i_t == 0))
-        if t != t_span[0]:
-            for name, original in contents_of_t0:
-                os.symlink(original, os.path.join(output_folder, name))
-        for i_specie, specie in enumerate(species_names):
-            write_buffer(fields[i_t, i_specie], output_folder + '/c_' + specie, t, specie, cmesh)
+
+    def sink_for(i_t, t):
+        def sink(buf):                                          # buf: [S, n_elements] of this output time, on the host
+            output_folder = output_folder_path + vtu_folder_path + str(t)
+            Path(output_folder).mkdir(parents=True, exist_ok=(i_t == 0))
+            if t != t_span[0]:
+                for name, original in contents_of_t0:
+                    os.symlink(original, os.path.join(output_folder, name))
+            for i_specie, specie in enumerate(species_names):
+                write_buffer(buf[i_specie], output_folder + '/c_' + specie, t, specie, cmesh)
+        return sink
+
+    with AsyncResultWriter(max_pending=2) as writer:
+        for i_t, t in enumerate(ts):
+            writer.submit(sink_for(i_t, t), fields[i_t])
     print("Done exporting simulation visualization")

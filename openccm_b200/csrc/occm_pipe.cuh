@@ -27,6 +27,9 @@
 #endif
 #define OCCM_PIPE_SUB_BYTES 4096u                           // a sub-chunk's rows of one vector: 7 * (32 / H) points * S * 8 B <= 4096
 #define OCCM_PIPE_MAX_DEPTH 8
+#ifndef OCCM_PIPE_L2_AHEAD
+#define OCCM_PIPE_L2_AHEAD 0                                // experiment (measured slower, see below): NEXT member's rows of the gathered vector(s) -> L2
+#endif
 #ifndef OCCM_PIPE_E_LIGHT
 #define OCCM_PIPE_E_LIGHT 1                                 // sub-chunks per trip in the light stages (see OccmPipeE)
 #endif
@@ -78,6 +81,10 @@ __device__ __forceinline__ void occm_mbar_wait(unsigned bar, unsigned parity) {
         "}" :: "r"(bar), "r"(parity) : "memory");
 }
 // global -> shared, completion counted in bytes on `bar`; dst, src and bytes are multiples of 16
+// contiguous range -> L2 only (no shared memory, no completion): src and bytes are multiples of 16
+__device__ __forceinline__ void occm_bulk_prefetch_l2(const void* src, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void occm_bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -203,7 +210,7 @@ occm_pipe_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
         //  consumers.  prefetch.global.L2 fetches whole lines for rows of which the gathers touch 2-3 sectors, and it runs ahead
         //  of the streaming pass that would have brought half of them in anyway: DRAM traffic up, every kernel 10-90 % slower.)
         if (lane != 0) return;
-        int cur_m = -1, par = 0;
+        int cur_m = -1, par = 0, ahead_m = -1, ahead_par = 0;
         for (bool valid = skip(); valid; valid = advance()) {
             if (cur_m != m) { cur_m = m; par = STAGE >= 2 ? rk.parity[m] : 0; }
             const int p0 = ci * g.pc;
@@ -220,6 +227,17 @@ occm_pipe_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
 #pragma unroll
             for (int k = 0; k < K; ++k)
                 occm_bulk_g2s(dst + NS * SB + (unsigned)(k * g.ell_stride), ell + (size_t)k * n_points + p0, ebytes, full);
+            // ---- experiment, off by default: one member ahead, the same chunk of the NEXT member's stage-state vector(s) goes to
+            //      L2 (cp.async.bulk.prefetch.L2), so that the out-of-chunk row gathers — half of which point ahead of the streaming
+            //      front and miss L2 — would hit, with every line fetched once and whole.  Measured (C4, 512 members): every kernel
+            //      20-45 % slower (plain RHS 3.19 -> 3.96 ms, stage 5 5.56 -> 7.00 ms): the prefetched lines do not survive the
+            //      65 us until their member is streamed and are read from DRAM twice.
+            if (OCCM_PIPE_L2_AHEAD && m + 1 < mem.M) {
+                if (ahead_m != m + 1) { ahead_m = m + 1; ahead_par = STAGE >= 2 ? rk.parity[m + 1] : 0; }
+                const long long e1 = (long long)(m + 1) * sys.ndof + (long long)p0 * S;
+                occm_bulk_prefetch_l2(occm_pipe_src<STAGE>(mem, rk, y_in, ahead_par, 0) + e1, vbytes);
+                if (STAGE == 1 || STAGE == 2) occm_bulk_prefetch_l2(occm_pipe_src<STAGE>(mem, rk, y_in, ahead_par, 1) + e1, vbytes);
+            }
             if (++slot == g.depth) { slot = 0; phase ^= 1u; }
         }
         return;

@@ -33,6 +33,7 @@ struct OccmBdfDev {
     double* D;                               // [8][M][ndof]
     double* y; double* psi; double* d; double* f; double* f2; double* z; double* w;
     double* V;                               // [restart + 1][M][ndof]
+    double* Z;                               // [restart][M][ndof]  preconditioned Krylov vectors z_j = M^-1 S v_j (flexible GMRES)
     double* t; double* h_abs; double* t_new; double* c; double* t_old_out;
     int* order; int* n_equal; int* status; int* fresh;      // fresh: first attempt of a new step
     int* newton_active; int* newton_k; int* converged; int* n_iter; double* dy_norm_old;
@@ -104,15 +105,13 @@ __device__ void bdf_set_change(const OccmBdfDev& b, int m, int order, double fac
 __global__ void __launch_bounds__(512) bdf_reduce(const double* __restrict__ partial, int nchunk, int nvals, double* __restrict__ out,
                                                   const int* __restrict__ mask) {
     __shared__ double scratch[16];
-    const int m = blockIdx.x;
+    const int m = blockIdx.x, k = blockIdx.y;            // one CTA per (member, slot): with one member a single CTA summed up to 32 slots in turn
     if (mask && !mask[m]) return;
-    for (int k = 0; k < nvals; ++k) {
-        const double* p = partial + ((long long)m * BDF_MAXDOT + k) * nchunk;
-        double v = 0.0;
-        for (int i = threadIdx.x; i < nchunk; i += blockDim.x) v += p[i];
-        const double s = occm_block_sum(v, scratch);
-        if (threadIdx.x == 0) out[(long long)m * BDF_MAXDOT + k] = s;
-    }
+    const double* p = partial + ((long long)m * BDF_MAXDOT + k) * nchunk;
+    double v = 0.0;
+    for (int i = threadIdx.x; i < nchunk; i += blockDim.x) v += p[i];
+    const double s = occm_block_sum(v, scratch);
+    if (threadIdx.x == 0) out[(long long)m * BDF_MAXDOT + k] = s;
 }
 
 // chunk iteration helper: CTA c handles elements [ci * BDF_CHUNK, ...) of member m
@@ -305,7 +304,7 @@ __device__ __forceinline__ void bdf_group_solve(const OccmTab& T, int nterm, int
 
 template <int MODEL, int W>
 __global__ void __launch_bounds__(128) bdf_precond_warp(const __grid_constant__ OccmSysDev sys, const OccmBdfDev b, const double* __restrict__ src,
-                                                        int src_is_V_col_j, double* __restrict__ dst, const int* __restrict__ mask) {
+                                                        int src_is_V_col_j, double* __restrict__ dst, const int* __restrict__ mask, int keep_z) {
     extern __shared__ double smem_d[];
     int* tab_s = reinterpret_cast<int*>(smem_d);
     occm_load_tables(sys.tables, sys.tables_bytes, tab_s);
@@ -330,7 +329,7 @@ __global__ void __launch_bounds__(128) bdf_precond_warp(const __grid_constant__ 
             const double y = on ? b.y[g0] : 0.0, d = on ? b.d[g0] : 0.0;
             double u = on ? (b.atol + b.rtol * fabs(y - d)) * in[idx * S + lane] : 0.0;
             bdf_group_solve<W>(T, nterm, nfac, S, lane, y, c, qs * b.tdiag[gv ? idx : 0], ksc, u);
-            if (on) dst[g0] = u;
+            if (on) { dst[g0] = u; if (keep_z) b.Z[(long long)b.gmres_j[m] * b.vstride + g0] = u; }
         } else {
             const double ca = c * qs * (-b.tdiag[gv ? idx : 0]);             // c * Q/dV of this PFR
             double xprev = 0.0;
@@ -348,7 +347,7 @@ __global__ void __launch_bounds__(128) bdf_precond_warp(const __grid_constant__ 
                     u += ca * xprev;
                     bdf_group_solve<W>(T, nterm, nfac, S, lane, y, c, -ca / c, ksc, u);
                 }
-                if (on) dst[gbase + (long long)i * S] = u;
+                if (on) { dst[gbase + (long long)i * S] = u; if (keep_z) b.Z[(long long)b.gmres_j[m] * b.vstride + gbase + (long long)i * S] = u; }
                 xprev = u;
                 y = yn; d = dn; w = wn;
             }
@@ -397,7 +396,7 @@ __global__ void __launch_bounds__(128) bdf_precond_factor(const __grid_constant_
 // ... and apply: out = M^-1 (scale .* in) as one S x S mat-vec per point (PFR: inside the flow-order sweep)
 template <int MODEL, int W>
 __global__ void __launch_bounds__(128) bdf_precond_apply(const OccmBdfDev b, const double* __restrict__ src, int src_is_V_col_j,
-                                                         double* __restrict__ dst, const int* __restrict__ mask) {
+                                                         double* __restrict__ dst, const int* __restrict__ mask, int keep_z) {
     const int S = b.S, P = b.P;
     const int lane = threadIdx.x % W, gib = threadIdx.x / W, gpb = 128 / W;
     const long long per_member = MODEL == 0 ? b.n_points : b.n_points / P;
@@ -423,7 +422,7 @@ __global__ void __launch_bounds__(128) bdf_precond_apply(const OccmBdfDev b, con
                 a0 += r[j] * __shfl_sync(0xffffffffu, u, j, W);
                 a1 += r[j + 1] * __shfl_sync(0xffffffffu, u, j + 1, W);
             }
-            if (on) dst[g0] = a0 + a1;
+            if (on) { dst[g0] = a0 + a1; if (keep_z) b.Z[(long long)b.gmres_j[m] * b.vstride + g0] = a0 + a1; }
         } else {
             const double c = b.c[m];
             const double qs = b.q_scale ? b.q_scale[m] : 1.0;
@@ -456,7 +455,7 @@ __global__ void __launch_bounds__(128) bdf_precond_apply(const OccmBdfDev b, con
                     }
                     u = a0 + a1;
                 }
-                if (on) dst[gbase + (long long)i * S] = u;
+                if (on) { dst[gbase + (long long)i * S] = u; if (keep_z) b.Z[(long long)b.gmres_j[m] * b.vstride + gbase + (long long)i * S] = u; }
                 xprev = u;
                 y = yn; d = dn; w = wn;
 #pragma unroll
@@ -528,7 +527,8 @@ __global__ void __launch_bounds__(256) bdf_orth(const OccmBdfDev b, int second_p
     }
 }
 
-// w = sum_k ycoef[m][k] V[k], k < n_iter_gmres[m]   (solution in the Krylov basis, before the preconditioner)
+// dy = z = sum_k ycoef[m][k] Z[k], k < n_iter_gmres[m]: the Newton correction straight from the stored preconditioned Krylov
+// vectors z_k = M^-1 S v_k (flexible GMRES) — no preconditioner application after the solve (one of ~3.3 per Newton iteration on C5)
 __global__ void __launch_bounds__(256) bdf_lincomb_V(const OccmBdfDev b) {
     BDF_FOR_CHUNKS(b, b.newton_active[m]) {
         const int n = b.gmres_j[m];             // number of Arnoldi vectors used
@@ -536,8 +536,8 @@ __global__ void __launch_bounds__(256) bdf_lincomb_V(const OccmBdfDev b) {
         BDF_ELEMS(b, ci, e) {
             const long long g = (long long)m * b.ndof + e;
             double acc = 0.0;
-            for (int k = 0; k < n; ++k) acc += yc[k] * b.V[(long long)k * b.vstride + g];
-            b.w[g] = acc;
+            for (int k = 0; k < n; ++k) acc += yc[k] * b.Z[(long long)k * b.vstride + g];
+            b.z[g] = acc;
         }
     }
 }
@@ -986,6 +986,7 @@ static size_t bdf_carve(const occm_system* sys, int M, int restart, int store, O
     b.y = (double*)take(vec); b.psi = (double*)take(vec); b.d = (double*)take(vec); b.f = (double*)take(vec);
     b.f2 = (double*)take(vec); b.z = (double*)take(vec); b.w = (double*)take(vec);
     b.V = (double*)take(vec * (restart + 1));
+    b.Z = (double*)take(vec * restart);
     const size_t md = (size_t)M * 8, mi = (size_t)M * 4, mm = (size_t)M * BDF_MAXDOT * 8;
     b.t = (double*)take(md); b.h_abs = (double*)take(md); b.t_new = (double*)take(md); b.c = (double*)take(md); b.t_old_out = (double*)take(md);
     b.order = (int*)take(mi); b.n_equal = (int*)take(mi); b.status = (int*)take(mi); b.fresh = (int*)take(mi);
@@ -1028,7 +1029,7 @@ static int bdf_grid(const occm_system* sys, long long chunks) {
     } while (0)
 
 static int bdf_reduce_launch(occm_bdf* h, int nvals, const int* mask, cudaStream_t st) {
-    BDF_LAUNCH(bdf_reduce, h->M, 512, 0, h->d.partial, h->d.nchunk, nvals, h->d.norms, mask);
+    BDF_LAUNCH(bdf_reduce, dim3(h->M, nvals), 512, 0, h->d.partial, h->d.nchunk, nvals, h->d.norms, mask);
     return OCCM_OK;
 }
 
@@ -1039,7 +1040,7 @@ static int bdf_rhs(occm_bdf* h, const int* mask, const double* z, const double* 
 }
 
 template <int MODEL, int W>
-static int bdf_precond_launch_w(occm_bdf* h, const double* src, int from_col_j, double* dst, const int* mask, cudaStream_t st) {
+static int bdf_precond_launch_w(occm_bdf* h, const double* src, int from_col_j, double* dst, const int* mask, int keep_z, cudaStream_t st) {
     const occm_system* sys = h->sys;
     const size_t smem = sys->smem_tables;
     static OccmLaunchCache cache;
@@ -1049,7 +1050,7 @@ static int bdf_precond_launch_w(occm_bdf* h, const double* src, int from_col_j, 
     long long blocks = (groups + gpb - 1) / gpb;
     const long long cap = (long long)sys->sm_count * 16;
     if (blocks > cap) blocks = cap;
-    BDF_LAUNCH((bdf_precond_warp<MODEL, W>), (int)blocks, 128, smem, sys->dev, h->d, src, from_col_j, dst, mask);
+    BDF_LAUNCH((bdf_precond_warp<MODEL, W>), (int)blocks, 128, smem, sys->dev, h->d, src, from_col_j, dst, mask, keep_z);
     return OCCM_OK;
 }
 
@@ -1074,14 +1075,14 @@ static int bdf_factor_launch(occm_bdf* h, cudaStream_t st) {
 }
 
 template <int MODEL, int W>
-static int bdf_apply_launch_w(occm_bdf* h, const double* src, int from_col_j, double* dst, const int* mask, cudaStream_t st) {
+static int bdf_apply_launch_w(occm_bdf* h, const double* src, int from_col_j, double* dst, const int* mask, int keep_z, cudaStream_t st) {
     const occm_system* sys = h->sys;
     const long long groups = (long long)h->M * (MODEL == 0 ? sys->dev.n_points : sys->dev.n_models);
     const int gpb = 128 / W;
     long long blocks = (groups + gpb - 1) / gpb;
     const long long cap = (long long)sys->sm_count * 16;
     if (blocks > cap) blocks = cap;
-    BDF_LAUNCH((bdf_precond_apply<MODEL, W>), (int)blocks, 128, 0, h->d, src, from_col_j, dst, mask);
+    BDF_LAUNCH((bdf_precond_apply<MODEL, W>), (int)blocks, 128, 0, h->d, src, from_col_j, dst, mask, keep_z);
     return OCCM_OK;
 }
 
@@ -1091,17 +1092,17 @@ static int bdf_precond_launch(occm_bdf* h, const double* src, int from_col_j, do
     int rc;
     if (h->d.store) {
         if (sys->dev.model == OCCM_MODEL_CSTR)
-            rc = S <= 4 ? bdf_apply_launch_w<0, 4>(h, src, from_col_j, dst, mask, st) : S <= 8 ? bdf_apply_launch_w<0, 8>(h, src, from_col_j, dst, mask, st)
-                                                                                              : S <= 16 ? bdf_apply_launch_w<0, 16>(h, src, from_col_j, dst, mask, st) : bdf_apply_launch_w<0, 32>(h, src, from_col_j, dst, mask, st);
+            rc = S <= 4 ? bdf_apply_launch_w<0, 4>(h, src, from_col_j, dst, mask, from_col_j, st) : S <= 8 ? bdf_apply_launch_w<0, 8>(h, src, from_col_j, dst, mask, from_col_j, st)
+                                                                                              : S <= 16 ? bdf_apply_launch_w<0, 16>(h, src, from_col_j, dst, mask, from_col_j, st) : bdf_apply_launch_w<0, 32>(h, src, from_col_j, dst, mask, from_col_j, st);
         else
-            rc = S <= 4 ? bdf_apply_launch_w<1, 4>(h, src, from_col_j, dst, mask, st) : S <= 8 ? bdf_apply_launch_w<1, 8>(h, src, from_col_j, dst, mask, st)
-                                                                                              : S <= 16 ? bdf_apply_launch_w<1, 16>(h, src, from_col_j, dst, mask, st) : bdf_apply_launch_w<1, 32>(h, src, from_col_j, dst, mask, st);
+            rc = S <= 4 ? bdf_apply_launch_w<1, 4>(h, src, from_col_j, dst, mask, from_col_j, st) : S <= 8 ? bdf_apply_launch_w<1, 8>(h, src, from_col_j, dst, mask, from_col_j, st)
+                                                                                              : S <= 16 ? bdf_apply_launch_w<1, 16>(h, src, from_col_j, dst, mask, from_col_j, st) : bdf_apply_launch_w<1, 32>(h, src, from_col_j, dst, mask, from_col_j, st);
     } else if (sys->dev.model == OCCM_MODEL_CSTR)
-        rc = S <= 4 ? bdf_precond_launch_w<0, 4>(h, src, from_col_j, dst, mask, st) : S <= 8 ? bdf_precond_launch_w<0, 8>(h, src, from_col_j, dst, mask, st)
-                                                                                           : S <= 16 ? bdf_precond_launch_w<0, 16>(h, src, from_col_j, dst, mask, st) : bdf_precond_launch_w<0, 32>(h, src, from_col_j, dst, mask, st);
+        rc = S <= 4 ? bdf_precond_launch_w<0, 4>(h, src, from_col_j, dst, mask, from_col_j, st) : S <= 8 ? bdf_precond_launch_w<0, 8>(h, src, from_col_j, dst, mask, from_col_j, st)
+                                                                                           : S <= 16 ? bdf_precond_launch_w<0, 16>(h, src, from_col_j, dst, mask, from_col_j, st) : bdf_precond_launch_w<0, 32>(h, src, from_col_j, dst, mask, from_col_j, st);
     else
-        rc = S <= 4 ? bdf_precond_launch_w<1, 4>(h, src, from_col_j, dst, mask, st) : S <= 8 ? bdf_precond_launch_w<1, 8>(h, src, from_col_j, dst, mask, st)
-                                                                                           : S <= 16 ? bdf_precond_launch_w<1, 16>(h, src, from_col_j, dst, mask, st) : bdf_precond_launch_w<1, 32>(h, src, from_col_j, dst, mask, st);
+        rc = S <= 4 ? bdf_precond_launch_w<1, 4>(h, src, from_col_j, dst, mask, from_col_j, st) : S <= 8 ? bdf_precond_launch_w<1, 8>(h, src, from_col_j, dst, mask, from_col_j, st)
+                                                                                           : S <= 16 ? bdf_precond_launch_w<1, 16>(h, src, from_col_j, dst, mask, from_col_j, st) : bdf_precond_launch_w<1, 32>(h, src, from_col_j, dst, mask, from_col_j, st);
     if (rc) return rc;
     if (want_norm) {
         const int gv = bdf_grid(sys, (long long)h->M * h->d.nchunk);
@@ -1224,8 +1225,7 @@ static int bdf_attempt(occm_bdf* h, cudaStream_t st) {
             if ((rc = bdf_read_counters(h, st))) return rc;
             gm_active = h->h_counters[2];
         }
-        BDF_LAUNCH(bdf_lincomb_V, gv, 256, 0, b);                                               // u~ = sum y_k v_k
-        if ((rc = bdf_precond_launch(h, b.w, 0, b.z, b.newton_active, 0, st))) return rc;      // dy = M^-1 S u~
+        BDF_LAUNCH(bdf_lincomb_V, gv, 256, 0, b);                                               // dy = sum y_k z_k
         BDF_LAUNCH(bdf_newton_update, gv, 256, 0, b);
         if ((rc = bdf_reduce_launch(h, 1, b.newton_active, st))) return rc;
         OCCM_CUDA_CHECK(cudaMemsetAsync(b.counters + 1, 0, sizeof(int), st));

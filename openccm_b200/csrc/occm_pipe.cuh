@@ -300,12 +300,8 @@ occm_pipe_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
         for (int i = 0; i < E; ++i) {
             const int pli = i * g.psub + pl;
             pt[i] = (lane_on && p0 + pli < n_points) ? p0 + pli : -1;
-            own[i] = make_double2(0.0, 0.0);
-            if (pt[i] >= 0) {
-                own[i] = occm_pipe_state<STAGE, V>(slot_sa, eo + i * sub_bytes, cc.h);
-                occm_sts2_at<0u, V>(row_sa + i * tile_sub + 8u * sp, own[i]);
-            }
         }
+        // (the gathers first: their latency then also covers the tile store and the warp barrier)
 #pragma unroll
         for (int i = 0; i < E; ++i) {
 #pragma unroll
@@ -322,6 +318,14 @@ occm_pipe_body(const OccmSysDev& sys, const OccmMemDev& mem, const OccmRkDev& rk
                 const unsigned rel = (unsigned)(src - p0);
                 if (rel < (unsigned)npts) gv[i][k] = occm_pipe_state<STAGE, V>(slot_sa, 8u * (rel * (unsigned)S + (unsigned)sp), cc.h);
                 else gv[i][k] = occm_fast_in<STAGE, V>(ga, gb, cc.h, src * S + sp);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            own[i] = make_double2(0.0, 0.0);
+            if (pt[i] >= 0) {
+                own[i] = occm_pipe_state<STAGE, V>(slot_sa, eo + i * sub_bytes, cc.h);
+                occm_sts2_at<0u, V>(row_sa + i * tile_sub + 8u * sp, own[i]);
             }
         }
         __syncwarp();                            // the staged rows of a warp's points are written and read by that warp only

@@ -154,3 +154,54 @@ def test_c5_mid_bdf_vs_tight_scipy(tmp_path):
     e_scipy = units(g['scipy_1e8']).max()
     print(f'C5 mid through the user policy (1e-8 / 1e-12): device {e_user:.2f}, scipy BDF {e_scipy:.2f} band units; {res.n_accepted[0]} steps')
     assert e_user <= 2.0, (e_user, e_scipy)
+
+
+@pytest.mark.parametrize('n_species,n_cstr,members', [(3, 20_000, 8), (5, 12_001, 4), (11, 10_000, 3)])
+def test_odd_species_counts_at_scale(n_species, n_cstr, members, tmp_path):
+    """Odd species counts (one species per thread, 64-bit accesses) at sizes where the error partials of the advisor's round-1
+    finding overflowed (S odd, N >= 1e4, several members): RHS against the oracle's sparse restatement, then a complete RK45
+    ensemble solve through every kernel form — pipelined, register-prefetching and generic — which must agree with each other
+    and spend scipy's number of RHS calls on the unscaled member.  (12 001 x 5 = odd ndof: rows not 16-byte aligned, the
+    pipelined kernels must decline and the 64-bit fast kernels take over.)"""
+    import os
+    import scipy.integrate
+    import torch
+    from oracle import openccm_oracle as O
+    from openccm_b200 import synthetic as syn
+    from openccm_b200.device import DeviceSystem, MemberParams
+    from openccm_b200.system_solvers.export import export_system
+    from openccm_b200.workloads import cstr_ensemble_workload
+    model, net, cp, cmesh = cstr_ensemble_workload(n_cstr=n_cstr, n_species=n_species, n_reactions=max(2, n_species // 2), t_end=2.0,
+                                                   n_out=5, workdir=str(tmp_path))
+    host = export_system(model, net, cp, cmesh)
+    ora = O.build_cstr(net.to_model_network(), cp, cmesh, sparse=True)
+    ks, qs, ics = syn.ensemble_sweeps(members, host.tables.n_rxn)
+    ks[0] = 1.0; qs[0] = 1.0; ics[0] = 1.0                                   # member 0 is the plain problem
+    te = np.linspace(0.0, 2.0, 5)
+    results = {}
+    for mode, env in (('pipe', {}), ('fast', {'OCCM_B200_NO_PIPE': '1'}), ('generic', {'OCCM_B200_NO_FAST': '1'})):
+        for k in ('OCCM_B200_NO_PIPE', 'OCCM_B200_NO_FAST'):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        try:
+            dev = DeviceSystem(host)
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+        mem = MemberParams(members, torch.as_tensor(ks, device='cuda'), torch.as_tensor(qs, device='cuda'), None)
+        c0 = torch.as_tensor(host.to_device_layout(host.c0.reshape(-1)), device='cuda')
+        y0 = (torch.as_tensor(ics, device='cuda')[:, None] * c0[None, :]).contiguous()
+        dy = dev.rhs(y0, 0.1, mem).cpu().numpy()
+        res = dev.rk45(y0, (0.0, 2.0), rtol=1e-6, atol=1e-10, first_step=1e-4, t_eval=te, members=mem)
+        assert np.all(res.status == 1)
+        results[mode] = (dy, res.y.cpu().numpy(), res.nfev.copy())
+    ref0 = ora.fun(0.1, ora.y0)
+    np.testing.assert_allclose(host.to_reference_layout(results['pipe'][0][0]), ref0, rtol=1e-12, atol=1e-12)
+    for mode in ('fast', 'generic'):
+        np.testing.assert_allclose(results[mode][0], results['pipe'][0], rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(results[mode][1], results['pipe'][1], rtol=1e-9, atol=1e-12)
+        np.testing.assert_array_equal(results[mode][2], results['pipe'][2])
+    sol = scipy.integrate.solve_ivp(ora.fun, (0.0, 2.0), ora.y0, method='RK45', rtol=1e-6, atol=1e-10, first_step=1e-4, t_eval=te)
+    assert abs(int(results['pipe'][2][0]) - sol.nfev) <= 12
+    got = results['pipe'][1][0].reshape(len(te), host.n_points, host.S).transpose(2, 1, 0).reshape(host.ndof, -1)
+    assert np.all(np.abs(got - sol.y) <= 1e-10 + 1e-6 * np.abs(sol.y))

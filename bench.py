@@ -449,6 +449,7 @@ def main():
     te = np.asarray(solver.t_eval)
     dev = solver.upload()
     device = dev.dev
+    dev_specialized = bool(dev.specialized)
 
     # ---- device-resident inputs for `value`
     mem = MemberParams(M_loc, torch.as_tensor(ks, device=device), torch.as_tensor(qs, device=device), None)
@@ -591,7 +592,8 @@ def main():
         e1.record(); torch.cuda.synchronize()
         ms_r = e0.elapsed_time(e1) / 10
         alg_r = M_loc * ndof * 16 + csr_bytes
-        plain = {"ms_per_launch": ms_r, "evals_per_s": M_loc * ndof / (ms_r * 1e-3), "achieved_gbs": alg_r / (ms_r * 1e-3) / 1e9,
+        plain = {"kernel": "occm_spec_stage0 (mechanism-specialised, thread per point)" if dev.specialized else "occm_pipe<CSTR, stage 0, K>",
+                 "ms_per_launch": ms_r, "evals_per_s": M_loc * ndof / (ms_r * 1e-3), "achieved_gbs": alg_r / (ms_r * 1e-3) / 1e9,
                  "frac": alg_r / (ms_r * 1e-3) / 1e9 / peak}
         del dy
 
@@ -652,7 +654,10 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "members_per_gpu": M_loc, "members_total": M_glob, "n_cstr": N, "n_species": S,
                            "l2": f"inputs larger than L2: {11 * M_loc * ndof * 8 / 2**30:.1f} GiB of state vectors per GPU",
-                           "parallelism": f"members dealt to {world_size} GPU(s) by a stiffness estimate, no data-path collective"},
+                           "parallelism": f"members dealt to {world_size} GPU(s) by a stiffness estimate, no data-path collective",
+                           "kernels": ("mechanism-specialised image for the plain RHS and stages 2, 7 (occm_spec_stage*), TMA-pipelined "
+                                       "table-driven kernels for stages 3-6 (occm_pipe)") if dev_specialized else
+                                      "TMA-pipelined table-driven kernels (occm_pipe)"},
                 "ode_solves_per_s": solves_per_s, "rhs_evals_total": evals, "step_ms": step_ms,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "solves_per_s": M_glob * args.steps / float(t_e.item()),

@@ -126,6 +126,19 @@ int occm_system_destroy(occm_system* sys);
 int64_t occm_system_ndof(const occm_system* sys);
 
 /*
+ * Mechanism-specialised kernels (optional).  The reference compiles the reactions file into one Python closure per run
+ * (openccm/system_solvers/helper_functions.py:52-184, generate_reaction_system: source text -> exec); the device analogue is a
+ * kernel image in which the stoichiometric terms are straight-line code: openccm_b200/specialize.py generates it from the parsed
+ * mechanism and compiles openccm_b200/csrc/spec/occm_spec.cu to a cubin (nvcc, sm_100a).  `image` is that cubin (host memory,
+ * copied by the driver).  The image must match the system (species count, ELL width, hash of the mechanism tables, ABI of
+ * csrc/occm_spec.h), else OCCM_ERR_INVALID; CSTR networks with polynomial rate laws only, else OCCM_ERR_UNSUPPORTED.  After a
+ * successful load the plain RHS and Dormand-Prince stages 2 and 7 run the image's kernels; without one the table-driven kernels
+ * run.  Results are bit-identical either way.
+ */
+int occm_system_load_specialized(occm_system* sys, const void* image, size_t bytes);
+int occm_system_is_specialized(const occm_system* sys);
+
+/*
  * Fused right-hand side: dy[m] = ddt(t[m], y[m]) for every member in one launch.
  * Replaces `cstr_system.ddt` (cstr_system.py:161-203) / `pfr_system.ddt` (pfr_system.py:218-316) including the
  * generated `_reactions` (reactions.py:395-467) and `_boundary_conditions` (boundary_and_initial_conditions.py:211-245).

@@ -55,6 +55,8 @@ SIGNATURES = {
     'occm_system_create': (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(SystemDesc)]),
     'occm_system_destroy': (C.c_int, [C.c_void_p]),
     'occm_system_ndof': (C.c_int64, [C.c_void_p]),
+    'occm_system_load_specialized': (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
+    'occm_system_is_specialized': (C.c_int, [C.c_void_p]),
     'occm_rhs': (C.c_int, [C.c_void_p, C.POINTER(Members), C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     'occm_rk45_workspace_bytes': (C.c_size_t, [C.c_void_p, C.c_int32]),
     'occm_rk45_init': (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(Members), C.POINTER(Rk45Problem),

@@ -16,6 +16,11 @@ struct occm_system {
     size_t smem_tables;   // bytes of the staged table blob (8-byte aligned)
     int device;           // CUDA device the handle was created on (launch state is kept per device)
     int use_pipe;         // 0: no TMA-pipelined kernels (OCCM_B200_NO_PIPE=1)
+    int use_row;          // 0: a loaded mechanism-specialised image is ignored (OCCM_B200_NO_SPEC=1)
+    struct OccmSpec* spec; // mechanism-specialised kernel image (occm_system_load_specialized), or NULL
+    int spec_smem_kb;     // shared memory per SM the specialised kernels plan their rings for (OCCM_B200_SPEC_SMEM_KB, default 196)
+    int any_prog;         // the mechanism has non-polynomial terms (byte-code programs)
+    int n_term;           // stoichiometric terms of the mechanism (table header)
     int use_small;        // 0: no persistent one-CTA-per-member RK45 for networks that fit in shared memory (OCCM_B200_NO_SMALL=1)
     int pipe_depth;       // cap on the ring depth of the pipelined kernels (OCCM_B200_PIPE_DEPTH, 0 = as deep as shared memory allows)
     int smem_per_block, smem_per_sm;
@@ -43,6 +48,11 @@ struct occm_system;
 struct OccmMemDev;
 int occm_launch_rhs(const occm_system* sys, const OccmMemDev& mem, const double* t_dev, double t_scalar, const double* y,
                     double* dy, cudaStream_t st);
+struct OccmRkDev;
+// specialised image (occm_spec.h): launch of stage 0 / 2 / 7 (returns 1 when it does not apply); unload at system destruction
+int occm_spec_launch(const occm_system* sys, int stage, const OccmMemDev& mem, const OccmRkDev& rk, const double* y_in,
+                     double* dy_out, cudaStream_t st, int* err_stride_out, int* main_partials_out);
+void occm_spec_unload(occm_system* s);
 
 #define OCCM_CUDA_CHECK(expr)                                                                      \
     do {                                                                                           \

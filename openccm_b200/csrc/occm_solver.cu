@@ -79,6 +79,205 @@ int occm_kernel_prepare(OccmLaunchCache* c, const void* kernel, int device, int 
     return OCCM_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ mechanism-specialised images
+// A cubin compiled per mechanism (spec/occm_spec.cu) is loaded with the driver API; its entry points are resolved through the
+// runtime (cudaGetDriverEntryPoint), so liboccm_b200.so carries no link-time dependency on libcuda.
+#include <cuda.h>
+#include "occm_spec.h"
+#include "occm_rk.cuh"
+struct OccmDrv {
+    CUresult (*moduleLoadData)(CUmodule*, const void*);
+    CUresult (*moduleUnload)(CUmodule);
+    CUresult (*moduleGetFunction)(CUfunction*, CUmodule, const char*);
+    CUresult (*moduleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*);
+    CUresult (*funcSetAttribute)(CUfunction, CUfunction_attribute, int);
+    CUresult (*occupancy)(int*, CUfunction, int, size_t);
+    CUresult (*launchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**);
+    CUresult (*getErrorString)(CUresult, const char**);
+    int state;      // 0 = not tried, 1 = resolved, -1 = unavailable
+};
+static OccmDrv g_drv;
+static int occm_drv_load(void) {
+    std::lock_guard<std::mutex> lock(g_launch_mutex);
+    if (g_drv.state) return g_drv.state > 0 ? OCCM_OK : OCCM_ERR_CUDA;
+    struct { const char* name; void** fn; } want[] = {
+        {"cuModuleLoadData", (void**)&g_drv.moduleLoadData}, {"cuModuleUnload", (void**)&g_drv.moduleUnload},
+        {"cuModuleGetFunction", (void**)&g_drv.moduleGetFunction}, {"cuModuleGetGlobal", (void**)&g_drv.moduleGetGlobal},
+        {"cuFuncSetAttribute", (void**)&g_drv.funcSetAttribute},
+        {"cuOccupancyMaxActiveBlocksPerMultiprocessor", (void**)&g_drv.occupancy},
+        {"cuLaunchKernel", (void**)&g_drv.launchKernel}, {"cuGetErrorString", (void**)&g_drv.getErrorString}};
+    for (auto& w : want) {
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint(w.name, w.fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !*w.fn) {
+            cudaGetLastError();
+            g_drv.state = -1;
+            occm_set_error("driver entry point %s is not available", w.name);
+            return OCCM_ERR_CUDA;
+        }
+    }
+    g_drv.state = 1;
+    return OCCM_OK;
+}
+static const char* occm_drv_str(CUresult r) { const char* s = nullptr; if (g_drv.getErrorString) g_drv.getErrorString(r, &s); return s ? s : "unknown driver error"; }
+#define OCCM_DRV_CHECK(expr)                                                                       \
+    do {                                                                                           \
+        CUresult _r = (expr);                                                                      \
+        if (_r != CUDA_SUCCESS) { occm_set_error("%s failed: %s", #expr, occm_drv_str(_r)); return OCCM_ERR_CUDA; } \
+    } while (0)
+
+struct OccmSpec {
+    CUmodule mod;
+    CUfunction fn[8];                  // by stage (0, 2, 7)
+    int S, K, n_term;
+    int warps[8], ctas[8];             // by stage
+    size_t smem_limit[8], occ_smem[8]; int occ[8];
+};
+
+void occm_spec_unload(occm_system* s) {
+    if (!s->spec) return;
+    if (g_drv.state > 0 && s->spec->mod) g_drv.moduleUnload(s->spec->mod);
+    free(s->spec);
+    s->spec = nullptr;
+    s->spec_smem_kb = getenv("OCCM_B200_SPEC_SMEM_KB") ? atoi(getenv("OCCM_B200_SPEC_SMEM_KB")) : 196;   // planning cap; the carve-out is set to what the planned CTAs use
+    if (s->spec_smem_kb < 32) s->spec_smem_kb = 32;
+}
+
+extern "C" int occm_system_load_specialized(occm_system* s, const void* image, size_t bytes) {
+    if (!s || !image || bytes < 64) { occm_set_error("occm_system_load_specialized: null system or image"); return OCCM_ERR_INVALID; }
+    const OccmSysDev& d = s->dev;
+    if (d.model != OCCM_MODEL_CSTR || s->any_prog || !s->desc.ell_packed || d.ell_k < 1) {
+        occm_set_error("specialised kernels cover CSTR networks with polynomial rate laws and a packed ELL operator");
+        return OCCM_ERR_UNSUPPORTED;
+    }
+    OCCM_CUDA_CHECK(cudaSetDevice(s->device));
+    OCCM_CUDA_CHECK(cudaFree(0));                                      // the primary context exists and is current
+    if (int rc = occm_drv_load()) return rc;
+    OccmSpec* sp = (OccmSpec*)calloc(1, sizeof(OccmSpec));
+    if (!sp) { occm_set_error("out of host memory"); return OCCM_ERR_INVALID; }
+    CUresult r = g_drv.moduleLoadData(&sp->mod, image);
+    if (r != CUDA_SUCCESS) { occm_set_error("cuModuleLoadData failed: %s (image not built for this GPU?)", occm_drv_str(r)); free(sp); return OCCM_ERR_CUDA; }
+    auto fail = [&](int code) { g_drv.moduleUnload(sp->mod); free(sp); return code; };
+    CUdeviceptr info_p = 0; size_t info_n = 0;
+    unsigned long long info[OCCM_SI_WORDS] = {0};
+    if (g_drv.moduleGetGlobal(&info_p, &info_n, sp->mod, "occm_spec_info") != CUDA_SUCCESS || info_n != sizeof(info) ||
+        cudaMemcpy(info, (const void*)info_p, sizeof(info), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaGetLastError();
+        occm_set_error("image has no occm_spec_info of %zu bytes", sizeof(info));
+        return fail(OCCM_ERR_INVALID);
+    }
+    // the image must have been generated from THIS mechanism: hash of the packed tables
+    unsigned char* blob = (unsigned char*)malloc((size_t)d.tables_bytes);
+    if (!blob || cudaMemcpy(blob, d.tables, (size_t)d.tables_bytes, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaGetLastError(); free(blob);
+        occm_set_error("could not read the mechanism tables back");
+        return fail(OCCM_ERR_CUDA);
+    }
+    const unsigned long long hash = occm_spec_hash(blob, (size_t)d.tables_bytes);
+    free(blob);
+    if (info[OCCM_SI_ABI] != OCCM_SPEC_ABI || (int)info[OCCM_SI_S] != d.S || (int)info[OCCM_SI_K] != d.ell_k ||
+        (int)info[OCCM_SI_NTERM] != s->n_term || info[OCCM_SI_HASH] != hash) {
+        occm_set_error("image does not match the system: abi %llu (library %d), S %llu (%d), K %llu (%d), terms %llu (%d), table hash %016llx (%016llx)",
+                       info[OCCM_SI_ABI], OCCM_SPEC_ABI, info[OCCM_SI_S], d.S, info[OCCM_SI_K], d.ell_k, info[OCCM_SI_NTERM], s->n_term,
+                       info[OCCM_SI_HASH], hash);
+        return fail(OCCM_ERR_INVALID);
+    }
+    sp->S = d.S; sp->K = d.ell_k; sp->n_term = s->n_term;
+    const int stages[3] = {0, 2, 7};
+    const int iw[3] = {OCCM_SI_W0, OCCM_SI_W2, OCCM_SI_W7}, ic[3] = {OCCM_SI_C0, OCCM_SI_C2, OCCM_SI_C7};
+    for (int i = 0; i < 3; ++i) {
+        const int st = stages[i];
+        sp->warps[st] = (int)info[iw[i]]; sp->ctas[st] = (int)info[ic[i]];
+        if (sp->warps[st] < 1 || sp->warps[st] > 31 || sp->ctas[st] < 1 || sp->ctas[st] > 16) {
+            occm_set_error("image reports %d warps, %d CTAs per SM for stage %d", sp->warps[st], sp->ctas[st], st);
+            return fail(OCCM_ERR_INVALID);
+        }
+        char name[32];
+        snprintf(name, sizeof(name), "occm_spec_stage%d", st);
+        if (g_drv.moduleGetFunction(&sp->fn[st], sp->mod, name) != CUDA_SUCCESS) { occm_set_error("image has no kernel %s", name); return fail(OCCM_ERR_INVALID); }
+    }
+    occm_spec_unload(s);
+    s->spec = sp;
+    return OCCM_OK;
+}
+
+extern "C" int occm_system_is_specialized(const occm_system* s) { return s && s->spec ? 1 : 0; }
+
+// One launch of a specialised stage kernel (stages 0, 2, 7).  Returns 1 when the configuration does not fit it.
+int occm_spec_launch(const occm_system* sys, int stage, const OccmMemDev& mem, const OccmRkDev& rk, const double* y_in,
+                     double* dy_out, cudaStream_t st, int* err_stride_out, int* main_partials_out) {
+    OccmSpec* sp = sys->spec;
+    const int S = sp->S, K = sp->K, W = sp->warps[stage], pts = 32 * W;
+    const int NS = stage == 0 ? 1 : stage == 2 ? 2 : 3, NOUT = stage == 2 ? 2 : 1;
+    if (stage == 0 && ((uintptr_t)y_in & 15 || (uintptr_t)dy_out & 15)) return 1;
+    OccmRowGeom g;
+    g.cpm = (int)((sys->dev.n_points + pts - 1) / pts);
+    g.stream_bytes = pts * S * 8;
+    g.slot_bytes = (NS * g.stream_bytes + K * pts * 16 + 127) & ~127;
+    size_t o = 0;
+    g.coef_off = 0;
+    o += (size_t)W * sp->n_term * 8;
+    o = (o + 15) & ~(size_t)15;
+    g.bar_off = (int)o;
+    o += 16 * OCCM_ROW_MAX_DEPTH;
+    o = (o + 127) & ~(size_t)127;
+    g.out_off = (int)o;
+    o += (size_t)W * NOUT * 32 * S * 8;
+    o = (o + 127) & ~(size_t)127;
+    g.ring_off = (int)o;
+    const size_t smem_cfg = (size_t)sys->spec_smem_kb * 1024;
+    const size_t smem_sm = (size_t)sys->smem_per_sm < smem_cfg ? (size_t)sys->smem_per_sm : smem_cfg;
+    const size_t cap = smem_sm / sp->ctas[stage] - 1024;
+    if (cap < o + 2 * (size_t)g.slot_bytes || o + 2 * (size_t)g.slot_bytes > (size_t)sys->smem_per_block) return 1;
+    int depth = (int)((cap - o) / (size_t)g.slot_bytes);
+    const int want = sys->pipe_depth > 0 ? sys->pipe_depth : 6;
+    if (depth > want) depth = want;
+    if (depth > OCCM_ROW_MAX_DEPTH) depth = OCCM_ROW_MAX_DEPTH;
+    if (depth < 2) depth = 2;
+    g.depth = depth;
+    const size_t smem = o + (size_t)depth * g.slot_bytes;
+    const long long chunks = (long long)mem.M * g.cpm;
+    if (chunks >= (1ll << 31)) { occm_set_error("too many chunks (%lld) for one launch", chunks); return OCCM_ERR_INVALID; }
+    const int n_flagged = sys->desc.n_flagged;
+    const int tcf = OCCM_BLOCK / S;
+    const int nfix = n_flagged > 0 ? (n_flagged + tcf - 1) / tcf : 0;
+    g.err_stride = g.cpm * W + nfix;
+    if (stage == 7 && (size_t)g.err_stride > occm_err_capacity(sys)) {
+        occm_set_error("error partials per member (%d) exceed the carved capacity (%zu)", g.err_stride, occm_err_capacity(sys));
+        return OCCM_ERR_WORKSPACE;
+    }
+    int ctas_per_sm = 1;
+    {
+        std::lock_guard<std::mutex> lock(g_launch_mutex);
+        if (smem > 48 * 1024 && smem > sp->smem_limit[stage]) {
+            OCCM_DRV_CHECK(g_drv.funcSetAttribute(sp->fn[stage], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
+            sp->smem_limit[stage] = smem;
+        }
+        if (sp->occ[stage] == 0 || sp->occ_smem[stage] != smem) {
+            // Carve out exactly what the planned CTAs need: the rest of the 256 KB stays L1, which the row gathers live on (a
+            // row is five 16-byte loads of one lane; with the 28 KB of L1 the largest carve-out leaves, its line is evicted
+            // between them: measured 2x slower).
+            const size_t need = (size_t)sp->ctas[stage] * (smem + 1024);
+            int pct = (int)((need * 100 + (size_t)sys->smem_per_sm - 1) / (size_t)sys->smem_per_sm);
+            if (pct > 100) pct = 100;
+            OCCM_DRV_CHECK(g_drv.funcSetAttribute(sp->fn[stage], CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, pct));
+            int n = 0;
+            OCCM_DRV_CHECK(g_drv.occupancy(&n, sp->fn[stage], 32 * (W + 1), smem));
+            if (n > sp->ctas[stage]) n = sp->ctas[stage];               // more CTAs would need a larger carve-out than planned
+            sp->occ[stage] = n < 1 ? 1 : n; sp->occ_smem[stage] = smem;
+        }
+        ctas_per_sm = sp->occ[stage];
+    }
+    const int grid = occm_grid(sys, chunks, ctas_per_sm);
+    const void* ell = sys->desc.ell_packed;
+    void* args[] = {(void*)&sys->dev, (void*)&mem, (void*)&rk, (void*)&y_in, (void*)&dy_out, (void*)&ell, (void*)&g};
+    OCCM_DRV_CHECK(g_drv.launchKernel(sp->fn[stage], (unsigned)grid, 1, 1, (unsigned)(32 * (W + 1)), 1, 1, (unsigned)smem, (CUstream)st, args, nullptr));
+    occm_count_launch();
+    *err_stride_out = g.err_stride;
+    *main_partials_out = g.cpm * W;
+    return OCCM_OK;
+}
+
 extern "C" const char* occm_last_error(void) { return g_err; }
 extern "C" int occm_abi_version(void) { return OCCM_ABI_VERSION; }
 extern "C" int64_t occm_launch_count(void) { return g_launches.load(); }
@@ -120,6 +319,12 @@ extern "C" int occm_system_create(occm_system** out, const occm_system_desc* d) 
     v.point_flags = d->point_flags;
     s->use_fast = getenv("OCCM_B200_NO_FAST") ? 0 : 1;
     s->use_small = getenv("OCCM_B200_NO_SMALL") ? 0 : 1;        // tests / A-B: batched kernels also for networks that fit in shared memory
+    s->use_row = getenv("OCCM_B200_NO_SPEC") ? 0 : 1;           // tests / A-B: ignore a loaded mechanism-specialised image
+    s->spec = nullptr;
+    s->spec_smem_kb = getenv("OCCM_B200_SPEC_SMEM_KB") ? atoi(getenv("OCCM_B200_SPEC_SMEM_KB")) : 196;   // planning cap; the carve-out is set to what the planned CTAs use
+    if (s->spec_smem_kb < 32) s->spec_smem_kb = 32;
+    s->any_prog = hdr[OCCM_H_ANY_PROG];
+    s->n_term = hdr[OCCM_H_NTERM];
     s->use_pipe = getenv("OCCM_B200_NO_PIPE") ? 0 : 1;          // tests / A-B measurements: register-prefetching fast kernels instead
     s->pipe_depth = getenv("OCCM_B200_PIPE_DEPTH") ? atoi(getenv("OCCM_B200_PIPE_DEPTH")) : 0;
     s->force_wide = getenv("OCCM_B200_FORCE_WIDE") ? 1 : 0;      // tests: run the shared-memory term-list variant on any mechanism
@@ -155,46 +360,13 @@ extern "C" int occm_system_create(occm_system** out, const occm_system_desc* d) 
     return OCCM_OK;
 }
 
-extern "C" int occm_system_destroy(occm_system* s) { free(s); return OCCM_OK; }
+extern "C" int occm_system_destroy(occm_system* s) { if (s) occm_spec_unload(s); free(s); return OCCM_OK; }
 extern "C" int64_t occm_system_ndof(const occm_system* s) { return s ? s->dev.ndof : -1; }
 
 #endif  // !OCCM_STAGE_TU
 
 // ------------------------------------------------------------------------------------------------ RK45 data
-// Dormand-Prince coefficients exactly as scipy builds them (scipy/integrate/_ivp/rk.py:280-320, Python float
-// divisions == IEEE double divisions evaluated at compile time here).
-namespace dp {
-constexpr double C2 = 1.0 / 5, C3 = 3.0 / 10, C4 = 4.0 / 5, C5 = 8.0 / 9;
-constexpr double A21 = 1.0 / 5;
-constexpr double A31 = 3.0 / 40, A32 = 9.0 / 40;
-constexpr double A41 = 44.0 / 45, A42 = -56.0 / 15, A43 = 32.0 / 9;
-constexpr double A51 = 19372.0 / 6561, A52 = -25360.0 / 2187, A53 = 64448.0 / 6561, A54 = -212.0 / 729;
-constexpr double A61 = 9017.0 / 3168, A62 = -355.0 / 33, A63 = 46732.0 / 5247, A64 = 49.0 / 176, A65 = -5103.0 / 18656;
-constexpr double B1 = 35.0 / 384, B3 = 500.0 / 1113, B4 = 125.0 / 192, B5 = -2187.0 / 6784, B6 = 11.0 / 84;
-constexpr double E1 = -71.0 / 57600, E3 = 71.0 / 16695, E4 = -71.0 / 1920, E5 = 17253.0 / 339200, E6 = -22.0 / 525, E7 = 1.0 / 40;
-// dense output polynomial, rows = stages 1..7 (row 2 is zero), columns = powers x^1..x^4 (rk.py:321-335)
-constexpr double P11 = 1.0, P12 = -8048581381.0 / 2820520608, P13 = 8663915743.0 / 2820520608, P14 = -12715105075.0 / 11282082432;
-constexpr double P32 = 131558114200.0 / 32700410799, P33 = -68118460800.0 / 10900136933, P34 = 87487479700.0 / 32700410799;
-constexpr double P42 = -1754552775.0 / 470086768, P43 = 14199869525.0 / 1410260304, P44 = -10690763975.0 / 1880347072;
-constexpr double P52 = 127303824393.0 / 49829197408, P53 = -318862633887.0 / 49829197408, P54 = 701980252875.0 / 199316789632;
-constexpr double P62 = -282668133.0 / 205662961, P63 = 2019193451.0 / 616988883, P64 = -1453857185.0 / 822651844;
-constexpr double P72 = 40617522.0 / 29380423, P73 = -110615467.0 / 29380423, P74 = 69997945.0 / 29380423;
-constexpr double SAFETY = 0.9, MIN_FACTOR = 0.2, MAX_FACTOR = 10.0, ERROR_EXPONENT = -1.0 / 5;
-}  // namespace dp
-
-struct OccmRkDev {
-    double* Y[2];     // state ping-pong; Y[parity[m]] is the current state of member m
-    double* KF[2];    // K1 / K7 ping-pong (first-same-as-last)
-    double* K2; double* K3; double* K4; double* K5; double* K6;
-    double* YS[2];    // materialised stage states
-    double* t; double* h; double* h_abs; double* t_new; double* t_old;
-    int* parity; int* status; int* rejected; int* accepted_now; int* out_lo; int* out_hi; int* n_rows;
-    long long* n_acc; long long* n_rej; long long* nfev;
-    double* err_partial;  // [M][chunks_per_member]
-    int* n_running;
-    double rtol, atol, t_bound;
-    long long max_steps;
-};
+#include "occm_rk.cuh"
 
 struct occm_rk45 {
     const occm_system* sys;
@@ -820,6 +992,23 @@ static int occm_launch_pipe(const occm_system* sys, const OccmMemDev& mem, const
     return OCCM_OK;
 }
 
+// Mechanism-specialised kernels of the light stages (occm_spec.h; image loaded with occm_system_load_specialized), then the
+// generic fixup of the flagged rows.  Returns 1 when there is no image or it does not apply.
+template <int STAGE>
+static int occm_launch_spec(const occm_system* sys, const OccmMemDev& mem, const OccmRkDev& rk, const double* t_dev,
+                            double t_scalar, const double* y_in, double* dy_out, cudaStream_t st, int* cpm_out) {
+    if constexpr (STAGE == 0 || STAGE == 2 || STAGE == 7) {
+        if (!sys->spec || !sys->use_row) return 1;
+        int err_stride = 0, main_partials = 0;
+        const int rc = occm_spec_launch(sys, STAGE, mem, rk, y_in, dy_out, st, &err_stride, &main_partials);
+        if (rc != OCCM_OK) return rc;
+        if (int rf = occm_launch_fixup<0, STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, err_stride, main_partials)) return rf;
+        if (cpm_out) *cpm_out = err_stride;
+        return OCCM_OK;
+    }
+    return 1;
+}
+
 // the pipelined kernel when it applies, else the register-prefetching one
 template <int MODEL, int STAGE, int K, int WIDE, int V>
 static int occm_launch_both(const occm_system* sys, const OccmMemDev& mem, const OccmRkDev& rk, const double* t_dev,
@@ -848,6 +1037,10 @@ int occm_launch_stage(const occm_system* sys, const OccmMemDev& mem, const OccmR
     if (fast && d.model == OCCM_MODEL_PFR && d.ell_k == 1 && sys->desc.n_flagged >= d.n_models)
         return wide ? OCCM_FAST_CALL_V(1, 1, 1) : OCCM_FAST_CALL_V(1, 1, 0);
     if (fast && d.model == OCCM_MODEL_CSTR) {
+        {
+            const int rc = occm_launch_spec<STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
+            if (rc <= 0) return rc;
+        }
         if (wide) switch (d.ell_k) {
             case 1: return OCCM_FAST_CALL_V(0, 1, 1);
             case 2: return OCCM_FAST_CALL_V(0, 2, 1);

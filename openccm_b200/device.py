@@ -98,7 +98,9 @@ class Rk45Result:
 
 
 class DeviceSystem:
-    def __init__(self, host: HostSystem):
+    def __init__(self, host: HostSystem, specialize: Optional[str] = None):
+        """specialize: 'auto' | 'on' | 'off' — mechanism-specialised kernel image (openccm_b200/specialize.py; default: the
+        OCCM_B200_SPECIALIZE environment variable, else 'auto')."""
         self.lib = _lib.load()
         self.dev = _require_cuda()
         self.host = host
@@ -111,6 +113,7 @@ class DeviceSystem:
         self.a = f64(host.a)
         self.pulse_ptr, self.pulse_fn, self.pulse_w = i32(host.pulse_ptr), i32(host.pulse_fn), f64(host.pulse_w)
         blob = host.tables.pack()
+        self.tables_blob = blob
         self.tables = torch.as_tensor(blob, device=self.dev)
         self.fields = f64(host.fields)
         self.n_rxn = host.tables.n_rxn
@@ -148,6 +151,9 @@ class DeviceSystem:
         _lib.check(self.lib.occm_system_create(C.byref(h), C.byref(desc)))
         self.handle = h
         self.ndof = host.ndof
+        self.spec_image = None
+        from .specialize import specialize as _specialize
+        self.specialized = _specialize(self, specialize)
 
     def __del__(self):
         try:

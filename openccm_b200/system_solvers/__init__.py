@@ -89,7 +89,7 @@ def solve_system(model: str, model_network, config_parser, cmesh, *, return_info
     out = (c, ts, dict(host.inlet_map), dict(host.outlet_map))
     if return_info:
         return out + (dict(status=status, message=message, nfev=int(res.nfev[0]), n_accepted=int(res.n_accepted[0]),
-                           n_rejected=int(res.n_rejected[0]), switched_at=switched),)
+                           n_rejected=int(res.n_rejected[0]), switched_at=switched, specialized=bool(dev.specialized)),)
     return out
 
 

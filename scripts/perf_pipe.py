@@ -35,8 +35,14 @@ csr = 12 * nnz + 4 * (N + 1)
 BYTES = {2: 32, 3: 48, 4: 56, 5: 64, 6: 72, 7: 32}
 
 
-def make(pipe: bool, depth: int = 0) -> DeviceSystem:
+ROW_AB = len(sys.argv) > 4 and sys.argv[4] == 'row'      # A/B of the mechanism-specialised light-stage kernels against the pipe kernels
+
+
+def make(pipe: bool, depth: int = 0, row: bool = True) -> DeviceSystem:
     os.environ.pop('OCCM_B200_NO_PIPE', None)
+    os.environ.pop('OCCM_B200_SPECIALIZE', None)
+    if not row:
+        os.environ['OCCM_B200_SPECIALIZE'] = '0'
     os.environ.pop('OCCM_B200_PIPE_DEPTH', None)
     if not pipe:
         os.environ['OCCM_B200_NO_PIPE'] = '1'
@@ -77,11 +83,11 @@ def measure(dev: DeviceSystem, label: str):
     return dy, res
 
 
-dev_f = make(False)
-dy_f, res_f = measure(dev_f, 'fast')
+dev_f = make(True, 0, False) if ROW_AB else make(False)
+dy_f, res_f = measure(dev_f, 'pipe, table-driven' if ROW_AB else 'fast')
 for d in DEPTHS:
     dev_p = make(True, d)
-    dy_p, res_p = measure(dev_p, f'pipe depth<={d or "max"}')
+    dy_p, res_p = measure(dev_p, ('specialised' if dev_p.specialized else 'pipe') + f' depth<={d or "max"}')
     print('   RHS bitwise equal:', bool(torch.equal(dy_f, dy_p)), ' max |diff|', float((dy_f - dy_p).abs().max()),
           ' solve outputs max |diff|:', float((res_f.y - res_p.y).abs().max()), ' nfev equal:', bool(np.array_equal(res_f.nfev, res_p.nfev)), flush=True)
     del dev_p, dy_p, res_p

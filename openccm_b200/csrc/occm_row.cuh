@@ -1,4 +1,4 @@
-// Thread-per-POINT form of the light stage kernels (plain RHS, stage 2, stage 7) of CSTR networks, compiled per mechanism
+// Thread-per-POINT form of the light stage kernels (plain RHS, J*v state, stages 2 and 7) of CSTR and PFR networks, compiled per mechanism
 // (spec/occm_spec.cu includes this file after the generated mechanism header; see occm_spec.h).
 //
 // Why: in occm_pipe.cuh a thread owns a species PAIR, so the species a reaction term multiplies differ from lane to lane and are
@@ -47,6 +47,7 @@ template <int STAGE>
 __device__ __forceinline__ double2 occm_row_state(unsigned slot_sa, unsigned off, unsigned stream_bytes, double hb) {
     const double2 a = occm_lds2<2>(slot_sa + off);
     if (STAGE == 2) { const double2 b = occm_lds2<2>(slot_sa + stream_bytes + off); return make_double2(a.x + (dp::A21 * b.x) * hb, a.y + (dp::A21 * b.y) * hb); }
+    if (STAGE == 1) { const double2 b = occm_lds2<2>(slot_sa + stream_bytes + off); return make_double2(a.x + b.x * hb, a.y + b.y * hb); }
     return a;
 }
 
@@ -56,13 +57,14 @@ __device__ __forceinline__ void occm_row_load(double (&c)[S], const double* pa, 
     double2 a[S / 2], b[S / 2];
 #pragma unroll
     for (int j = 0; j < S / 2; ++j) a[j] = reinterpret_cast<const double2*>(pa)[j];
-    if (STAGE == 2) {
+    if (STAGE == 1 || STAGE == 2) {
 #pragma unroll
         for (int j = 0; j < S / 2; ++j) b[j] = reinterpret_cast<const double2*>(pb)[j];
     }
 #pragma unroll
     for (int j = 0; j < S / 2; ++j) {
         if (STAGE == 2) { c[2 * j] = a[j].x + (dp::A21 * b[j].x) * hb; c[2 * j + 1] = a[j].y + (dp::A21 * b[j].y) * hb; }
+        else if (STAGE == 1) { c[2 * j] = a[j].x + b[j].x * hb; c[2 * j + 1] = a[j].y + b[j].y * hb; }
         else { c[2 * j] = a[j].x; c[2 * j + 1] = a[j].y; }
     }
 }
@@ -73,7 +75,9 @@ __device__ __forceinline__ void occm_row_body(const OccmSysDev& sys, const OccmM
                                               const OccmEllEntry* __restrict__ ell, const OccmRowGeom& g) {
     constexpr int S = OCCM_SPEC_S, K = OCCM_SPEC_K, NT = OCCM_SPEC_NTERM;
     static_assert(S % 2 == 0 && S <= OCCM_SPEC_MAX_S, "even species counts up to 16");
-    static_assert(STAGE == 0 || STAGE == 2 || STAGE == 7, "light stages");
+    static_assert(STAGE == 0 || STAGE == 1 || STAGE == 2 || STAGE == 7, "light stages");
+    constexpr int MODEL = OCCM_SPEC_MODEL;           // 0: CSTR rows (K ELL entries), 1: PFR (one upwind entry per point)
+    static_assert(MODEL == 0 || K == 1, "a PFR point has one upwind neighbour");
     extern __shared__ __align__(128) unsigned char smem_p[];
     constexpr int NS = OccmPipeStreams<STAGE>::value, NOUT = OccmRowOut<STAGE>::value;
     constexpr int POINTS = 32 * W;
@@ -222,7 +226,7 @@ __device__ __forceinline__ void occm_row_body(const OccmSysDev& sys, const OccmM
                 occm_row_load<STAGE, S>(nb, pa[k], pb[k], cc.h);
                 const double w = __hiloint2double(e4[k].w, e4[k].z);
 #pragma unroll
-                for (int s = 0; s < S; ++s) acc[s] = fma(w, nb[s], acc[s]);
+                for (int s = 0; s < S; ++s) acc[s] = MODEL == 0 ? fma(w, nb[s], acc[s]) : nb[s];      // PFR: keeps the upwind row
             }
 #else
 #pragma unroll
@@ -240,7 +244,7 @@ __device__ __forceinline__ void occm_row_body(const OccmSysDev& sys, const OccmM
                 }
                 const double w = __hiloint2double(e4[k].w, e4[k].z);
 #pragma unroll
-                for (int s = 0; s < S; ++s) acc[s] = fma(w, nb[s], acc[s]);
+                for (int s = 0; s < S; ++s) acc[s] = MODEL == 0 ? fma(w, nb[s], acc[s]) : nb[s];      // PFR: keeps the upwind row
             }
 #endif
             // ---- reactions: straight-line code over the registers of the point (generated per mechanism)
@@ -254,7 +258,13 @@ __device__ __forceinline__ void occm_row_body(const OccmSysDev& sys, const OccmM
             for (int s = 0; s < S; ++s) r[s] = 0.0;
             OCCM_SPEC_TERMS(c, my_scaled, r)
 #pragma unroll
-            for (int s = 0; s < S; ++s) f[s] = __dadd_rn(__dmul_rn(cc.qs, acc[s]), r[s]);
+            for (int s = 0; s < S; ++s) {
+                if (MODEL == 0) f[s] = __dadd_rn(__dmul_rn(cc.qs, acc[s]), r[s]);
+                else {                   // first-order upwind difference along the PFR (pfr_system.py:296), roundings of occm_pipe
+                    const double na = -(cc.qs * __hiloint2double(e4[0].w, e4[0].z));
+                    f[s] = __dadd_rn(__dmul_rn(na, c[s] - acc[s]), r[s]);
+                }
+            }
         }
         // ---- epilogue of the stage; rows of flagged points are rewritten by occm_fixup afterwards (zeros here)
         double2 o0[S / 2], o1[S / 2];
@@ -279,7 +289,7 @@ __device__ __forceinline__ void occm_row_body(const OccmSysDev& sys, const OccmM
         if (lane == 0) occm_mbar_arrive(bar_sa + 8u * (g.depth + slot));
         if (++slot == g.depth) { slot = 0; phase ^= 1u; }
 
-        double* out0 = (STAGE == 0 ? dy_out : STAGE == 2 ? rk.K2 : rk.KF[cc.par ^ 1]) + mbase;
+        double* out0 = (STAGE <= 1 ? dy_out : STAGE == 2 ? rk.K2 : rk.KF[cc.par ^ 1]) + mbase;
         double* out1 = STAGE == 2 ? rk.YS[0] + mbase : nullptr;
 #if OCCM_ROW_BULK_STORE
         const int w0 = p0 + warp * 32;                                  // first point of this warp

@@ -128,7 +128,7 @@ static const char* occm_drv_str(CUresult r) { const char* s = nullptr; if (g_drv
 
 struct OccmSpec {
     CUmodule mod;
-    CUfunction fn[8];                  // by stage (0, 2, 7)
+    CUfunction fn[8];                  // by stage (0, 1, 2, 7)
     int S, K, n_term;
     int warps[8], ctas[8];             // by stage
     size_t smem_limit[8], occ_smem[8]; int occ[8];
@@ -146,8 +146,8 @@ void occm_spec_unload(occm_system* s) {
 extern "C" int occm_system_load_specialized(occm_system* s, const void* image, size_t bytes) {
     if (!s || !image || bytes < 64) { occm_set_error("occm_system_load_specialized: null system or image"); return OCCM_ERR_INVALID; }
     const OccmSysDev& d = s->dev;
-    if (d.model != OCCM_MODEL_CSTR || s->any_prog || !s->desc.ell_packed || d.ell_k < 1) {
-        occm_set_error("specialised kernels cover CSTR networks with polynomial rate laws and a packed ELL operator");
+    if (s->any_prog || !s->desc.ell_packed || d.ell_k < 1 || (d.model == OCCM_MODEL_PFR && d.ell_k != 1)) {
+        occm_set_error("specialised kernels cover networks with polynomial rate laws and a packed ELL operator");
         return OCCM_ERR_UNSUPPORTED;
     }
     OCCM_CUDA_CHECK(cudaSetDevice(s->device));
@@ -175,17 +175,17 @@ extern "C" int occm_system_load_specialized(occm_system* s, const void* image, s
     }
     const unsigned long long hash = occm_spec_hash(blob, (size_t)d.tables_bytes);
     free(blob);
-    if (info[OCCM_SI_ABI] != OCCM_SPEC_ABI || (int)info[OCCM_SI_S] != d.S || (int)info[OCCM_SI_K] != d.ell_k ||
-        (int)info[OCCM_SI_NTERM] != s->n_term || info[OCCM_SI_HASH] != hash) {
-        occm_set_error("image does not match the system: abi %llu (library %d), S %llu (%d), K %llu (%d), terms %llu (%d), table hash %016llx (%016llx)",
-                       info[OCCM_SI_ABI], OCCM_SPEC_ABI, info[OCCM_SI_S], d.S, info[OCCM_SI_K], d.ell_k, info[OCCM_SI_NTERM], s->n_term,
-                       info[OCCM_SI_HASH], hash);
+    if (info[OCCM_SI_ABI] != OCCM_SPEC_ABI || (int)info[OCCM_SI_MODEL] != d.model || (int)info[OCCM_SI_S] != d.S ||
+        (int)info[OCCM_SI_K] != d.ell_k || (int)info[OCCM_SI_NTERM] != s->n_term || info[OCCM_SI_HASH] != hash) {
+        occm_set_error("image does not match the system: abi %llu (library %d), model %llu (%d), S %llu (%d), K %llu (%d), terms %llu (%d), "
+                       "table hash %016llx (%016llx)", info[OCCM_SI_ABI], OCCM_SPEC_ABI, info[OCCM_SI_MODEL], d.model, info[OCCM_SI_S], d.S,
+                       info[OCCM_SI_K], d.ell_k, info[OCCM_SI_NTERM], s->n_term, info[OCCM_SI_HASH], hash);
         return fail(OCCM_ERR_INVALID);
     }
     sp->S = d.S; sp->K = d.ell_k; sp->n_term = s->n_term;
-    const int stages[3] = {0, 2, 7};
-    const int iw[3] = {OCCM_SI_W0, OCCM_SI_W2, OCCM_SI_W7}, ic[3] = {OCCM_SI_C0, OCCM_SI_C2, OCCM_SI_C7};
-    for (int i = 0; i < 3; ++i) {
+    const int stages[4] = {0, 1, 2, 7};
+    const int iw[4] = {OCCM_SI_W0, OCCM_SI_W1, OCCM_SI_W2, OCCM_SI_W7}, ic[4] = {OCCM_SI_C0, OCCM_SI_C1, OCCM_SI_C2, OCCM_SI_C7};
+    for (int i = 0; i < 4; ++i) {
         const int st = stages[i];
         sp->warps[st] = (int)info[iw[i]]; sp->ctas[st] = (int)info[ic[i]];
         if (sp->warps[st] < 1 || sp->warps[st] > 31 || sp->ctas[st] < 1 || sp->ctas[st] > 16) {
@@ -203,13 +203,13 @@ extern "C" int occm_system_load_specialized(occm_system* s, const void* image, s
 
 extern "C" int occm_system_is_specialized(const occm_system* s) { return s && s->spec ? 1 : 0; }
 
-// One launch of a specialised stage kernel (stages 0, 2, 7).  Returns 1 when the configuration does not fit it.
+// One launch of a specialised stage kernel (stages 0, 1, 2, 7).  Returns 1 when the configuration does not fit it.
 int occm_spec_launch(const occm_system* sys, int stage, const OccmMemDev& mem, const OccmRkDev& rk, const double* y_in,
                      double* dy_out, cudaStream_t st, int* err_stride_out, int* main_partials_out) {
     OccmSpec* sp = sys->spec;
     const int S = sp->S, K = sp->K, W = sp->warps[stage], pts = 32 * W;
-    const int NS = stage == 0 ? 1 : stage == 2 ? 2 : 3, NOUT = stage == 2 ? 2 : 1;
-    if (stage == 0 && ((uintptr_t)y_in & 15 || (uintptr_t)dy_out & 15)) return 1;
+    const int NS = stage == 0 ? 1 : stage == 7 ? 3 : 2, NOUT = stage == 2 ? 2 : 1;
+    if (stage <= 1 && ((uintptr_t)y_in & 15 || (uintptr_t)dy_out & 15 || (uintptr_t)mem.z & 15)) return 1;
     OccmRowGeom g;
     g.cpm = (int)((sys->dev.n_points + pts - 1) / pts);
     g.stream_bytes = pts * S * 8;
@@ -997,12 +997,15 @@ static int occm_launch_pipe(const occm_system* sys, const OccmMemDev& mem, const
 template <int STAGE>
 static int occm_launch_spec(const occm_system* sys, const OccmMemDev& mem, const OccmRkDev& rk, const double* t_dev,
                             double t_scalar, const double* y_in, double* dy_out, cudaStream_t st, int* cpm_out) {
-    if constexpr (STAGE == 0 || STAGE == 2 || STAGE == 7) {
+    if constexpr (STAGE == 0 || STAGE == 1 || STAGE == 2 || STAGE == 7) {
         if (!sys->spec || !sys->use_row) return 1;
         int err_stride = 0, main_partials = 0;
         const int rc = occm_spec_launch(sys, STAGE, mem, rk, y_in, dy_out, st, &err_stride, &main_partials);
         if (rc != OCCM_OK) return rc;
-        if (int rf = occm_launch_fixup<0, STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, err_stride, main_partials)) return rf;
+        const int rf = sys->dev.model == OCCM_MODEL_PFR
+            ? occm_launch_fixup<1, STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, err_stride, main_partials)
+            : occm_launch_fixup<0, STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, err_stride, main_partials);
+        if (rf) return rf;
         if (cpm_out) *cpm_out = err_stride;
         return OCCM_OK;
     }
@@ -1034,8 +1037,11 @@ int occm_launch_stage(const occm_system* sys, const OccmMemDev& mem, const OccmR
                       (!even || (occm_aligned16(y_in) && occm_aligned16(dy_out) && occm_aligned16(mem.z)));
 #define OCCM_FAST_CALL(MODEL, K, WIDE, V) occm_launch_both<MODEL, STAGE, K, WIDE, V>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out)
 #define OCCM_FAST_CALL_V(MODEL, K, WIDE) (even ? OCCM_FAST_CALL(MODEL, K, WIDE, 2) : OCCM_FAST_CALL(MODEL, K, WIDE, 1))
-    if (fast && d.model == OCCM_MODEL_PFR && d.ell_k == 1 && sys->desc.n_flagged >= d.n_models)
+    if (fast && d.model == OCCM_MODEL_PFR && d.ell_k == 1 && sys->desc.n_flagged >= d.n_models) {
+        const int rc = occm_launch_spec<STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);
+        if (rc <= 0) return rc;
         return wide ? OCCM_FAST_CALL_V(1, 1, 1) : OCCM_FAST_CALL_V(1, 1, 0);
+    }
     if (fast && d.model == OCCM_MODEL_CSTR) {
         {
             const int rc = occm_launch_spec<STAGE>(sys, mem, rk, t_dev, t_scalar, y_in, dy_out, st, cpm_out);

@@ -8,7 +8,7 @@
 // Without an image the table-driven kernels (occm_pipe.cuh / occm_fast.cuh) run: same arithmetic, same roundings.
 #pragma once
 
-#define OCCM_SPEC_ABI 4                 // bump whenever OccmRowGeom, a kernel signature or the meaning of occm_spec_info changes
+#define OCCM_SPEC_ABI 5                 // bump whenever OccmRowGeom, a kernel signature or the meaning of occm_spec_info changes
 
 // Consumer warps per CTA (32 points each; + one producer warp) and CTAs per SM the register budget is sized for, per stage.
 // The kernels are latency bound on the out-of-chunk row gathers, so the plain RHS (one staged stream: small ring slots) runs as
@@ -18,6 +18,12 @@
 #endif
 #ifndef OCCM_ROW_C0
 #define OCCM_ROW_C0 2
+#endif
+#ifndef OCCM_ROW_W1
+#define OCCM_ROW_W1 4                   // stage 1 (state y + eps z of the matrix-free Jacobian action): two staged streams like stage 2
+#endif
+#ifndef OCCM_ROW_C1
+#define OCCM_ROW_C1 2
 #endif
 #ifndef OCCM_ROW_W2
 #define OCCM_ROW_W2 4
@@ -36,7 +42,8 @@
 #define OCCM_SPEC_MAX_S 16
 
 // words of the image's `occm_spec_info` array
-enum { OCCM_SI_ABI = 0, OCCM_SI_S, OCCM_SI_K, OCCM_SI_NTERM, OCCM_SI_HASH, OCCM_SI_W0, OCCM_SI_C0, OCCM_SI_W2, OCCM_SI_C2, OCCM_SI_W7, OCCM_SI_C7, OCCM_SI_WORDS };
+enum { OCCM_SI_ABI = 0, OCCM_SI_S, OCCM_SI_K, OCCM_SI_NTERM, OCCM_SI_HASH, OCCM_SI_MODEL, OCCM_SI_W0, OCCM_SI_C0, OCCM_SI_W1, OCCM_SI_C1,
+       OCCM_SI_W2, OCCM_SI_C2, OCCM_SI_W7, OCCM_SI_C7, OCCM_SI_WORDS };
 
 struct OccmRowGeom {
     int cpm;           // chunks (32 * warps points) per member

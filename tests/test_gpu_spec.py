@@ -69,6 +69,35 @@ def test_synthetic_networks(n_cstr, S, R, M):
     _compare(_synthetic_host(n_cstr, S, R, seed=S), M=M, t_end=1.0)
 
 
+@pytest.mark.parametrize('name', ['pfr_net8', 'pfr_net8_nacl', 'pfr_single'])
+def test_pfr_reference_cases(name, tmp_path):
+    """PFR networks: one upwind entry per point, inlet nodes through occm_fixup."""
+    _compare(_case_host(name, tmp_path), M=3, t_end=2.0)
+
+
+def test_pfr_bdf_newton_krylov_is_unchanged():
+    """Stiff PFR chains through BDF + GMRES: the residual (plain RHS) and the matrix-free Jacobian action (RHS of y + eps z, the
+    stage-1 kernel) of the image are bit-identical to the table-driven ones, so the whole solve is — same steps, same orders,
+    same iteration counts, same numbers."""
+    import torch
+    from openccm_b200.bdf import solve_bdf
+    from openccm_b200.device import DeviceSystem
+    from openccm_b200.system_solvers.export import export_system
+    from openccm_b200.workloads import pfr_stiff_workload
+    model, net, cp, cmesh = pfr_stiff_workload(n_chains=6, chain_len=5, P=40, t_end=2.0)
+    host = export_system(model, net, cp, cmesh)
+    y0 = torch.as_tensor(host.to_device_layout(host.c0.reshape(-1)), device='cuda')[None].contiguous()
+    out = []
+    for how in ('off', 'on'):
+        dev = DeviceSystem(host, specialize=how)
+        assert dev.specialized == (how == 'on')
+        out.append(solve_bdf(dev, y0, (0.0, 2.0), rtol=1e-8, atol=1e-12, first_step=1e-5, t_eval=np.linspace(0, 2, 9)))
+    a, b = out
+    assert int(a.status[0]) == 1 and int(b.status[0]) == 1
+    assert int(a.nfev[0]) == int(b.nfev[0]) and int(a.n_accepted[0]) == int(b.n_accepted[0])
+    assert torch.equal(a.y, b.y)
+
+
 def test_auto_mode_specialises_large_networks_only(monkeypatch):
     from openccm_b200.device import DeviceSystem
     monkeypatch.delenv('OCCM_B200_SPECIALIZE', raising=False)
@@ -81,7 +110,7 @@ def test_auto_mode_specialises_large_networks_only(monkeypatch):
 def test_ineligible_systems_keep_the_table_driven_kernels(tmp_path):
     import torch
     from openccm_b200.device import DeviceSystem
-    for name in ('pfr_net8', 'cstr_net20_timebc', 'cstr_monod'):
+    for name in ('pfr_net6_pointmass', 'cstr_net20_timebc', 'cstr_monod'):
         host = _case_host(name, tmp_path)
         dev = DeviceSystem(host, specialize='on')
         assert not dev.specialized
@@ -109,7 +138,7 @@ def test_loader_rejects_foreign_images(tmp_path):
     pfr = DeviceSystem(_case_host('pfr_net8', tmp_path), specialize='off')
     with open(sp.build_image(host.tables, dev.tables_blob, host.S, dev.ell_k), 'rb') as fh:
         img = fh.read()
-    assert pfr.lib.occm_system_load_specialized(pfr.handle, img, len(img)) == -4
+    assert pfr.lib.occm_system_load_specialized(pfr.handle, img, len(img)) == -1 and 'model' in pfr.lib.occm_last_error().decode()
 
 
 def test_finished_members_are_skipped():

@@ -51,11 +51,13 @@ def test_header_lists_every_term_in_storage_order(tmp_path):
 @pytest.mark.parametrize('name,ok', [('cstr_net12_nacl', True), ('cstr_reversible', True), ('cstr_zeroth', True),
                                      ('cstr_net20_timebc', False),       # three species: odd
                                      ('cstr_monod', False),              # Monod kinetics: byte-code terms
-                                     ('pfr_net8', False),                # PFR networks run the table-driven kernels
+                                     ('pfr_net8', True),                 # PFR: one upwind entry per point
+                                     ('pfr_net6_pointmass', False),      # one species: odd
                                      ('cstr_net9_tracer', False)])       # no reactions: nothing to specialise
 def test_eligibility(name, ok, tmp_path):
     from openccm_b200.specialize import eligible
-    assert eligible(_host(name, tmp_path), 2) is ok
+    host = _host(name, tmp_path)
+    assert eligible(host, 1 if host.model == 'pfr' else 2) is ok
 
 
 @pytest.mark.skipif(shutil.which('nvcc') is None and not os.path.exists('/usr/local/cuda/bin/nvcc'), reason='needs nvcc')
@@ -72,7 +74,7 @@ def test_image_builds_and_is_cached(tmp_path, monkeypatch):
     cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
     if os.path.exists(cuobjdump):
         out = subprocess.run([cuobjdump, '-elf', path], capture_output=True, text=True).stdout
-        for sym in ('occm_spec_stage0', 'occm_spec_stage2', 'occm_spec_stage7', 'occm_spec_info'):
+        for sym in ('occm_spec_stage0', 'occm_spec_stage1', 'occm_spec_stage2', 'occm_spec_stage7', 'occm_spec_info'):
             assert sym in out
         sass = subprocess.run([cuobjdump, '-sass', path], capture_output=True, text=True).stdout
         assert 'UBLKCP' in sass and 'SYNCS' in sass          # bulk copies + mbarriers of the ring

@@ -20,6 +20,21 @@
 #include "occm_host.h"
 
 #define BDF_MAX_ORDER 5
+// Storage type of the preconditioner's block inverses.  They are 8 S of the (32 + 8 S) bytes per unknown a preconditioner
+// application moves in fp64, i.e. the kernel is a stream over them; a preconditioner needs no more than single precision (GMRES is
+// flexible here — the preconditioned vectors are stored — and Newton is driven by fp64 residuals), so they are stored as float:
+// (32 + 4 S) bytes per unknown.  -DOCCM_BDF_BINV_F64 keeps doubles (A/B).
+#ifdef OCCM_BDF_BINV_F64
+typedef double occm_binv_t;
+#else
+typedef float occm_binv_t;
+#endif
+// Layout: Binv[member][unknown i of a point][j] = (B_point^-1)(i, j), rows padded to whole 16-byte vectors: a lane reads its row
+// with 128-bit loads.  Measured on C5 (S = 12, 2.4e7 unknowns, one application): float rows 0.53 ms; float column-major with
+// 4-byte loads 2.27 ms; float interleaved so that the lanes of a point read contiguous 16-byte pieces 0.63 ms; fp64
+// column-major (round 1) 0.67 ms, fp64 rows 0.78 ms.
+#define BDF_BINV_VEC (16 / (int)sizeof(occm_binv_t))
+static inline __host__ __device__ int bdf_binv_row(int S) { return (S + BDF_BINV_VEC - 1) / BDF_BINV_VEC * BDF_BINV_VEC; }
 #define BDF_NEWTON_MAXITER 4
 #define BDF_NVEC_D 8            // MAX_ORDER + 3 difference vectors
 #define BDF_CHUNK 2048          // elements per CTA trip of the streaming kernels (256 threads x 8)
@@ -47,9 +62,9 @@ struct OccmBdfDev {
     long long max_steps;
     const double* tdiag;                     // transport diagonal per model (CSTR: A_jj, PFR: -Q/dV)
     const double* q_scale; const double* k_scale;
-    // stored block inverses (precond_mode 0): Binv[m][point][j][i] = (B_point^-1)(i, j)
+    // stored block inverses (precond_mode 0): Binv[m][unknown i][j] = (B_point^-1)(i, j) (occm_binv_t rows, see above)
     int store;
-    double* Binv; double* c_fact; int* need_factor; int* since_factor; int* force_factor; long long* n_factor;
+    occm_binv_t* Binv; double* c_fact; int* need_factor; int* since_factor; int* force_factor; long long* n_factor;
     int* reorth; double* wn2;                // second Gram-Schmidt pass wanted (DGKS test); |w|^2 before orthogonalisation
     double* crate; int carry;                // convergence rate of the Newton iteration carried from step to step (CVODE); 0 = scipy's rule
 };
@@ -355,6 +370,44 @@ __global__ void __launch_bounds__(128) bdf_precond_warp(const __grid_constant__ 
     }
 }
 
+// row of a stored block inverse -> registers / registers -> row (128-bit accesses; entries past S are zero)
+template <int W>
+__device__ __forceinline__ void bdf_binv_load(const occm_binv_t* __restrict__ row, int RS, bool on, double (&r)[W]) {
+#pragma unroll
+    for (int j = 0; j < W; j += BDF_BINV_VEC) {
+        int4 raw = make_int4(0, 0, 0, 0);
+        const bool ld = on && j < RS;
+        if (ld) raw = __ldg(reinterpret_cast<const int4*>(row + j));
+        if (sizeof(occm_binv_t) == 4) {
+            r[j] = ld ? (double)__int_as_float(raw.x) : 0.0;
+            if (j + 1 < W) r[j + 1] = ld ? (double)__int_as_float(raw.y) : 0.0;
+            if (j + 2 < W) r[j + 2] = ld ? (double)__int_as_float(raw.z) : 0.0;
+            if (j + 3 < W) r[j + 3] = ld ? (double)__int_as_float(raw.w) : 0.0;
+        } else {
+            r[j] = ld ? __hiloint2double(raw.y, raw.x) : 0.0;
+            if (j + 1 < W) r[j + 1] = ld ? __hiloint2double(raw.w, raw.z) : 0.0;
+        }
+    }
+}
+template <int W>
+__device__ __forceinline__ void bdf_binv_store(occm_binv_t* __restrict__ row, int S, int RS, const double (&inv)[W]) {
+#pragma unroll
+    for (int j = 0; j < W; j += BDF_BINV_VEC) {
+        if (j >= RS) break;
+        int4 raw;
+        if (sizeof(occm_binv_t) == 4) {
+            raw.x = __float_as_int(j < S ? (float)inv[j] : 0.0f);
+            raw.y = __float_as_int(j + 1 < S && j + 1 < W ? (float)inv[j + 1 < W ? j + 1 : 0] : 0.0f);
+            raw.z = __float_as_int(j + 2 < S && j + 2 < W ? (float)inv[j + 2 < W ? j + 2 : 0] : 0.0f);
+            raw.w = __float_as_int(j + 3 < S && j + 3 < W ? (float)inv[j + 3 < W ? j + 3 : 0] : 0.0f);
+        } else {
+            const double a = j < S ? inv[j] : 0.0, c = j + 1 < S && j + 1 < W ? inv[j + 1 < W ? j + 1 : 0] : 0.0;
+            raw.x = __double2loint(a); raw.y = __double2hiint(a); raw.z = __double2loint(c); raw.w = __double2hiint(c);
+        }
+        *reinterpret_cast<int4*>(row + j) = raw;
+    }
+}
+
 // ---- stored variant: factor (all points in parallel, members with need_factor) ...
 template <int W>
 __global__ void __launch_bounds__(128) bdf_precond_factor(const __grid_constant__ OccmSysDev sys, const OccmBdfDev b) {
@@ -363,7 +416,7 @@ __global__ void __launch_bounds__(128) bdf_precond_factor(const __grid_constant_
     int* tab_s = reinterpret_cast<int*>(smem_d);
     occm_load_tables(sys.tables, sys.tables_bytes, tab_s);
     const OccmTab T = occm_tab_views(tab_s);
-    const int S = sys.S, P = sys.P;
+    const int S = sys.S, P = sys.P, RS = bdf_binv_row(S);
     const int nterm = tab_s[OCCM_H_MAX_TERMS], nfac = min(4, tab_s[OCCM_H_MAX_SLOTS]);
     const int lane = threadIdx.x % W, gib = threadIdx.x / W, gpb = 128 / W;
     const long long per_member = sys.n_points;
@@ -385,11 +438,7 @@ __global__ void __launch_bounds__(128) bdf_precond_factor(const __grid_constant_
         double row[W], inv[W];
         bdf_group_rows<W>(T, nterm, nfac, S, lane, y, b.c[m], qs * b.tdiag[gv ? model : 0], ksc, row);
         bdf_group_invert<W>(S, lane, row, inv);
-        if (on) {
-            double* o = b.Binv + e * S + lane;
-#pragma unroll
-            for (int j = 0; j < W; ++j) if (j < S) o[(long long)j * S] = inv[j];
-        }
+        if (on) bdf_binv_store<W>(b.Binv + (e + lane) * RS, S, RS, inv);
     }
 }
 
@@ -397,7 +446,7 @@ __global__ void __launch_bounds__(128) bdf_precond_factor(const __grid_constant_
 template <int MODEL, int W>
 __global__ void __launch_bounds__(128) bdf_precond_apply(const OccmBdfDev b, const double* __restrict__ src, int src_is_V_col_j,
                                                          double* __restrict__ dst, const int* __restrict__ mask, int keep_z) {
-    const int S = b.S, P = b.P;
+    const int S = b.S, P = b.P, RS = bdf_binv_row(S);
     const int lane = threadIdx.x % W, gib = threadIdx.x / W, gpb = 128 / W;
     const long long per_member = MODEL == 0 ? b.n_points : b.n_points / P;
     const long long total = (long long)b.M * per_member;
@@ -410,10 +459,8 @@ __global__ void __launch_bounds__(128) bdf_precond_apply(const OccmBdfDev b, con
         const double* in = src + (src_is_V_col_j ? (long long)b.gmres_j[m] * b.vstride : 0) + (long long)m * b.ndof;
         if (MODEL == 0) {
             const long long g0 = (long long)m * b.ndof + idx * S + lane;
-            const double* bi = b.Binv + ((long long)m * b.ndof + idx * S) * S + lane;
             double r[W];
-#pragma unroll
-            for (int j = 0; j < W; ++j) r[j] = (on && j < S) ? bi[(long long)j * S] : 0.0;
+            bdf_binv_load<W>(b.Binv + g0 * RS, RS, on, r);
             const double y = on ? b.y[g0] : 0.0, d = on ? b.d[g0] : 0.0;
             const double u = on ? (b.atol + b.rtol * fabs(y - d)) * in[idx * S + lane] : 0.0;
             double a0 = 0.0, a1 = 0.0;
@@ -429,7 +476,7 @@ __global__ void __launch_bounds__(128) bdf_precond_apply(const OccmBdfDev b, con
             const double ca = c * qs * (-b.tdiag[gv ? idx : 0]);             // c * Q/dV of this PFR
             const long long gbase = (long long)m * b.ndof + idx * P * S + lane;
             const double* inp = in + idx * P * S + lane;
-            const double* bi = b.Binv + ((long long)m * b.ndof + idx * P * S) * S + lane;
+            const occm_binv_t* bi = b.Binv + gbase * RS;                       // this lane's row of the PFR's first point
             double xprev = 0.0;
             double y = on ? b.y[gbase] : 0.0, d = on ? b.d[gbase] : 0.0, w = on ? inp[0] : 0.0;
             double r[W];
@@ -439,8 +486,7 @@ __global__ void __launch_bounds__(128) bdf_precond_apply(const OccmBdfDev b, con
                 // the next point's block row and operands are requested before this point's (sequentially dependent) mat-vec
                 const bool more = on && i + 1 < P;
                 double rn[W];
-#pragma unroll
-                for (int j = 0; j < W; ++j) rn[j] = (more && j < S) ? bi[((long long)(i + 1) * S + j) * S] : 0.0;
+                bdf_binv_load<W>(bi + (long long)(i + 1) * S * RS, RS, more, rn);
                 const double yn = more ? b.y[gbase + (long long)(i + 1) * S] : 0.0;
                 const double dn = more ? b.d[gbase + (long long)(i + 1) * S] : 0.0;
                 const double wn = more ? inp[(long long)(i + 1) * S] : 0.0;
@@ -1005,7 +1051,7 @@ static size_t bdf_carve(const occm_system* sys, int M, int restart, int store, O
     b.c_fact = (double*)take(md); b.need_factor = (int*)take(mi); b.since_factor = (int*)take(mi); b.force_factor = (int*)take(mi);
     b.n_factor = (long long*)take(md);
     b.reorth = (int*)take(mi); b.wn2 = (double*)take(md); b.crate = (double*)take(md);
-    b.Binv = store ? (double*)take((size_t)M * sys->dev.ndof * sys->dev.S * sizeof(double)) : nullptr;
+    b.Binv = store ? (occm_binv_t*)take((size_t)M * sys->dev.ndof * bdf_binv_row(sys->dev.S) * sizeof(occm_binv_t)) : nullptr;
     b.nchunk = nchunk;
     return o;
 }

@@ -36,3 +36,4 @@ with BdfRun(dev, y0, (0.0, t_end), **kw) as run:
     run.stats()
     print(f'{ATTEMPTS} attempts after {SKIP}: {1e3 * dt / ATTEMPTS:.2f} ms per attempt; nfev {int(run.nfev[0])} gmres {int(run.n_gmres[0])} '
           f'accepted {int(run.n_acc[0])} rejected {int(run.n_rej[0])}', flush=True)
+    print('kernel ms: rhs %.3f  jv %.3f  precond_apply %.3f' % tuple(run.time_kernel(w, 10) for w in (0, 1, 2)), flush=True)

@@ -362,7 +362,7 @@ def bdf_block(args, peak):
         mode = run.precond_mode
     ndof, S = host.ndof, host.S
     newton_its = nfev - n_gmres - 1                 # RHS calls that are Newton residuals (the others are Jacobian actions)
-    alg = {'rhs': 16.0 * ndof, 'jv': 24.0 * ndof, 'precond_apply': (32.0 + 4.0 * S) * ndof}      # bytes per launch (block inverses stored as float)
+    alg = {'rhs': 16.0 * ndof, 'jv': 24.0 * ndof, 'precond_apply': (24.0 + 4.0 * S) * ndof}      # bytes per launch (block inverses stored as float)
     roof = {k: {"ms_per_launch": v, "achieved_gbs": alg[k] / (v * 1e-3) / 1e9, "frac": alg[k] / (v * 1e-3) / 1e9 / peak} for k, v in kern.items()}
     out = {"workload": "C5: 1e4 PFRs (500 recycle chains of 20) x 200 points x 12 species = 2.4e7 DOF, 20 reactions with k in [1e-3, 1e4], "
                        "t in [0, 20], rtol 1e-6 atol 1e-10, BDF + block-preconditioned GMRES(30), one member",

@@ -50,6 +50,7 @@ struct OccmBdfDev {
     long long ndof, n_points, vstride;      // vstride = M * ndof
     double* D;                               // [8][M][ndof]
     double* y; double* psi; double* d; double* f; double* f2; double* z; double* w;
+    double* sc;     // error weights of the attempt, atol + rtol |y_predict| (written by bdf_predict; y - d would rebuild y_predict)
     double* V;                               // [restart + 1][M][ndof]
     double* Z;                               // [restart][M][ndof]  preconditioned Krylov vectors z_j = M^-1 S v_j (flexible GMRES)
     double* t; double* h_abs; double* t_new; double* c; double* t_old_out;
@@ -177,7 +178,7 @@ __device__ __forceinline__ void bdf_predict_elems(const OccmBdfDev& b, int m, in
             yp += di;
             ps += di * gam[i];
         }
-        b.y[g] = yp; b.psi[g] = ps * inv_alpha; b.d[g] = 0.0;
+        b.y[g] = yp; b.psi[g] = ps * inv_alpha; b.d[g] = 0.0; b.sc[g] = b.atol + b.rtol * fabs(yp);
     }
 }
 
@@ -344,8 +345,8 @@ __global__ void __launch_bounds__(128) bdf_precond_warp(const __grid_constant__ 
         const double* in = src + (src_is_V_col_j ? (long long)b.gmres_j[m] * b.vstride : 0) + (long long)m * b.ndof;
         if (MODEL == 0) {
             const long long g0 = (long long)m * b.ndof + idx * S + lane;
-            const double y = on ? b.y[g0] : 0.0, d = on ? b.d[g0] : 0.0;
-            double u = on ? (b.atol + b.rtol * fabs(y - d)) * in[idx * S + lane] : 0.0;
+            const double y = on ? b.y[g0] : 0.0;
+            double u = on ? b.sc[g0] * in[idx * S + lane] : 0.0;
             bdf_group_solve<W>(T, nterm, nfac, S, lane, y, c, qs * b.tdiag[gv ? idx : 0], ksc, u);
             if (on) { dst[g0] = u; if (keep_z) b.Z[(long long)b.gmres_j[m] * b.vstride + g0] = u; }
         } else {
@@ -353,14 +354,14 @@ __global__ void __launch_bounds__(128) bdf_precond_warp(const __grid_constant__ 
             double xprev = 0.0;
             const long long gbase = (long long)m * b.ndof + idx * P * S + lane;
             const double* inp = in + idx * P * S + lane;
-            double y = on ? b.y[gbase] : 0.0, d = on ? b.d[gbase] : 0.0, w = on ? inp[0] : 0.0;
+            double y = on ? b.y[gbase] : 0.0, d = on ? b.sc[gbase] : 0.0, w = on ? inp[0] : 0.0;       // d: error weight
             for (int i = 0; i < P; ++i) {
                 // operands of the next point are requested before this point's (sequentially dependent) solve
                 const bool more = on && i + 1 < P;
                 const double yn = more ? b.y[gbase + (long long)(i + 1) * S] : 0.0;
-                const double dn = more ? b.d[gbase + (long long)(i + 1) * S] : 0.0;
+                const double dn = more ? b.sc[gbase + (long long)(i + 1) * S] : 0.0;
                 const double wn = more ? inp[(long long)(i + 1) * S] : 0.0;
-                double u = (b.atol + b.rtol * fabs(y - d)) * w;
+                double u = d * w;
                 if (i > 0) {
                     u += ca * xprev;
                     bdf_group_solve<W>(T, nterm, nfac, S, lane, y, c, -ca / c, ksc, u);
@@ -476,8 +477,7 @@ __global__ void __launch_bounds__(128) bdf_precond_apply(const OccmBdfDev b, con
             const long long g0 = (long long)m * b.ndof + idx * S + lane;
             double r[W];
             bdf_binv_load<W>(b.Binv + g0 * RS, RS, on, r);
-            const double y = on ? b.y[g0] : 0.0, d = on ? b.d[g0] : 0.0;
-            const double u = on ? (b.atol + b.rtol * fabs(y - d)) * in[idx * S + lane] : 0.0;
+            const double u = on ? b.sc[g0] * in[idx * S + lane] : 0.0;
             double a0 = 0.0, a1 = 0.0;
 #pragma unroll
             for (int j = 0; j < W; j += 2) {
@@ -499,13 +499,12 @@ __global__ void __launch_bounds__(128) bdf_precond_apply(const OccmBdfDev b, con
             // doubles one point ahead, the previous form: 0.531).
             constexpr int D = BDF_SWEEP_AHEAD, NV = W / BDF_BINV_VEC;
             int4 q[D][NV];
-            double yq[D], dq[D], wq[D];
+            double sq[D], wq[D];
 #pragma unroll
             for (int s = 0; s < D; ++s) {
                 const bool ld = on && s < P;
                 bdf_binv_raw<W>(bi + (long long)s * S * RS, RS, ld, q[s]);
-                yq[s] = ld ? b.y[gbase + (long long)s * S] : 0.0;
-                dq[s] = ld ? b.d[gbase + (long long)s * S] : 0.0;
+                sq[s] = ld ? b.sc[gbase + (long long)s * S] : 0.0;
                 wq[s] = ld ? inp[(long long)s * S] : 0.0;
             }
             for (int i0 = 0; i0 < P; i0 += D) {
@@ -515,11 +514,10 @@ __global__ void __launch_bounds__(128) bdf_precond_apply(const OccmBdfDev b, con
                     if (i < P) {                                  // uniform
                         double r[W];
                         bdf_binv_unpack<W>(q[s], r);
-                        double u = (b.atol + b.rtol * fabs(yq[s] - dq[s])) * wq[s];
+                        double u = sq[s] * wq[s];
                         const bool more = on && i + D < P;        // refill the slot with the point D ahead
                         bdf_binv_raw<W>(bi + (long long)(i + D) * S * RS, RS, more, q[s]);
-                        yq[s] = more ? b.y[gbase + (long long)(i + D) * S] : 0.0;
-                        dq[s] = more ? b.d[gbase + (long long)(i + D) * S] : 0.0;
+                        sq[s] = more ? b.sc[gbase + (long long)(i + D) * S] : 0.0;
                         wq[s] = more ? inp[(long long)(i + D) * S] : 0.0;
                         if (i > 0) {                              // the inlet node keeps the identity block
                             u += ca * xprev;
@@ -561,9 +559,7 @@ __global__ void __launch_bounds__(256) bdf_arnoldi_w(const OccmBdfDev b) {
         for (int i = 0; i <= j + 1; ++i) dots[i] = 0.0;
         BDF_ELEMS(b, ci, e) {
             const long long g = (long long)m * b.ndof + e;
-            const double y = b.y[g], d = b.d[g];
-            const double scale = b.atol + b.rtol * fabs(y - d);
-            const double w = (b.z[g] - c * ((b.f2[g] - b.f[g]) * inv_eps)) / scale;
+            const double w = (b.z[g] - c * ((b.f2[g] - b.f[g]) * inv_eps)) / b.sc[g];
             b.V[(long long)(j + 1) * b.vstride + g] = w;
             for (int i = 0; i <= j; ++i) dots[i] += w * b.V[(long long)i * b.vstride + g];
             dots[j + 1] += w * w;
@@ -1059,7 +1055,7 @@ static size_t bdf_carve(const occm_system* sys, int M, int restart, int store, O
     OccmBdfDev& b = d ? *d : t;
     b.D = (double*)take(vec * BDF_NVEC_D);
     b.y = (double*)take(vec); b.psi = (double*)take(vec); b.d = (double*)take(vec); b.f = (double*)take(vec);
-    b.f2 = (double*)take(vec); b.z = (double*)take(vec); b.w = (double*)take(vec);
+    b.f2 = (double*)take(vec); b.z = (double*)take(vec); b.w = (double*)take(vec); b.sc = (double*)take(vec);
     b.V = (double*)take(vec * (restart + 1));
     b.Z = (double*)take(vec * restart);
     const size_t md = (size_t)M * 8, mi = (size_t)M * 4, mm = (size_t)M * BDF_MAXDOT * 8;

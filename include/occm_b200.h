@@ -126,8 +126,8 @@ int occm_system_destroy(occm_system* sys);
 int64_t occm_system_ndof(const occm_system* sys);
 
 /*
- * Mechanism-specialised kernels (optional).  The reference compiles the reactions file into one Python closure per run
- * (openccm/system_solvers/helper_functions.py:52-184, generate_reaction_system: source text -> exec); the device analogue is a
+ * Mechanism-specialised kernels (optional).  The reference writes the reactions file as the source of one @njit function and lets
+ * numba compile it per run (openccm/system_solvers/reactions.py:41-93 generate_reaction_system, 395-467); the device analogue is a
  * kernel image in which the stoichiometric terms are straight-line code: openccm_b200/specialize.py generates it from the parsed
  * mechanism and compiles openccm_b200/csrc/spec/occm_spec.cu to a cubin (nvcc, sm_100a).  `image` is that cubin (host memory,
  * copied by the driver).  The image must match the system (species count, ELL width, hash of the mechanism tables, ABI of

@@ -1,8 +1,8 @@
 // Mechanism-specialised stage kernels: what liboccm_b200.so (loader + launcher, occm_solver.cu) and a specialised kernel image
 // (spec/occm_spec.cu, one cubin per mechanism / species count / ELL width) have to agree on.
 //
-// The reference builds one Python closure per reactions file (openccm/system_solvers/helper_functions.py:52-184 generates the
-// source of `reactions(C)` and exec's it), i.e. the mechanism is a compile-time constant of its RHS.  The same holds here: the
+// The reference writes the mechanism as the source of one `@njit` function per reactions file and lets numba compile it
+// (openccm/system_solvers/reactions.py:41-93, 395-467), i.e. the mechanism is a compile-time constant of its RHS.  The same holds here: the
 // host side (openccm_b200/specialize.py) writes the stoichiometric terms of the parsed mechanism as straight-line fp64 code,
 // nvcc compiles spec/occm_spec.cu around it for sm_100a, and occm_system_load_specialized() hands the image to the library.
 // Without an image the table-driven kernels (occm_pipe.cuh / occm_fast.cuh) run: same arithmetic, same roundings.

@@ -18,7 +18,9 @@
 // member status, step, parity, flow and rate scales are requested one trip ahead (consumers) / before the wait for the slot
 // (producer), which takes two dependent L2 round trips off every trip.
 // Measured and rejected (C4, 512 members): L2 prefetch of the next trip's out-of-chunk rows (plain RHS 1.62 -> 1.84 ms); branching
-// between shared-memory and global loads instead of generic loads (+2 %); 128-bit stores from registers instead of the staged
+// between shared-memory and global loads instead of generic loads (+2 %); a warp-cooperative gather of the out-of-chunk rows
+// (S / 2 lanes per row, redistributed through shared memory: fewer L1 wavefronts, but the loads of a column then wait on each
+// other: plain RHS 1.66 -> 2.31 ms); 128-bit stores from registers instead of the staged
 // bulk store (+16 %: a lane's row is 80 contiguous bytes, a warp store instruction scatters over 32 sectors); the largest
 // shared-memory carve-out (28 KB of L1 left: 2x slower — the five 16-byte loads of a gathered row hit the line the first one brought).
 // Same arithmetic and roundings as the other kernel forms (bit-identical outputs); flagged rows are left to occm_fixup.
@@ -27,9 +29,6 @@
 
 #ifndef OCCM_ROW_BULK_STORE
 #define OCCM_ROW_BULK_STORE 1          // 0: 128-bit stores straight from registers (A/B)
-#endif
-#ifndef OCCM_ROW_GENERIC_LD
-#define OCCM_ROW_GENERIC_LD 1          // 0: branch per neighbour (shared-memory load or global gather) (A/B)
 #endif
 
 template <int STAGE> struct OccmRowOut { static constexpr int value = STAGE == 2 ? 2 : 1; };      // output vectors of a stage
@@ -191,27 +190,31 @@ __device__ __forceinline__ void occm_row_body(const OccmSysDev& sys, const OccmM
         double err2 = 0.0;
         int4 e4[K];
         bool work = p < n_points;
-        if (work) {
 #pragma unroll
-            for (int k = 0; k < K; ++k)
+        for (int k = 0; k < K; ++k) {
+            if (work)
                 asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(e4[k].x), "=r"(e4[k].y), "=r"(e4[k].z), "=r"(e4[k].w)
                              : "r"(slot_sa + NS * stream_bytes + k * ELL_COL + 16u * (unsigned)pl));
-            work = !e4[0].y;
+            else e4[k] = make_int4(n_points - 1, 1, 0, 0);           // past the end: a valid row to point at, weight 0, flagged
         }
+        work = !e4[0].y;
+#if OCCM_ROW_BULK_STORE
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the previous trip's stores have left the staging rows
+        __syncwarp();
+#endif
         double f[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) f[s] = 0.0;
         double c[S];                                   // own stage state (stage 7: y_new)
 #pragma unroll
         for (int s = 0; s < S; ++s) c[s] = 0.0;
-        if (work) {
+        {
             const double* ga = occm_fast_in_a<STAGE>(sys, rk, y_in, cc);
             const double* gb = occm_fast_in_b<STAGE>(sys, mem, rk, cc);
             // ---- transport: acc = sum_k w_k * row(src_k)
             double acc[S];
 #pragma unroll
             for (int s = 0; s < S; ++s) acc[s] = 0.0;
-#if OCCM_ROW_GENERIC_LD
             const double* pa[K]; const double* pb[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
@@ -228,25 +231,6 @@ __device__ __forceinline__ void occm_row_body(const OccmSysDev& sys, const OccmM
 #pragma unroll
                 for (int s = 0; s < S; ++s) acc[s] = MODEL == 0 ? fma(w, nb[s], acc[s]) : nb[s];      // PFR: keeps the upwind row
             }
-#else
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                double nb[S];
-                const unsigned rel = (unsigned)(e4[k].x - p0);
-                if (rel < (unsigned)npts) {
-#pragma unroll
-                    for (int j = 0; j < S / 2; ++j) {
-                        const double2 v = occm_row_state<STAGE>(slot_sa, rel * ROW_BYTES + 16u * j, stream_bytes, cc.h);
-                        nb[2 * j] = v.x; nb[2 * j + 1] = v.y;
-                    }
-                } else {
-                    occm_row_load<STAGE, S>(nb, ga + (long long)e4[k].x * S, gb + (long long)e4[k].x * S, cc.h);
-                }
-                const double w = __hiloint2double(e4[k].w, e4[k].z);
-#pragma unroll
-                for (int s = 0; s < S; ++s) acc[s] = MODEL == 0 ? fma(w, nb[s], acc[s]) : nb[s];      // PFR: keeps the upwind row
-            }
-#endif
             // ---- reactions: straight-line code over the registers of the point (generated per mechanism)
 #pragma unroll
             for (int j = 0; j < S / 2; ++j) {
@@ -264,6 +248,7 @@ __device__ __forceinline__ void occm_row_body(const OccmSysDev& sys, const OccmM
                     const double na = -(cc.qs * __hiloint2double(e4[0].w, e4[0].z));
                     f[s] = __dadd_rn(__dmul_rn(na, c[s] - acc[s]), r[s]);
                 }
+                if (!work) f[s] = 0.0;                   // flagged rows and the tail past the last point: rewritten by occm_fixup / not stored
             }
         }
         // ---- epilogue of the stage; rows of flagged points are rewritten by occm_fixup afterwards (zeros here)
@@ -294,8 +279,6 @@ __device__ __forceinline__ void occm_row_body(const OccmSysDev& sys, const OccmM
 #if OCCM_ROW_BULK_STORE
         const int w0 = p0 + warp * 32;                                  // first point of this warp
         const int wn = min(32, n_points - w0);                          // its valid points (<= 0: nothing to store)
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the previous trip's stores have left the staging rows
-        __syncwarp();
 #pragma unroll
         for (int j = 0; j < S / 2; ++j) {
             occm_sts2(out_sa + (unsigned)lane * ROW_BYTES + 16u * j, o0[j]);

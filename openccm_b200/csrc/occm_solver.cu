@@ -208,7 +208,7 @@ int occm_spec_launch(const occm_system* sys, int stage, const OccmMemDev& mem, c
                      double* dy_out, cudaStream_t st, int* err_stride_out, int* main_partials_out) {
     OccmSpec* sp = sys->spec;
     const int S = sp->S, K = sp->K, W = sp->warps[stage], pts = 32 * W;
-    const int NS = stage == 0 ? 1 : stage == 7 ? 3 : 2, NOUT = stage == 2 ? 2 : 1;
+    const int NS = stage == 0 ? 1 : stage == 7 ? 3 : 2, NSTG = stage == 2 ? 2 : 1;      // staged streams; staging rows per warp (one per output vector)
     if (stage <= 1 && ((uintptr_t)y_in & 15 || (uintptr_t)dy_out & 15 || (uintptr_t)mem.z & 15)) return 1;
     OccmRowGeom g;
     g.cpm = (int)((sys->dev.n_points + pts - 1) / pts);
@@ -222,7 +222,7 @@ int occm_spec_launch(const occm_system* sys, int stage, const OccmMemDev& mem, c
     o += 16 * OCCM_ROW_MAX_DEPTH;
     o = (o + 127) & ~(size_t)127;
     g.out_off = (int)o;
-    o += (size_t)W * NOUT * 32 * S * 8;
+    o += (size_t)W * NSTG * 32 * S * 8;
     o = (o + 127) & ~(size_t)127;
     g.ring_off = (int)o;
     const size_t smem_cfg = (size_t)sys->spec_smem_kb * 1024;

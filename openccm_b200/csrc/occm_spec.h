@@ -8,7 +8,7 @@
 // Without an image the table-driven kernels (occm_pipe.cuh / occm_fast.cuh) run: same arithmetic, same roundings.
 #pragma once
 
-#define OCCM_SPEC_ABI 5                 // bump whenever OccmRowGeom, a kernel signature or the meaning of occm_spec_info changes
+#define OCCM_SPEC_ABI 6                 // bump whenever OccmRowGeom, a kernel signature or the meaning of occm_spec_info changes
 
 // Consumer warps per CTA (32 points each; + one producer warp) and CTAs per SM the register budget is sized for, per stage.
 // The kernels are latency bound on the out-of-chunk row gathers, so the plain RHS (one staged stream: small ring slots) runs as

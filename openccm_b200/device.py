@@ -70,6 +70,13 @@ def ell_from_csr(row_ptr: np.ndarray, row_src: np.ndarray, row_w: np.ndarray, pu
         idx = row_ptr[:-1][take] + col
         src[col, take] = row_src[idx]
         w[col, take] = row_w[idx]
+    # columns ordered nearest source first: the diagonal and the numbering's neighbours land in the leading columns, whose rows the
+    # pipelined kernels find in the staged chunk; far (out-of-chunk) sources share the last columns, which the specialised
+    # kernels gather warp-cooperatively (csrc/occm_row.cuh)
+    if k > 1 and n:
+        order = np.argsort(np.abs(src - np.arange(n, dtype=np.int64)[None, :]), axis=0, kind='stable')
+        src = np.take_along_axis(src, order, axis=0)
+        w = np.take_along_axis(w, order, axis=0)
     return k, src.astype(np.int32), w, flags
 
 

@@ -42,6 +42,14 @@ static inline __host__ __device__ int bdf_binv_row(int S) { return (S + BDF_BINV
 #define BDF_NVEC_D 8            // MAX_ORDER + 3 difference vectors
 #define BDF_CHUNK 2048          // elements per CTA trip of the streaming kernels (256 threads x 8)
 #define BDF_MAXDOT 48           // partial-sum slots per chunk (>= restart + 2)
+// Second Gram-Schmidt pass only when the first one cancelled enough digits to matter: one classical pass leaves the new vector
+// orthogonal to the basis to about eps |w| / |w'|, so |w'| < eta |w| with eta = 1e-4 (eta^2 here) keeps the basis orthogonal to
+// 1e-12 — far below the linear tolerance.  The DGKS value eta = 1/sqrt(2) (and Rutishauser's 1/10) fired on every Krylov vector
+// of C5: the preconditioned operator is close to the identity, so A v_j always has its largest component along v_j; that was a
+// full extra pass over the basis per iteration (0.15-0.25 ms of 1.7 ms on C5).
+#ifndef BDF_REORTH_ETA2
+#define BDF_REORTH_ETA2 1e-8
+#endif
 #define BDF_MIN_FACTOR 0.2
 #define BDF_MAX_FACTOR 10.0
 
@@ -851,7 +859,7 @@ __global__ void bdf_ctrl_h2(const OccmBdfDev b) {
     if (!b.gmres_active[m]) return;
     const int j = b.gmres_j[m];
     const double* nr = b.norms + (long long)m * BDF_MAXDOT;
-    if (!(nr[0] < 0.5 * b.wn2[m])) return;
+    if (!(nr[0] < BDF_REORTH_ETA2 * b.wn2[m])) return;
     b.reorth[m] = 1;
     double* Hc = b.H + ((long long)m * BDF_MAXDOT + j) * BDF_MAXDOT;
     for (int i = 0; i <= j; ++i) Hc[i] += nr[1 + i];

@@ -221,16 +221,6 @@ __global__ void __launch_bounds__(256) bdf_newton_rhs(const OccmBdfDev b) {
     }
 }
 
-// dst[m] *= alpha[m]  (dst = V[col])
-__global__ void __launch_bounds__(256) bdf_scale_col(const OccmBdfDev b, int col_from_j, const double* __restrict__ alpha) {
-    BDF_FOR_CHUNKS(b, b.gmres_active[m]) {
-        const int col = col_from_j ? b.gmres_j[m] : 0;
-        const double a = alpha[m];
-        double* v = b.V + col * b.vstride + (long long)m * b.ndof;
-        BDF_ELEMS(b, ci, e) v[e] *= a;
-    }
-}
-
 // ---- warp-cooperative block preconditioner: out = M^{-1} (scale .* in), M ~ I - c J, nothing stored between applications
 // W = 4, 8 or 16 lanes form a group, lane i < S owns row i of the S x S block in registers; elimination without
 // pivoting through warp shuffles (I - c J of a mass-action mechanism is column diagonally dominant).
@@ -330,7 +320,7 @@ __device__ __forceinline__ void bdf_group_solve(const OccmTab& T, int nterm, int
 }
 
 template <int MODEL, int W>
-__global__ void __launch_bounds__(128) bdf_precond_warp(const __grid_constant__ OccmSysDev sys, const OccmBdfDev b, const double* __restrict__ src,
+__global__ void __launch_bounds__(128) bdf_precond_warp(const __grid_constant__ OccmSysDev sys, const OccmBdfDev b, const double* src,
                                                         int src_is_V_col_j, double* __restrict__ dst, const int* __restrict__ mask, int keep_z) {
     extern __shared__ double smem_d[];
     int* tab_s = reinterpret_cast<int*>(smem_d);
@@ -351,10 +341,16 @@ __global__ void __launch_bounds__(128) bdf_precond_warp(const __grid_constant__ 
         const double qs = b.q_scale ? b.q_scale[m] : 1.0;
         const double* ksc = b.k_scale ? b.k_scale + (long long)m * sys.n_rxn : nullptr;
         const double* in = src + (src_is_V_col_j ? (long long)b.gmres_j[m] * b.vstride : 0) + (long long)m * b.ndof;
+        // inside GMRES (keep_z) the source is the not yet normalised Krylov vector: it is scaled by 1 / h_{j+1,j} (b.eps) on the way
+        // in and the normalised value is written back — the separate scaling pass over V is gone
+        const double va = keep_z ? b.eps[m] : 1.0;
+        double* vin = const_cast<double*>(in);
         if (MODEL == 0) {
             const long long g0 = (long long)m * b.ndof + idx * S + lane;
             const double y = on ? b.y[g0] : 0.0;
-            double u = on ? b.sc[g0] * in[idx * S + lane] : 0.0;
+            const double vw = on ? in[idx * S + lane] * va : 0.0;
+            if (on && keep_z) vin[idx * S + lane] = vw;
+            double u = on ? b.sc[g0] * vw : 0.0;
             bdf_group_solve<W>(T, nterm, nfac, S, lane, y, c, qs * b.tdiag[gv ? idx : 0], ksc, u);
             if (on) { dst[g0] = u; if (keep_z) b.Z[(long long)b.gmres_j[m] * b.vstride + g0] = u; }
         } else {
@@ -362,6 +358,7 @@ __global__ void __launch_bounds__(128) bdf_precond_warp(const __grid_constant__ 
             double xprev = 0.0;
             const long long gbase = (long long)m * b.ndof + idx * P * S + lane;
             const double* inp = in + idx * P * S + lane;
+            double* inpm = vin + idx * P * S + lane;
             double y = on ? b.y[gbase] : 0.0, d = on ? b.sc[gbase] : 0.0, w = on ? inp[0] : 0.0;       // d: error weight
             for (int i = 0; i < P; ++i) {
                 // operands of the next point are requested before this point's (sequentially dependent) solve
@@ -369,7 +366,9 @@ __global__ void __launch_bounds__(128) bdf_precond_warp(const __grid_constant__ 
                 const double yn = more ? b.y[gbase + (long long)(i + 1) * S] : 0.0;
                 const double dn = more ? b.sc[gbase + (long long)(i + 1) * S] : 0.0;
                 const double wn = more ? inp[(long long)(i + 1) * S] : 0.0;
-                double u = d * w;
+                const double vw = w * va;
+                if (on && keep_z) inpm[(long long)i * S] = vw;
+                double u = d * vw;
                 if (i > 0) {
                     u += ca * xprev;
                     bdf_group_solve<W>(T, nterm, nfac, S, lane, y, c, -ca / c, ksc, u);
@@ -468,7 +467,7 @@ __global__ void __launch_bounds__(128) bdf_precond_factor(const __grid_constant_
 
 // ... and apply: out = M^-1 (scale .* in) as one S x S mat-vec per point (PFR: inside the flow-order sweep)
 template <int MODEL, int W>
-__global__ void __launch_bounds__(128) bdf_precond_apply(const OccmBdfDev b, const double* __restrict__ src, int src_is_V_col_j,
+__global__ void __launch_bounds__(128) bdf_precond_apply(const OccmBdfDev b, const double* src, int src_is_V_col_j,
                                                          double* __restrict__ dst, const int* __restrict__ mask, int keep_z) {
     const int S = b.S, P = b.P, RS = bdf_binv_row(S);
     const int lane = threadIdx.x % W, gib = threadIdx.x / W, gpb = 128 / W;
@@ -481,11 +480,17 @@ __global__ void __launch_bounds__(128) bdf_precond_apply(const OccmBdfDev b, con
         const long long idx = gv ? g - (long long)m * per_member : 0;
         const bool on = gv && (!mask || mask[m]) && lane < S;
         const double* in = src + (src_is_V_col_j ? (long long)b.gmres_j[m] * b.vstride : 0) + (long long)m * b.ndof;
+        // inside GMRES (keep_z) the source is the not yet normalised Krylov vector: it is scaled by 1 / h_{j+1,j} (b.eps) on the way
+        // in and the normalised value is written back — the separate scaling pass over V is gone
+        const double va = keep_z ? b.eps[m] : 1.0;
+        double* vin = const_cast<double*>(in);
         if (MODEL == 0) {
             const long long g0 = (long long)m * b.ndof + idx * S + lane;
             double r[W];
             bdf_binv_load<W>(b.Binv + g0 * RS, RS, on, r);
-            const double u = on ? b.sc[g0] * in[idx * S + lane] : 0.0;
+            const double vw = on ? in[idx * S + lane] * va : 0.0;
+            if (on && keep_z) vin[idx * S + lane] = vw;
+            const double u = on ? b.sc[g0] * vw : 0.0;
             double a0 = 0.0, a1 = 0.0;
 #pragma unroll
             for (int j = 0; j < W; j += 2) {
@@ -500,6 +505,7 @@ __global__ void __launch_bounds__(128) bdf_precond_apply(const OccmBdfDev b, con
             const long long gbase = (long long)m * b.ndof + idx * P * S + lane;
             const double* inp = in + idx * P * S + lane;
             const occm_binv_t* bi = b.Binv + gbase * RS;                       // this lane's row of the PFR's first point
+            double* inpm = vin + idx * P * S + lane;
             double xprev = 0.0;
             // The sweep along a PFR is sequential (x_p needs x_{p-1}) and a point's mat-vec takes ~150 cycles, a fraction of the
             // memory latency: the block rows and operands of the next BDF_SWEEP_AHEAD points are kept in flight in a register ring
@@ -522,7 +528,9 @@ __global__ void __launch_bounds__(128) bdf_precond_apply(const OccmBdfDev b, con
                     if (i < P) {                                  // uniform
                         double r[W];
                         bdf_binv_unpack<W>(q[s], r);
-                        double u = sq[s] * wq[s];
+                        const double vw = wq[s] * va;
+                        if (on && keep_z) inpm[(long long)i * S] = vw;
+                        double u = sq[s] * vw;
                         const bool more = on && i + D < P;        // refill the slot with the point D ahead
                         bdf_binv_raw<W>(bi + (long long)(i + D) * S * RS, RS, more, q[s]);
                         sq[s] = more ? b.sc[gbase + (long long)(i + D) * S] : 0.0;
@@ -826,7 +834,7 @@ __global__ void bdf_ctrl_gmres_start(const OccmBdfDev b) {
     double* gv = b.gv + (long long)m * BDF_MAXDOT;
     for (int i = 0; i <= b.restart; ++i) gv[i] = 0.0;
     gv[0] = beta;
-    b.eps[m] = 1.0 / beta;              // bdf_scale_col: V0 *= 1 / beta
+    b.eps[m] = 1.0 / beta;              // the first preconditioner application scales V0 by it (v0 = b~ / beta)
     atomicAdd(&b.counters[2], 1);
 }
 
@@ -887,7 +895,7 @@ __global__ void bdf_ctrl_givens(const OccmBdfDev b) {
     gv[j] = cs[j] * gv[j];
     b.n_gmres[m] += 1;
     const double res = fabs(gv[j + 1]) / sqrt((double)b.ndof);
-    b.eps[m] = hn > 0.0 ? 1.0 / hn : 0.0;           // bdf_scale_col: V[j+1] *= 1 / h_{j+1,j}
+    b.eps[m] = hn > 0.0 ? 1.0 / hn : 0.0;           // the next preconditioner application scales V[j+1] by it
     b.gmres_j[m] = j + 1;
     if (!(res > b.lin_tol) || j + 1 >= b.restart || !(hn > 0.0)) {
         // back substitution R y = g
@@ -1281,7 +1289,6 @@ static int bdf_attempt(occm_bdf* h, cudaStream_t st) {
         if ((rc = bdf_reduce_launch(h, 2, b.newton_active, st))) return rc;
         OCCM_CUDA_CHECK(cudaMemsetAsync(b.counters + 2, 0, sizeof(int), st));
         BDF_LAUNCH(bdf_ctrl_gmres_start, gm, 64, 0, b);
-        BDF_LAUNCH(bdf_scale_col, gv, 256, 0, b, 0, b.eps);                                     // v0 = b~ / beta
         if ((rc = bdf_read_counters(h, st))) return rc;
         int gm_active = h->h_counters[2];
         for (int j = 0; j < b.restart && gm_active > 0; ++j) {
@@ -1298,9 +1305,8 @@ static int bdf_attempt(occm_bdf* h, cudaStream_t st) {
             BDF_LAUNCH(bdf_orth, gv, 256, 0, b, 1);                                             // re-orthogonalisation where needed
             if ((rc = bdf_reduce_launch(h, 1, b.reorth, st))) return rc;
             OCCM_CUDA_CHECK(cudaMemsetAsync(b.counters + 2, 0, sizeof(int), st));
-            // scale_col must see the pre-update gmres_j: run it with the members that stay active AFTER givens
-            BDF_LAUNCH(bdf_ctrl_givens, gm, 64, 0, b);
-            BDF_LAUNCH(bdf_scale_col, gv, 256, 0, b, 1, b.eps);
+            BDF_LAUNCH(bdf_ctrl_givens, gm, 64, 0, b);                // leaves 1 / h_{j+1,j} in b.eps: the next preconditioner
+                                                                      // application normalises v_{j+1} while it reads it
             if ((rc = bdf_read_counters(h, st))) return rc;
             gm_active = h->h_counters[2];
         }

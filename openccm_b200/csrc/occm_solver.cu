@@ -150,6 +150,9 @@ extern "C" int occm_system_load_specialized(occm_system* s, const void* image, s
         occm_set_error("specialised kernels cover networks with polynomial rate laws and a packed ELL operator");
         return OCCM_ERR_UNSUPPORTED;
     }
+    int prev_device = -1;
+    OCCM_CUDA_CHECK(cudaGetDevice(&prev_device));
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_device == s->device ? -1 : prev_device};
     OCCM_CUDA_CHECK(cudaSetDevice(s->device));
     OCCM_CUDA_CHECK(cudaFree(0));                                      // the primary context exists and is current
     if (int rc = occm_drv_load()) return rc;

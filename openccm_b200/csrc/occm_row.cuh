@@ -23,6 +23,11 @@
 // other: plain RHS 1.66 -> 2.31 ms); 128-bit stores from registers instead of the staged
 // bulk store (+16 %: a lane's row is 80 contiguous bytes, a warp store instruction scatters over 32 sectors); the largest
 // shared-memory carve-out (28 KB of L1 left: 2x slower — the five 16-byte loads of a gathered row hit the line the first one brought).
+// Where the remaining gap is (C4, 512 members): with every neighbour taken from the staged chunk (wrong results, timing only) the
+// plain RHS runs at 0.97 of the HBM peak, stage 2 at 0.93, stage 7 at 0.79 — the one far (out-of-chunk) neighbour row per point
+// costs 0.34 / 1.45 / 0.63 ms.  The ELL columns are ordered nearest source first, so the far sources share the last column; copying
+// the next trip's far rows into per-lane staging rows with cp.async while the current trip computes was 50 % SLOWER (plain RHS
+// 1.70 -> 2.55 ms, with or without waiting for the next slot's ELL columns), like every other form of prefetch tried here.
 // Same arithmetic and roundings as the other kernel forms (bit-identical outputs); flagged rows are left to occm_fixup.
 #pragma once
 #include "occm_spec.h"

@@ -98,6 +98,40 @@ def test_pfr_bdf_newton_krylov_is_unchanged():
     assert torch.equal(a.y, b.y)
 
 
+@pytest.mark.parametrize('kind', ['pfr', 'cstr'])
+def test_bdf_ensembles_with_members_finishing_at_different_attempts(kind):
+    """Batched BDF: members with other flow / rate scales take other step sequences and finish at different attempts, so the RHS
+    and J*v launches run under the active-member mask; image and table-driven kernels give identical solves."""
+    import torch
+    from openccm_b200.bdf import solve_bdf
+    from openccm_b200.device import DeviceSystem, MemberParams
+    from openccm_b200.system_solvers.export import export_system
+    from openccm_b200.workloads import cstr_ensemble_workload, pfr_stiff_workload
+    if kind == 'pfr':
+        model, net, cp, cmesh = pfr_stiff_workload(n_chains=4, chain_len=4, P=30, t_end=1.5)
+    else:
+        model, net, cp, cmesh = cstr_ensemble_workload(n_cstr=1500, n_species=6, n_reactions=4, seed=7)
+    host = export_system(model, net, cp, cmesh)
+    M = 5
+    rng = np.random.default_rng(2)
+    ks = 10.0 ** rng.uniform(-0.7, 0.7, (M, host.tables.n_rxn))
+    qs = rng.uniform(0.3, 3.0, M)
+    mem = MemberParams(M, torch.as_tensor(ks, device='cuda'), torch.as_tensor(qs, device='cuda'), None)
+    y0 = torch.as_tensor(host.to_device_layout(host.c0.reshape(-1)), device='cuda')[None].repeat(M, 1).contiguous()
+    if kind == 'cstr':
+        y0 = y0 * torch.as_tensor(rng.uniform(0.2, 1.0, M), device='cuda')[:, None]
+    out = []
+    for how in ('off', 'on'):
+        dev = DeviceSystem(host, specialize=how)
+        assert dev.specialized == (how == 'on')
+        out.append(solve_bdf(dev, y0, (0.0, 1.5), rtol=1e-7, atol=1e-11, first_step=1e-5, t_eval=np.linspace(0, 1.5, 7), members=mem))
+    a, b = out
+    assert np.all(a.status == 1) and np.all(b.status == 1)
+    assert len(set((a.n_accepted + a.n_rejected).tolist())) > 1          # the members really take different numbers of attempts
+    assert np.array_equal(a.nfev, b.nfev) and np.array_equal(a.n_accepted, b.n_accepted)
+    assert torch.equal(a.y, b.y)
+
+
 def test_auto_mode_specialises_large_networks_only(monkeypatch):
     from openccm_b200.device import DeviceSystem
     monkeypatch.delenv('OCCM_B200_SPECIALIZE', raising=False)

@@ -1262,8 +1262,8 @@ static int occm_rk45_run_small(occm_rk45* rk, int64_t max_launch_steps, int32_t*
     if (!sys->use_small || !rk->prob.t_eval || ndof > OCCM_SMALL_MAX_NDOF || rk->M > 65535) return 1;
     const int nm = sys->dev.n_models, nnz = sys->nnz, pnnz = sys->pulse_nnz;
     const size_t smem = (size_t)sys->dev.tables_bytes + sizeof(double) * (11 * (size_t)ndof + nnz + nm + pnnz) +
-                        sizeof(int) * (2 * (size_t)(nm + 1) + nnz + pnnz) + 16;
-    if (smem > (size_t)sys->smem_per_block) return 1;
+                        sizeof(int) * (2 * (size_t)(nm + 1) + nnz + pnnz) + 4 * (size_t)ndof + 16;      // + element plan (2 x u16 per unknown)
+    if (smem + 8192 > (size_t)sys->smem_per_block) return 1;        // + the kernel's static shared memory (controller, boundary-value table)
     int block = (int)((ndof + 31) / 32 * 32);
     block = block < 64 ? 64 : block > 512 ? 512 : block;          // (1024 threads = 64 registers: the generic RHS spilled)
     const bool pfr = sys->dev.model == OCCM_MODEL_PFR;

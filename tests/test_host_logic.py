@@ -107,6 +107,11 @@ def test_ell_conversion_roundtrip():
     good = flags == 0
     np.testing.assert_allclose(ell[good], csr[good], rtol=1e-13, atol=1e-15)
     assert set(np.nonzero(flags)[0]) >= set(rows[~ok])          # rows with boundary entries are flagged
+    # columns are ordered nearest source first: the diagonal / numbering neighbours lead, the far (random permutation) sources of
+    # this network share the last column — what the staged-chunk lookups of the pipelined and specialised kernels rely on
+    dist = np.abs(src.astype(np.int64) - np.arange(host.n_models)[None, :])
+    assert np.all(np.diff(dist, axis=0) >= 0)
+    assert np.median(dist[0][good]) <= 1 and np.median(dist[-1][good]) > 20
 
 
 def test_generate_t_eval_forms(tmp_path):

@@ -132,6 +132,19 @@ def test_bdf_ensembles_with_members_finishing_at_different_attempts(kind):
     assert torch.equal(a.y, b.y)
 
 
+def test_ring_network_ell_width_two():
+    """A pure ring (diagonal + predecessor: ELL width 2, every source inside or next to the staged chunk)."""
+    from openccm_b200 import synthetic as syn
+    from openccm_b200.device import DeviceSystem
+    from openccm_b200.system_solvers.export import export_system
+    from openccm_b200.workloads import cstr_ensemble_workload
+    model, _, cp, cmesh = cstr_ensemble_workload(n_cstr=2600, n_species=8, n_reactions=5, seed=3)
+    net = syn.random_network(2600, n_io=16, seed=3, permutation_edges=False)
+    host = export_system(model, net, cp, cmesh)
+    plain, spec = _compare(host, M=4, t_end=1.0)
+    assert spec.ell_k == 2
+
+
 def test_auto_mode_specialises_large_networks_only(monkeypatch):
     from openccm_b200.device import DeviceSystem
     monkeypatch.delenv('OCCM_B200_SPECIALIZE', raising=False)
